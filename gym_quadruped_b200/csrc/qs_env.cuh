@@ -1,0 +1,1178 @@
+// qs_env.cuh -- per-environment physics of the fused step kernel, one environment per warp.
+//
+// Everything the reference obtains from `mujoco.mj_step` (gym_quadruped/quadruped_env.py:271) -- forward kinematics,
+// composite-rigid-body mass matrix, RNE bias forces, collision against the terrain, soft-constraint build, Newton
+// solve, implicit-damping Euler integration -- plus the env-side observation / termination pack
+// (quadruped_env.py:1146-1257) is expressed here as warp-cooperative phases:
+//   lanes <-> bodies (13), dofs (18), geoms, constraint units; cross-lane traffic through a per-warp shared-memory
+//   workspace (`WS`) and warp shuffles; `syncwarp()` between phases.
+// The tree sparsity (6-dof base + four independent 3-dof legs) is exploited throughout: M and the Newton Hessian are
+// stored as {base 6x6, four 3x6 couplings, four 3x3 leg blocks} and factored by a Schur complement on the leg blocks.
+//
+// This header is compiled by nvcc for sm_100a (qstep.cu) and, unchanged, by g++ against a 32-thread warp emulator
+// (tests/emu) so the exact kernel source can be checked against the fp64 oracle on a CPU-only host.
+#pragma once
+#include "qs_math.cuh"
+
+namespace qs {
+
+constexpr int NB = 14, NJ = 12, NQ = 19, NV = 18, NU = 12, MAXGEOM = 40;
+constexpr int NOBS_BASE = 227;
+constexpr int NFL = 12;   // friction-loss units (one per hinge)
+constexpr int NLIM = 12;  // joint-limit units (one slot per hinge; lower and upper cannot be active together)
+
+enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_BOX = 6, GEOM_MESH = 7 };
+
+template <typename real> struct alignas(16) Vert4 { real x, y, z, w; };
+
+// Robot + scene constants in the kernel's precision; built on the host from QsModel (qstep.cu: build_dmodel),
+// staged into shared memory once per CTA with one TMA bulk copy.
+template <typename real> struct alignas(16) DModel {
+  real timestep, gravity[3];
+  real impratio, tolerance, ls_tolerance, meaninertia;
+  real terrain_limits[4];
+  real floor_fri[4];
+  real imu_pos[4];
+  real imu_mat[12];
+  real mass_total, pad_r[3];
+  real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_iquat[NB][4], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
+  real jnt_pos[NJ][3], jnt_axis[NJ][3], jnt_range[NJ][2], jnt_K[NJ], jnt_B[NJ], jnt_solimp[NJ][5], jnt_margin[NJ];
+  real qpos0[20], key_qpos[20];
+  real dof_damping[NV], dof_armature[NV], dof_floss[NV], dof_iw[NV], dof_B[NV], dof_R[NV], dof_D[NV];
+  real act_clo[NU], act_chi[NU], act_flo[NU], act_fhi[NU];
+  real geom_pos[MAXGEOM][3], geom_mat[MAXGEOM][9], geom_size[MAXGEOM][3], geom_bcenter[MAXGEOM][3], geom_rbound[MAXGEOM],
+      geom_fri[MAXGEOM][3], geom_margin[MAXGEOM], geom_incmargin[MAXGEOM], geom_K[MAXGEOM], geom_B[MAXGEOM], geom_solimp[MAXGEOM][5];
+  int cone, iterations, ls_iterations, ngeom, nvert, terrain_type, nbox, has_imu;
+  int jnt_limited[NJ];
+  int geom_type[MAXGEOM], geom_body[MAXGEOM], geom_leg[MAXGEOM], geom_vertadr[MAXGEOM], geom_vertnum[MAXGEOM], geom_dim[MAXGEOM],
+      geom_prio[MAXGEOM];
+  int foot_geom[4];
+  int pad_i[4];
+};
+
+// Per-warp workspace (shared memory).
+template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
+  // state (internal frame: base xy relative to the per-env origin `org`)
+  real qpos[20], qvel[NV], ctrl[NU], warm[NV], applied[6];
+  real mu_floor, mu_feet;
+  double org[2];
+  // position stage
+  real xpos[NB][3], xquat[NB][4], xmat[NB][9], xaxis[NJ][3], xanchor[NJ][3], com[4];
+  real cdof[NV][6], cdofdot[NV][6], cinert[NB][10], crb[NB][10], cvel[NB][6], cfrc[NB][6];
+  real footpos[4][3];
+  // block mass matrix / Hessian: base-base, leg-base, leg-leg
+  real Mbb[6][6], Mlb[4][3][6], Mll[4][3][3];
+  real Hbb[6][6], Hlb[4][3][6], Hll[4][3][3];
+  real Ci[4][3][3], Y[4][3][6], SL[6][6], SLinv[8];
+  // dof vectors
+  real bias[NV], fsm[NV], asmooth[NV], qacc[NV], fcon[NV], grad[NV], search[NV], Mv[NV], Ma[NV], rhs[NV], sol[NV];
+  // constraint units: [0,12) friction loss, [12,24) joint limits, then contacts
+  real u_ar[NFL + NLIM], u_D[NFL + NLIM], u_R[NFL + NLIM], u_sign[NFL + NLIM], u_r[NFL + NLIM], u_v[NFL + NLIM], u_F[NFL + NLIM],
+      u_W[NFL + NLIM];
+  int ncon, overflow;
+  real c_dist[NCON], c_pos[NCON][3], c_frame[NCON][9], c_fri[NCON][3], c_mu[NCON], c_sign[NCON];
+  int c_geom[NCON], c_body[NCON], c_dim[NCON];
+  real c_D[NCON][MAXDIM], c_ar[NCON][MAXDIM], c_r[NCON][MAXDIM], c_v[NCON][MAXDIM], c_F[NCON][MAXDIM], c_W[NCON][MAXDIM][MAXDIM];
+  real Jc[NCON][MAXDIM][9], Tc[NCON][MAXDIM][9];
+  real sens[8];
+  real obs[NOBS_BASE + 5];
+};
+
+template <typename real, int NCON, int MAXDIM> struct Env {
+  using N = Num<real>;
+  using W = WS<real, NCON, MAXDIM>;
+  const DModel<real>& m;
+  W& w;
+  const Vert4<real>* vert;
+  const int lane;
+  int solver_iter;
+  bool solver_maxed;
+
+  QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_) : m(m_), w(w_), vert(v_), lane(lane_), solver_iter(0), solver_maxed(false) {}
+
+  // ------------------------------------------------------------------ position stage
+  // [MJ] mj_kinematics: lane j<12 walks the chain base -> ... -> body j+2 on its own, lane 12 owns the base.
+  QS_DEV void kinematics() {
+    real qb[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]};
+    quat_normalize(qb);
+    real Rb[9];
+    quat_to_mat(Rb, qb);
+    if (lane == 12) {
+      for (int i = 0; i < 3; i++) w.xpos[1][i] = w.qpos[i];
+      for (int i = 0; i < 4; i++) w.xquat[1][i] = qb[i];
+      for (int i = 0; i < 9; i++) w.xmat[1][i] = Rb[i];
+    } else if (lane == 13) {
+      for (int i = 0; i < 3; i++) w.xpos[0][i] = 0;
+      w.xquat[0][0] = 1; w.xquat[0][1] = w.xquat[0][2] = w.xquat[0][3] = 0;
+      for (int i = 0; i < 9; i++) w.xmat[0][i] = (i % 4 == 0) ? real(1) : real(0);
+    } else if (lane < 12) {
+      const int l = lane / 3, k = lane % 3;
+      real pos[3] = {w.qpos[0], w.qpos[1], w.qpos[2]}, quat[4] = {qb[0], qb[1], qb[2], qb[3]}, R[9], anchor[3] = {0, 0, 0}, axis[3] = {0, 0, 0};
+      for (int i = 0; i < 9; i++) R[i] = Rb[i];
+      for (int t = 0; t < 3; t++) {
+        if (t > k) break;
+        const int b = 2 + 3 * l + t, j = b - 2;
+        real tmp[3], q2[4];
+        mul_mv(tmp, R, m.body_pos[b]);
+        for (int i = 0; i < 3; i++) pos[i] += tmp[i];
+        quat_mul(q2, quat, m.body_quat[b]);
+        quat_to_mat(R, q2);
+        mul_mv(tmp, R, m.jnt_pos[j]);
+        for (int i = 0; i < 3; i++) anchor[i] = pos[i] + tmp[i];
+        mul_mv(axis, R, m.jnt_axis[j]);
+        real s, c;
+        N::sincos(real(0.5) * (w.qpos[7 + j] - m.qpos0[7 + j]), &s, &c);
+        real qloc[4] = {c, s * m.jnt_axis[j][0], s * m.jnt_axis[j][1], s * m.jnt_axis[j][2]};
+        quat_mul(quat, q2, qloc);
+        quat_to_mat(R, quat);
+        mul_mv(tmp, R, m.jnt_pos[j]);
+        for (int i = 0; i < 3; i++) pos[i] = anchor[i] - tmp[i];
+        quat_normalize(quat);
+        quat_to_mat(R, quat);
+      }
+      const int b = lane + 2;
+      for (int i = 0; i < 3; i++) { w.xpos[b][i] = pos[i]; w.xanchor[lane][i] = anchor[i]; w.xaxis[lane][i] = axis[i]; }
+      for (int i = 0; i < 4; i++) w.xquat[b][i] = quat[i];
+      for (int i = 0; i < 9; i++) w.xmat[b][i] = R[i];
+    }
+    syncwarp();
+  }
+
+  // [MJ] mj_comPos + mj_crb: body lanes 0..12 (body = lane+1); composite inertias by shuffles.
+  QS_DEV void com_inertia() {
+    const int b = lane + 1;
+    const bool isb = lane < 13;
+    const int bb = isb ? b : 1;
+    real xipos[3], Ri[9], qi[4], tmp[3];
+    mul_mv(tmp, w.xmat[bb], m.body_ipos[bb]);
+    for (int i = 0; i < 3; i++) xipos[i] = w.xpos[bb][i] + tmp[i];
+    quat_mul(qi, w.xquat[bb], m.body_iquat[bb]);
+    quat_to_mat(Ri, qi);
+    const real mass = isb ? m.body_mass[bb] : real(0);
+    real c[3];
+    for (int i = 0; i < 3; i++) c[i] = warp_sum(mass * xipos[i]) / m.mass_total;
+    real I[10];
+    {
+      const real* in = m.body_inertia[bb];
+      real o[3] = {xipos[0] - c[0], xipos[1] - c[1], xipos[2] - c[2]};
+      real A00 = Ri[0] * in[0] * Ri[0] + Ri[1] * in[1] * Ri[1] + Ri[2] * in[2] * Ri[2];
+      real A11 = Ri[3] * in[0] * Ri[3] + Ri[4] * in[1] * Ri[4] + Ri[5] * in[2] * Ri[5];
+      real A22 = Ri[6] * in[0] * Ri[6] + Ri[7] * in[1] * Ri[7] + Ri[8] * in[2] * Ri[8];
+      real A01 = Ri[0] * in[0] * Ri[3] + Ri[1] * in[1] * Ri[4] + Ri[2] * in[2] * Ri[5];
+      real A02 = Ri[0] * in[0] * Ri[6] + Ri[1] * in[1] * Ri[7] + Ri[2] * in[2] * Ri[8];
+      real A12 = Ri[3] * in[0] * Ri[6] + Ri[4] * in[1] * Ri[7] + Ri[5] * in[2] * Ri[8];
+      real oo = dot3(o, o);
+      I[0] = A00 + mass * (oo - o[0] * o[0]); I[1] = A11 + mass * (oo - o[1] * o[1]); I[2] = A22 + mass * (oo - o[2] * o[2]);
+      I[3] = A01 - mass * o[0] * o[1]; I[4] = A02 - mass * o[0] * o[2]; I[5] = A12 - mass * o[1] * o[2];
+      I[6] = mass * o[0]; I[7] = mass * o[1]; I[8] = mass * o[2]; I[9] = mass;
+      if (!isb) for (int i = 0; i < 10; i++) I[i] = 0;
+    }
+    // composite: base = sum of all; hip = self+thigh+calf; thigh = self+calf
+    const int k = (lane >= 1 && lane < 13) ? (lane - 1) % 3 : 3;
+    real cr[10];
+    for (int i = 0; i < 10; i++) {
+      real tot = warp_sum(I[i]);
+      real t1 = shfl(I[i], (lane + 1) & 31), t2 = shfl(I[i], (lane + 2) & 31);
+      cr[i] = (lane == 0) ? tot : I[i] + (k <= 1 ? t1 : real(0)) + (k == 0 ? t2 : real(0));
+    }
+    if (isb) {
+      for (int i = 0; i < 10; i++) { w.cinert[b][i] = I[i]; w.crb[b][i] = cr[i]; }
+    }
+    if (lane == 13) for (int i = 0; i < 3; i++) w.com[i] = c[i];
+    syncwarp();
+  }
+
+  // [MJ] cdof (mj_comPos) then M (mj_crb) in block form; dof lanes 0..17
+  QS_DEV void cdof_and_mass() {
+    if (lane < NV) {
+      const int d = lane;
+      real ax[3], off[3], cd[6];
+      if (d < 3) {
+        cd[0] = cd[1] = cd[2] = 0; cd[3] = d == 0; cd[4] = d == 1; cd[5] = d == 2;
+      } else {
+        if (d < 6) {
+          const int kk = d - 3;
+          ax[0] = w.xmat[1][kk]; ax[1] = w.xmat[1][3 + kk]; ax[2] = w.xmat[1][6 + kk];
+          for (int i = 0; i < 3; i++) off[i] = w.com[i] - w.xpos[1][i];
+        } else {
+          for (int i = 0; i < 3; i++) { ax[i] = w.xaxis[d - 6][i]; off[i] = w.com[i] - w.xanchor[d - 6][i]; }
+        }
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        cross3(cd + 3, ax, off);
+      }
+      for (int i = 0; i < 6; i++) w.cdof[d][i] = cd[i];
+    }
+    syncwarp();
+    if (lane < NV) {
+      const int d = lane, body = d < 6 ? 1 : d - 4;
+      real buf[6], cd[6];
+      for (int i = 0; i < 6; i++) cd[i] = w.cdof[d][i];
+      mul_inert_vec(buf, w.crb[body], cd);
+      if (d < 6) {
+        for (int j = 0; j <= d; j++) {
+          real v = 0;
+          for (int i = 0; i < 6; i++) v += w.cdof[j][i] * buf[i];
+          if (j == d) v += m.dof_armature[d];
+          w.Mbb[d][j] = v; w.Mbb[j][d] = v;
+        }
+      } else {
+        const int l = (d - 6) / 3, k = (d - 6) % 3;
+        for (int j = 0; j < 6; j++) {
+          real v = 0;
+          for (int i = 0; i < 6; i++) v += w.cdof[j][i] * buf[i];
+          w.Mlb[l][k][j] = v;
+        }
+        for (int k2 = 0; k2 <= k; k2++) {
+          real v = 0;
+          for (int i = 0; i < 6; i++) v += w.cdof[6 + 3 * l + k2][i] * buf[i];
+          if (k2 == k) v += m.dof_armature[d];
+          w.Mll[l][k][k2] = v; w.Mll[l][k2][k] = v;
+        }
+      }
+    }
+    syncwarp();
+  }
+
+  // ------------------------------------------------------------------ velocity / force stage
+  // [MJ] mj_comVel + mj_rne + passive + actuation; body lanes then dof lanes
+  QS_DEV void bias_and_smooth() {
+    const int b = lane + 1;
+    const bool isb = lane < 13;
+    const int l = (lane >= 1 && isb) ? (lane - 1) / 3 : 0, k = (lane >= 1 && isb) ? (lane - 1) % 3 : -1;
+    real cv[6] = {0, 0, 0, 0, 0, 0};
+    if (isb) {
+      // base: translations, then rotations (cdofdot of the rotations uses the velocity after the translations)
+      real vt[6] = {0, 0, 0, w.qvel[0], w.qvel[1], w.qvel[2]};
+      for (int i = 0; i < 6; i++) cv[i] = vt[i];
+      for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) cv[i] += w.cdof[d][i] * w.qvel[d];
+      if (lane == 0) {
+        for (int d = 0; d < 3; d++) for (int i = 0; i < 6; i++) w.cdofdot[d][i] = 0;
+        for (int d = 3; d < 6; d++) { real t[6]; cross_motion(t, vt, w.cdof[d]); for (int i = 0; i < 6; i++) w.cdofdot[d][i] = t[i]; }
+      } else {
+        for (int t = 0; t <= k; t++) {
+          const int d = 6 + 3 * l + t;
+          if (t == k) { real cdd[6]; cross_motion(cdd, cv, w.cdof[d]); for (int i = 0; i < 6; i++) w.cdofdot[d][i] = cdd[i]; }
+          for (int i = 0; i < 6; i++) cv[i] += w.cdof[d][i] * w.qvel[d];
+        }
+      }
+      for (int i = 0; i < 6; i++) w.cvel[b][i] = cv[i];
+    }
+    syncwarp();
+    real f[6] = {0, 0, 0, 0, 0, 0};
+    if (isb) {
+      real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+      for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d];
+      for (int t = 0; t <= k; t++) { const int d = 6 + 3 * l + t; for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d]; }
+      real I[10], t1[6], t2[6];
+      for (int i = 0; i < 10; i++) I[i] = w.cinert[b][i];
+      mul_inert_vec(t1, I, ca);
+      mul_inert_vec(t2, I, cv);
+      cross_force(f, cv, t2);
+      for (int i = 0; i < 6; i++) f[i] += t1[i];
+    }
+    const int kk = (lane >= 1 && isb) ? k : 3;
+    for (int i = 0; i < 6; i++) {
+      real tot = warp_sum(f[i]);
+      real t1 = shfl(f[i], (lane + 1) & 31), t2 = shfl(f[i], (lane + 2) & 31);
+      real s = (lane == 0) ? tot : f[i] + (kk <= 1 ? t1 : real(0)) + (kk == 0 ? t2 : real(0));
+      if (isb) w.cfrc[b][i] = s;
+    }
+    syncwarp();
+    if (lane < NV) {
+      const int d = lane, body = d < 6 ? 1 : d - 4;
+      real s = 0;
+      for (int i = 0; i < 6; i++) s += w.cdof[d][i] * w.cfrc[body][i];
+      w.bias[d] = s;
+      real act;
+      if (d < 6) act = w.applied[d];
+      else {
+        const int a = d - 6;
+        real c = w.ctrl[a];
+        c = N::min(N::max(c, m.act_clo[a]), m.act_chi[a]);
+        c = N::min(N::max(c, m.act_flo[a]), m.act_fhi[a]);
+        act = c;
+      }
+      w.fsm[d] = -m.dof_damping[d] * w.qvel[d] - s + act;
+    }
+    syncwarp();
+  }
+
+  // ------------------------------------------------------------------ structured linear algebra
+  // y = A x for a block matrix (bb, lb, ll); valid on dof lanes (< NV), x read from shared memory
+  QS_DEV real block_matvec(const real (*Abb)[6], const real (*Alb)[3][6], const real (*All)[3][3], const real* x) const {
+    real s = 0;
+    if (lane < 6) {
+      for (int j = 0; j < 6; j++) s += Abb[lane][j] * x[j];
+      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) s += Alb[l][k][lane] * x[6 + 3 * l + k];
+    } else if (lane < NV) {
+      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
+      for (int j = 0; j < 6; j++) s += Alb[l][k][j] * x[j];
+      for (int k2 = 0; k2 < 3; k2++) s += All[l][k][k2] * x[6 + 3 * l + k2];
+    }
+    return s;
+  }
+
+  // Factor the block matrix currently in (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
+  // Schur complement S = A - sum B_l^T Y_l -> Cholesky SL (lower) with reciprocal diagonal.
+  QS_DEV void factor_H() {
+    if (lane < 24) {
+      const int l = lane / 6, c = lane % 6;
+      // LDL^T of the 3x3 leg block, done redundantly by the 6 column lanes of a leg
+      const real c00 = w.Hll[l][0][0], c10 = w.Hll[l][1][0], c20 = w.Hll[l][2][0], c11 = w.Hll[l][1][1], c21 = w.Hll[l][2][1], c22 = w.Hll[l][2][2];
+      const real id0 = real(1) / c00, l10 = c10 * id0, l20 = c20 * id0;
+      const real d1 = c11 - l10 * c10, id1 = real(1) / d1;
+      const real l21 = (c21 - l20 * c10) * id1;
+      const real d2 = c22 - l20 * c20 - l21 * l21 * d1, id2 = real(1) / d2;
+      // solve C y = b for b = B_l[:, c]
+      real b0 = w.Hlb[l][0][c], b1 = w.Hlb[l][1][c], b2 = w.Hlb[l][2][c];
+      real z0 = b0, z1 = b1 - l10 * z0, z2 = b2 - l20 * z0 - l21 * z1;
+      real y2 = z2 * id2, y1 = z1 * id1 - l21 * y2, y0 = z0 * id0 - l10 * y1 - l20 * y2;
+      w.Y[l][0][c] = y0; w.Y[l][1][c] = y1; w.Y[l][2][c] = y2;
+      if (c < 3) {  // column c of the explicit inverse
+        real e0 = c == 0, e1 = c == 1, e2 = c == 2;
+        real u0 = e0, u1 = e1 - l10 * u0, u2 = e2 - l20 * u0 - l21 * u1;
+        real v2 = u2 * id2, v1 = u1 * id1 - l21 * v2, v0 = u0 * id0 - l10 * v1 - l20 * v2;
+        w.Ci[l][0][c] = v0; w.Ci[l][1][c] = v1; w.Ci[l][2][c] = v2;
+      }
+    }
+    syncwarp();
+    // Schur complement entries (lower triangle) spread over 21 lanes, parked in SL
+    if (lane < 21) {
+      int i = 0, j = lane;
+      while (j > i) { j -= i + 1; i++; }
+      real s = w.Hbb[i][j];
+      for (int l = 0; l < 4; l++)
+        for (int k = 0; k < 3; k++) s -= w.Hlb[l][k][i] * w.Y[l][k][j];
+      w.SL[i][j] = s;
+    }
+    syncwarp();
+    // every lane runs the 6x6 Cholesky redundantly in registers (6 dependent pivots, no further synchronisation)
+    real S[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) S[i][j] = w.SL[i][j];
+    syncwarp();
+    real inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      real s = S[j][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= S[j][k] * S[j][k];
+      s = N::max(s, N::minval);
+      real r = N::sqrt(s);
+      S[j][j] = r;
+      inv[j] = real(1) / r;
+#pragma unroll
+      for (int i = j + 1; i < 6; i++) {
+        real t = S[i][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) t -= S[i][k] * S[j][k];
+        S[i][j] = t * inv[j];
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) w.SL[i][j] = S[i][j];
+        w.SLinv[i] = inv[i];
+      }
+    }
+    syncwarp();
+  }
+
+  // solve (factored H) x = rhs; rhs in w.rhs, result in w.sol (both shared); all lanes participate
+  QS_DEV void solve_H() {
+    real t = 0;
+    if (lane < 6) {
+      t = w.rhs[lane];
+      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) t -= w.Y[l][k][lane] * w.rhs[6 + 3 * l + k];
+    }
+    real tb[6], xb[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) tb[i] = shfl(t, i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      real s = tb[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) s -= w.SL[i][k] * xb[k];
+      xb[i] = s * w.SLinv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+      real s = xb[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; k++) s -= w.SL[k][i] * xb[k];
+      xb[i] = s * w.SLinv[i];
+    }
+    if (lane < 6) w.sol[lane] = xb[lane];
+    else if (lane < NV) {
+      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
+      real s = 0;
+      for (int k2 = 0; k2 < 3; k2++) s += w.Ci[l][k][k2] * w.rhs[6 + 3 * l + k2];
+      for (int j = 0; j < 6; j++) s -= w.Y[l][k][j] * xb[j];
+      w.sol[lane] = s;
+    }
+    syncwarp();
+  }
+
+  QS_DEV void copy_M_to_H(real h_damp) {
+    for (int e = lane; e < 144; e += 32) {
+      if (e < 36) { const int i = e / 6, j = e % 6; w.Hbb[i][j] = w.Mbb[i][j] + ((i == j) ? h_damp * m.dof_damping[i] : real(0)); }
+      else if (e < 108) { const int q = e - 36; (&w.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
+      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? h_damp * m.dof_damping[6 + 3 * l + k] : real(0)); }
+    }
+    syncwarp();
+  }
+
+  // ------------------------------------------------------------------ collision with the terrain
+  QS_DEV void contact_friction(int g, bool world_is_floor, real* fri) const {
+    real gf[3] = {m.geom_fri[g][0], m.geom_fri[g][1], m.geom_fri[g][2]};
+    if (m.geom_leg[g] >= 0 && w.mu_feet >= 0) { gf[0] = w.mu_feet; gf[1] = real(0.005); gf[2] = 0; }   // quadruped_env.py:1290-1296
+    real wf[3] = {m.floor_fri[0], m.floor_fri[1], m.floor_fri[2]};
+    if (world_is_floor && w.mu_floor >= 0) { wf[0] = w.mu_floor; wf[1] = real(0.005); wf[2] = 0; }
+    const int prio = m.geom_prio[g];
+    for (int i = 0; i < 3; i++) {
+      real f = prio == 0 ? N::max(gf[i], wf[i]) : (prio > 0 ? gf[i] : wf[i]);
+      fri[i] = N::max(f, real(1e-5));  // [MJ] mjMINMU
+    }
+  }
+
+  // store one contact (called by a single lane); frame[0:3] = normal, yhint optional
+  QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, bool world_is_floor) {
+    w.c_dist[slot] = dist; w.c_geom[slot] = g; w.c_body[slot] = m.geom_body[g]; w.c_sign[slot] = sign; w.c_dim[slot] = m.geom_dim[g];
+    real f[9];
+    for (int i = 0; i < 3; i++) { w.c_pos[slot][i] = pos[i]; f[i] = normal[i]; f[3 + i] = yhint ? yhint[i] : real(0); }
+    // [MJ] mju_makeFrame
+    if (dot3(f + 3, f + 3) < real(0.25)) { f[3] = f[4] = f[5] = 0; if (f[1] < real(0.5) && f[1] > real(-0.5)) f[4] = 1; else f[5] = 1; }
+    real dd = dot3(f, f + 3);
+    for (int i = 0; i < 3; i++) f[3 + i] -= dd * f[i];
+    real inv = real(1) / N::sqrt(dot3(f + 3, f + 3));
+    for (int i = 0; i < 3; i++) f[3 + i] *= inv;
+    cross3(f + 6, f, f + 3);
+    for (int i = 0; i < 9; i++) w.c_frame[slot][i] = f[i];
+    real fri[3];
+    contact_friction(g, world_is_floor, fri);
+    for (int i = 0; i < 3; i++) w.c_fri[slot][i] = fri[i];
+  }
+
+  // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
+  QS_DEV void collide_floor() {
+    int ncon = 0;
+    // primitives: one lane per geom, up to 4 candidate contacts each
+    real cd[4], cp[4][3], yh[3] = {0, 0, 0};
+    int nc = 0;
+    const int g = lane;
+    if (g < m.ngeom && m.geom_type[g] != GEOM_MESH) {
+      const int b = m.geom_body[g];
+      real gx[3], tmp[3];
+      mul_mv(tmp, w.xmat[b], m.geom_pos[g]);
+      for (int i = 0; i < 3; i++) gx[i] = w.xpos[b][i] + tmp[i];
+      const real margin = m.geom_margin[g];
+      const real* sz = m.geom_size[g];
+      const int type = m.geom_type[g];
+      if (m.geom_leg[g] >= 0) for (int i = 0; i < 3; i++) w.footpos[m.geom_leg[g]][i] = gx[i];
+      if (type == GEOM_SPHERE) {
+        real dist = gx[2] - sz[0];
+        if (!(dist > margin)) { cd[0] = dist; cp[0][0] = gx[0]; cp[0][1] = gx[1]; cp[0][2] = gx[2] - (sz[0] + real(0.5) * dist); nc = 1; }
+      } else if (type == GEOM_CAPSULE) {
+        // capsule axis = third column of (R_body * R_geom)
+        real gz[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]}, axis[3];
+        mul_mv(axis, w.xmat[b], gz);
+        for (int i = 0; i < 3; i++) yh[i] = axis[i];
+        for (int s = 1; s >= -1; s -= 2) {
+          real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
+          real dist = p[2] - sz[0];
+          if (dist > margin) continue;
+          cd[nc] = dist; cp[nc][0] = p[0]; cp[nc][1] = p[1]; cp[nc][2] = p[2] - (sz[0] + real(0.5) * dist); nc++;
+        }
+      } else if (type == GEOM_BOX) {
+        real gm[9];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.xmat[b][3 * r] * m.geom_mat[g][c] + w.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
+        for (int i = 0; i < 8; i++) {
+          if (nc >= 4) break;
+          real v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, corner[3];
+          mul_mv(corner, gm, v);
+          real ldist = corner[2];
+          if (gx[2] + ldist > margin || ldist > 0) continue;
+          real dist = gx[2] + ldist;
+          cd[nc] = dist; cp[nc][0] = corner[0] + gx[0]; cp[nc][1] = corner[1] + gx[1]; cp[nc][2] = corner[2] + gx[2] - real(0.5) * dist; nc++;
+        }
+      }
+    }
+    const real nrm[3] = {0, 0, 1};
+    for (int r = 0; r < 4; r++) {
+      const bool has = nc > r;
+      const unsigned mask = ballot(has);
+      if (mask == 0) break;
+      const int slot = ncon + popc(mask & ((1u << lane) - 1u));
+      if (has) {
+        if (slot < NCON) store_contact(slot, g, real(1), cd[r], cp[r], nrm, (m.geom_type[g] == GEOM_CAPSULE) ? yh : nullptr, true);
+      }
+      ncon += popc(mask);
+    }
+    // convex meshes: the whole warp scans the hull vertices of each mesh that passes the bounding-sphere test
+    for (int gm_ = 0; gm_ < m.ngeom; gm_++) {
+      if (m.geom_type[gm_] != GEOM_MESH) continue;
+      const int b = m.geom_body[gm_];
+      const real margin = m.geom_margin[gm_];
+      const real* R = w.xmat[b];
+      const real cz = w.xpos[b][2] + R[6] * m.geom_bcenter[gm_][0] + R[7] * m.geom_bcenter[gm_][1] + R[8] * m.geom_bcenter[gm_][2];
+      if (cz - m.geom_rbound[gm_] > margin) continue;
+      const real dx = -R[6], dy = -R[7], dz = -R[8];  // R^T * (-normal)
+      const Vert4<real>* v = vert + m.geom_vertadr[gm_];
+      const int nv = m.geom_vertnum[gm_];
+      real best = -N::big;
+      int bi = 0x7fffffff;
+      for (int i = lane; i < nv; i += 32) {
+        const Vert4<real> p = v[i];
+        const real s = p.x * dx + p.y * dy + p.z * dz;
+        if (s > best) { best = s; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const real ob = shfl_xor(best, o);
+        const int oi = shfl_xor(bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const Vert4<real> p = v[bi];
+      const real pw[3] = {w.xpos[b][0] + R[0] * p.x + R[1] * p.y + R[2] * p.z, w.xpos[b][1] + R[3] * p.x + R[4] * p.y + R[5] * p.z,
+                          w.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};
+      const real dist = pw[2];
+      if (dist > margin) continue;
+      if (lane == 0 && ncon < NCON) {
+        const real pos[3] = {pw[0], pw[1], pw[2] - real(0.5) * dist};
+        store_contact(ncon, gm_, real(1), dist, pos, nrm, nullptr, true);
+      }
+      ncon++;
+    }
+    if (lane == 0) { w.overflow = ncon > NCON; w.ncon = ncon > NCON ? NCON : ncon; }
+    syncwarp();
+  }
+
+  // ------------------------------------------------------------------ constraint construction
+  // [MJ] getimpedance
+  QS_DEV real impedance(const real* si, real x) const {
+    real d0 = N::min(N::max(si[0], real(0.0001)), real(0.9999)), d1 = N::min(N::max(si[1], real(0.0001)), real(0.9999));
+    real width = N::max(si[2], real(0)), mid = N::min(N::max(si[3], real(0.0001)), real(0.9999)), power = N::max(si[4], real(1));
+    if (d0 == d1 || width <= N::minval) return real(0.5) * (d0 + d1);
+    x = N::abs(x) / width;
+    if (x >= 1) return d1;
+    if (x == 0) return d0;
+    real y;
+    if (power == real(1)) y = x;
+    else if (power == real(2)) y = (x <= mid) ? x * x / mid : real(1) - (real(1) - x) * (real(1) - x) / (real(1) - mid);
+    else if (x <= mid) y = N::pow(x, power) / N::pow(mid, power - 1);
+    else y = real(1) - N::pow(real(1) - x, power) / N::pow(real(1) - mid, power - 1);
+    return d0 + y * (d1 - d0);
+  }
+
+  // selected generalized-velocity-like vector entry for contact-Jacobian column col (0..5 base, 6..8 leg of the contact body)
+  QS_DEV static int col_dof(int body, int col) { return col < 6 ? col : 6 + 3 * ((body - 2) / 3) + (col - 6); }
+
+  // [MJ] mj_makeConstraint / mj_makeImpedance / mj_referenceConstraint in "unit" form:
+  //   friction-loss and limit units are scalar; a contact unit carries its contact-frame Jacobian Jc (dim x 9), the
+  //   contact-frame reference acceleration ar and regularisers D; pyramid rows are expanded on the fly as r0 +- mu r_j.
+  QS_DEV void make_constraints() {
+    const int ncon = w.ncon;
+    // contact Jacobians: item (c, col)
+    for (int it = lane; it < ncon * 9; it += 32) {
+      const int c = it / 9, col = it % 9, body = w.c_body[c], dim = w.c_dim[c];
+      bool on = col < 6;
+      if (!on && body >= 2) on = (col - 6) <= (body - 2) % 3;
+      real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
+      if (on) {
+        const int d = col_dof(body, col);
+        const real off[3] = {w.c_pos[c][0] - w.com[0], w.c_pos[c][1] - w.com[1], w.c_pos[c][2] - w.com[2]};
+        real cr[3];
+        cross3(cr, w.cdof[d], off);
+        for (int i = 0; i < 3; i++) { jp[i] = w.cdof[d][3 + i] + cr[i]; jr[i] = w.cdof[d][i]; }
+      }
+      const real sg = w.c_sign[c];
+      for (int k = 0; k < 3; k++) if (k < dim) w.Jc[c][k][col] = sg * dot3(&w.c_frame[c][3 * k], jp);
+      if (MAXDIM > 3) for (int k = 3; k < MAXDIM; k++) if (k < dim) w.Jc[c][k][col] = sg * dot3(&w.c_frame[c][3 * (k - 3)], jr);
+    }
+    // scalar units
+    if (lane < NFL) {
+      const int d = 6 + lane;
+      w.u_D[lane] = m.dof_floss[d] > 0 ? m.dof_D[d] : real(0);
+      w.u_R[lane] = m.dof_R[d];
+      w.u_sign[lane] = 1;
+      w.u_ar[lane] = -m.dof_B[d] * w.qvel[d];
+    } else if (lane < NFL + NLIM) {
+      const int j = lane - NFL;
+      real D = 0, R = 1, ar = 0, sign = 0;
+      if (m.jnt_limited[j]) {
+        const real value = w.qpos[7 + j], dlo = value - m.jnt_range[j][0], dhi = m.jnt_range[j][1] - value, margin = m.jnt_margin[j];
+        real pos = 0;
+        if (dlo < margin) { sign = 1; pos = dlo; } else if (dhi < margin) { sign = -1; pos = dhi; }
+        if (sign != 0) {
+          const real imp = impedance(m.jnt_solimp[j], pos - margin);
+          R = N::max(N::minval, (1 - imp) * m.dof_iw[6 + j] / imp);
+          D = 1 / R;
+          ar = -m.jnt_B[j] * (sign * w.qvel[6 + j]) - m.jnt_K[j] * imp * (pos - margin);
+        }
+      }
+      w.u_D[lane] = D; w.u_R[lane] = R; w.u_sign[lane] = sign; w.u_ar[lane] = ar;
+    }
+    syncwarp();
+    for (int c = lane; c < ncon; c += 32) {
+      const int g = w.c_geom[c], body = w.c_body[c], dim = w.c_dim[c];
+      real velc[MAXDIM];
+      for (int k = 0; k < MAXDIM; k++) {
+        real s = 0;
+        if (k < dim) for (int col = 0; col < 9; col++) { if (col >= 6 && body < 2) break; s += w.Jc[c][k][col] * w.qvel[col_dof(body, col)]; }
+        velc[k] = s;
+      }
+      const real x = w.c_dist[c] - m.geom_incmargin[g];
+      const bool active = w.c_dist[c] < m.geom_incmargin[g];
+      const real imp = impedance(m.geom_solimp[g], x);
+      const real tran = m.body_iw[body][0], rot = m.body_iw[body][1];
+      const real K = m.geom_K[g], B = m.geom_B[g];
+      const real f0 = w.c_fri[c][0];
+      for (int k = 0; k < MAXDIM; k++) { w.c_D[c][k] = 0; w.c_ar[c][k] = -B * velc[k]; }
+      w.c_ar[c][0] -= K * imp * x;
+      if (!active) { w.c_mu[c] = f0; continue; }
+      if (dim == 1) {
+        w.c_D[c][0] = 1 / N::max(N::minval, (1 - imp) * tran / imp);
+        w.c_mu[c] = f0;
+      } else if (m.cone == 0) {
+        const real Rn = N::max(N::minval, (1 - imp) * (tran + f0 * f0 * tran) / imp);
+        const real mur = f0 * N::sqrt(1 / N::max(N::minval, m.impratio));
+        const real Rpy = 2 * mur * mur * Rn;
+        for (int k = 0; k < MAXDIM; k++) w.c_D[c][k] = 1 / Rpy;
+        w.c_mu[c] = f0;  // pyramid rows use the friction coefficient itself
+      } else {
+        const real R0 = N::max(N::minval, (1 - imp) * tran / imp), R1 = R0 / N::max(N::minval, m.impratio);
+        w.c_mu[c] = f0 * N::sqrt(R1 / R0);
+        w.c_D[c][0] = 1 / R0; w.c_D[c][1] = 1 / R1; w.c_D[c][2] = 1 / R1;
+        if (MAXDIM > 3 && dim > 3) {
+          const real f1 = w.c_fri[c][1], f2 = w.c_fri[c][2];
+          w.c_D[c][3] = 1 / (R1 * f0 * f0 / (f1 * f1));
+          w.c_D[c][MAXDIM > 4 ? 4 : 0] = 1 / (R1 * f0 * f0 / (f2 * f2));
+          w.c_D[c][MAXDIM > 5 ? 5 : 0] = 1 / (R1 * f0 * f0 / (f2 * f2));
+        }
+        (void)rot;
+      }
+    }
+    syncwarp();
+  }
+
+  // friction coefficient that multiplies contact-frame dimension k (k>=1): slide, slide, spin, roll, roll
+  QS_DEV real fri_k(int c, int k) const { return k <= 2 ? w.c_fri[c][0] : (k == 3 ? w.c_fri[c][1] : w.c_fri[c][2]); }
+
+  // ------------------------------------------------------------------ per-unit cost model  [MJ] mj_constraintUpdate
+  // one-sided quadratic row
+  QS_DEV static void row_q(real x, real v, real D, real& cost, real& d1, real& d2) {
+    if (x < 0) { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+  }
+  // scalar unit u at residual x with direction v
+  QS_DEV void scalar_unit_eval(int u, real x, real v, real& cost, real& d1, real& d2) const {
+    const real D = w.u_D[u];
+    if (u < NFL) {
+      const real f = m.dof_floss[6 + u], rf = w.u_R[u] * f;
+      if (D == 0) return;
+      if (x <= -rf) { cost += -f * (real(0.5) * rf + x); d1 += -f * v; }
+      else if (x >= rf) { cost += -f * (real(0.5) * rf - x); d1 += f * v; }
+      else { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+    } else row_q(x, v, D, cost, d1, d2);
+  }
+  // contact unit c at contact-frame residual r[] with direction v[]
+  QS_DEV void contact_unit_eval(int c, const real* r, const real* v, real& cost, real& d1, real& d2) const {
+    const int dim = w.c_dim[c];
+    const real D0 = w.c_D[c][0];
+    if (D0 == 0) return;
+    if (dim == 1) { row_q(r[0], v[0], D0, cost, d1, d2); return; }
+    if (m.cone == 0) {
+      const real mu = w.c_mu[c];
+      for (int j = 1; j < 3; j++) {
+        row_q(r[0] + mu * r[j], v[0] + mu * v[j], D0, cost, d1, d2);
+        row_q(r[0] - mu * r[j], v[0] - mu * v[j], D0, cost, d1, d2);
+      }
+      return;
+    }
+    const real mu = w.c_mu[c];
+    const real Nn = r[0] * mu, N1 = v[0] * mu;
+    real T2 = 0, UV = 0, VV = 0;
+    for (int k = 1; k < MAXDIM; k++) if (k < dim) { const real f = fri_k(c, k), U = r[k] * f, V = v[k] * f; T2 += U * U; UV += U * V; VV += V * V; }
+    const real T = N::sqrt(T2);
+    if (Nn >= mu * T || (T <= 0 && Nn >= 0)) return;
+    if (mu * Nn + T <= 0 || (T <= 0 && Nn < 0)) {
+      for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; cost += real(0.5) * Dk * r[k] * r[k]; d1 += Dk * r[k] * v[k]; d2 += Dk * v[k] * v[k]; }
+      return;
+    }
+    const real Dm = D0 / N::max(N::minval, mu * mu * (1 + mu * mu)), NmT = Nn - mu * T;
+    const real T1 = UV / T, T2d = VV / T - UV * UV / (T * T * T), e1 = N1 - mu * T1;
+    cost += real(0.5) * Dm * NmT * NmT;
+    d1 += Dm * NmT * e1;
+    d2 += Dm * (e1 * e1 - NmT * mu * T2d);
+  }
+  // contact unit c: contact-frame force F and Hessian weight W at residual r; returns cost
+  QS_DEV real contact_unit_update(int c) {
+    const int dim = w.c_dim[c];
+    real* r = w.c_r[c];
+    real* F = w.c_F[c];
+    for (int a = 0; a < MAXDIM; a++) { F[a] = 0; for (int b = 0; b < MAXDIM; b++) w.c_W[c][a][b] = 0; }
+    const real D0 = w.c_D[c][0];
+    if (D0 == 0) return 0;
+    real cost = 0;
+    if (dim == 1) {
+      if (r[0] < 0) { F[0] = -D0 * r[0]; w.c_W[c][0][0] = D0; cost = real(0.5) * D0 * r[0] * r[0]; }
+      return cost;
+    }
+    if (m.cone == 0) {
+      const real mu = w.c_mu[c];
+      real fe[4], de[4];
+      for (int e = 0; e < 4; e++) {
+        const real x = r[0] + ((e & 1) ? -mu : mu) * r[1 + e / 2];
+        const bool act = x < 0;
+        fe[e] = act ? -D0 * x : real(0);
+        de[e] = act ? D0 : real(0);
+        if (act) cost += real(0.5) * D0 * x * x;
+      }
+      F[0] = fe[0] + fe[1] + fe[2] + fe[3]; F[1] = mu * (fe[0] - fe[1]); F[2] = mu * (fe[2] - fe[3]);
+      w.c_W[c][0][0] = de[0] + de[1] + de[2] + de[3];
+      w.c_W[c][0][1] = w.c_W[c][1][0] = mu * (de[0] - de[1]);
+      w.c_W[c][0][2] = w.c_W[c][2][0] = mu * (de[2] - de[3]);
+      w.c_W[c][1][1] = mu * mu * (de[0] + de[1]);
+      w.c_W[c][2][2] = mu * mu * (de[2] + de[3]);
+      return cost;
+    }
+    const real mu = w.c_mu[c];
+    real U[MAXDIM], fk[MAXDIM];
+    U[0] = r[0] * mu; fk[0] = mu;
+    real T2 = 0;
+    for (int k = 1; k < MAXDIM; k++) { fk[k] = (k < dim) ? fri_k(c, k) : real(0); U[k] = (k < dim) ? r[k] * fk[k] : real(0); T2 += U[k] * U[k]; }
+    const real Nn = U[0], T = N::sqrt(T2);
+    if (Nn >= mu * T || (T <= 0 && Nn >= 0)) return 0;
+    if (mu * Nn + T <= 0 || (T <= 0 && Nn < 0)) {
+      for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; F[k] = -Dk * r[k]; w.c_W[c][k][k] = Dk; cost += real(0.5) * Dk * r[k] * r[k]; }
+      return cost;
+    }
+    const real Dm = D0 / N::max(N::minval, mu * mu * (1 + mu * mu)), NmT = Nn - mu * T;
+    cost = real(0.5) * Dm * NmT * NmT;
+    F[0] = -Dm * NmT * mu;
+    real de[MAXDIM];
+    de[0] = mu;
+    for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? -mu * fk[k] * U[k] / T : real(0); if (k < dim) F[k] = -F[0] / T * U[k] * fk[k]; }
+    for (int a = 0; a < MAXDIM; a++)
+      for (int b = 0; b < MAXDIM; b++) {
+        if (a >= dim || b >= dim) continue;
+        real h = Dm * de[a] * de[b];
+        if (a > 0 && b > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? 1 / T : real(0)) - U[a] * U[b] / (T * T * T));
+        w.c_W[c][a][b] = h;
+      }
+    return cost;
+  }
+
+  // J x for every unit: out_u[] (scalar units) and out_c[][] (contacts). x in shared memory. minus_ar: subtract reference.
+  QS_DEV void units_Jx(const real* x, real* out_u, real (*out_c)[MAXDIM], bool minus_ar) {
+    if (lane < NFL + NLIM) {
+      const int d = 6 + (lane < NFL ? lane : lane - NFL);
+      out_u[lane] = w.u_sign[lane] * x[d] - (minus_ar ? w.u_ar[lane] : real(0));
+    }
+    const int ncon = w.ncon;
+    for (int it = lane; it < ncon * MAXDIM; it += 32) {
+      const int c = it / MAXDIM, k = it % MAXDIM, body = w.c_body[c];
+      real s = 0;
+      if (k < w.c_dim[c]) {
+        const int ncol = body < 2 ? 6 : 9;
+        for (int col = 0; col < ncol; col++) s += w.Jc[c][k][col] * x[col_dof(body, col)];
+        if (minus_ar) s -= w.c_ar[c][k];
+      }
+      out_c[c][k] = s;
+    }
+    syncwarp();
+  }
+
+  // states / forces / weights at the current residuals (w.u_r, w.c_r); returns the constraint cost (warp-uniform)
+  QS_DEV real units_update() {
+    real cost = 0;
+    if (lane < NFL + NLIM) {
+      const int u = lane;
+      const real x = w.u_r[u], D = w.u_D[u];
+      real F = 0, Wt = 0;
+      if (D != 0) {
+        if (u < NFL) {
+          const real f = m.dof_floss[6 + u], rf = w.u_R[u] * f;
+          if (x <= -rf) { F = f; cost = -f * (real(0.5) * rf + x); }
+          else if (x >= rf) { F = -f; cost = -f * (real(0.5) * rf - x); }
+          else { F = -D * x; Wt = D; cost = real(0.5) * D * x * x; }
+        } else if (x < 0) { F = -D * x; Wt = D; cost = real(0.5) * D * x * x; }
+      }
+      w.u_F[u] = F; w.u_W[u] = Wt;
+    }
+    const int ncon = w.ncon;
+    for (int c = lane; c < ncon; c += 32) cost += contact_unit_update(c);
+    cost = warp_sum(cost);
+    syncwarp();
+    return cost;
+  }
+
+  // qfrc_constraint = J^T F (into w.fcon) and grad = Ma - fsm - fcon; dof lanes
+  QS_DEV void constraint_force_and_grad() {
+    if (lane < NV) {
+      const int d = lane;
+      real s = 0;
+      const int ncon = w.ncon;
+      if (d >= 6) {
+        const int j = d - 6, l = j / 3, k = j % 3;
+        s += w.u_F[j] + w.u_sign[NFL + j] * w.u_F[NFL + j];
+        for (int c = 0; c < ncon; c++) {
+          const int body = w.c_body[c];
+          if (body < 2 || (body - 2) / 3 != l) continue;
+          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.c_F[c][a];
+        }
+      } else {
+        for (int c = 0; c < ncon; c++)
+          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][d] * w.c_F[c][a];
+      }
+      w.fcon[d] = s;
+      w.grad[d] = w.Ma[d] - w.fsm[d] - s;
+    }
+    syncwarp();
+  }
+
+  // H = M + J^T W J in block form
+  QS_DEV void build_hessian() {
+    const int ncon = w.ncon;
+    for (int it = lane; it < ncon * MAXDIM * 9; it += 32) {
+      const int c = it / (MAXDIM * 9), a = (it / 9) % MAXDIM, col = it % 9;
+      real s = 0;
+      const int dim = w.c_dim[c];
+      if (a < dim) for (int b = 0; b < MAXDIM; b++) if (b < dim) s += w.c_W[c][a][b] * w.Jc[c][b][col];
+      w.Tc[c][a][col] = s;
+    }
+    syncwarp();
+    for (int e = lane; e < 144; e += 32) {
+      if (e < 36) {
+        const int i = e / 6, j = e % 6;
+        real s = w.Mbb[i][j];
+        for (int c = 0; c < ncon; c++) for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][i] * w.Tc[c][a][j];
+        w.Hbb[i][j] = s;
+      } else if (e < 108) {
+        const int q = e - 36, l = q / 18, k = (q % 18) / 6, j = q % 6;
+        real s = w.Mlb[l][k][j];
+        for (int c = 0; c < ncon; c++) {
+          const int body = w.c_body[c];
+          if (body < 2 || (body - 2) / 3 != l) continue;
+          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.Tc[c][a][j];
+        }
+        w.Hlb[l][k][j] = s;
+      } else {
+        const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3;
+        real s = w.Mll[l][k][k2];
+        if (k == k2) { const int j = 3 * l + k; s += w.u_W[j] + w.u_W[NFL + j]; }
+        for (int c = 0; c < ncon; c++) {
+          const int body = w.c_body[c];
+          if (body < 2 || (body - 2) / 3 != l) continue;
+          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.Tc[c][a][6 + k2];
+        }
+        w.Hll[l][k][k2] = s;
+      }
+    }
+    syncwarp();
+  }
+
+  struct LsPoint { real cost, d1, d2; };
+
+  // cost and derivatives along qacc + alpha*search (warp-uniform result)
+  QS_DEV LsPoint ls_eval(real alpha, real qg0, real qg1, real qg2) {
+    real cost = 0, d1 = 0, d2 = 0;
+    if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane] + alpha * w.u_v[lane], w.u_v[lane], cost, d1, d2);
+    const int ncon = w.ncon;
+    for (int c = lane; c < ncon; c += 32) {
+      real r[MAXDIM];
+      for (int k = 0; k < MAXDIM; k++) r[k] = w.c_r[c][k] + alpha * w.c_v[c][k];
+      contact_unit_eval(c, r, w.c_v[c], cost, d1, d2);
+    }
+    LsPoint p;
+    p.cost = warp_sum(cost) + alpha * alpha * qg2 + alpha * qg1 + qg0;
+    p.d1 = warp_sum(d1) + 2 * alpha * qg2 + qg1;
+    p.d2 = warp_sum(d2) + 2 * qg2;
+    return p;
+  }
+
+  // [MJ] mj_fwdConstraint + mj_solNewton
+  QS_DEV void solve(int max_iter, real tol) {
+    // qacc_smooth = M^-1 qfrc_smooth
+    copy_M_to_H(real(0));
+    factor_H();
+    if (lane < NV) w.rhs[lane] = w.fsm[lane];
+    syncwarp();
+    solve_H();
+    if (lane < NV) w.asmooth[lane] = w.sol[lane];
+    syncwarp();
+    // warm start: cheaper of qacc_warmstart and qacc_smooth
+    real cost_w, cost_s;
+    {
+      units_Jx(w.warm, w.u_r, w.c_r, true);
+      real cc = units_update();
+      real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.warm);
+      real g = (lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.warm[lane] - w.asmooth[lane]) : real(0);
+      cost_w = cc + warp_sum(g);
+      units_Jx(w.asmooth, w.u_r, w.c_r, true);
+      cost_s = units_update();
+    }
+    const bool use_warm = cost_w < cost_s;
+    if (lane < NV) w.qacc[lane] = use_warm ? w.warm[lane] : w.asmooth[lane];
+    syncwarp();
+    if (use_warm) units_Jx(w.qacc, w.u_r, w.c_r, true);
+    real ccost = use_warm ? units_update() : cost_s;
+    real gauss;
+    {
+      real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+      if (lane < NV) w.Ma[lane] = ma;
+      gauss = warp_sum((lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
+    }
+    real cost = gauss + ccost;
+    syncwarp();
+    constraint_force_and_grad();
+    const real scale = real(1) / (m.meaninertia * NV);
+    int iter = 0;
+    solver_maxed = false;
+    while (true) {
+      if (iter >= max_iter) { solver_maxed = true; break; }
+      // Newton direction
+      build_hessian();
+      factor_H();
+      if (lane < NV) w.rhs[lane] = w.grad[lane];
+      syncwarp();
+      solve_H();
+      if (lane < NV) w.search[lane] = -w.sol[lane];
+      syncwarp();
+      // ---- exact line search, [MJ] PrimalSearch
+      real sn = (lane < NV) ? w.search[lane] * w.search[lane] : real(0);
+      const real snorm = N::sqrt(warp_sum(sn));
+      if (snorm < N::minval) break;
+      const real gtol = tol * m.ls_tolerance * snorm / scale;
+      real mv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.search);
+      if (lane < NV) w.Mv[lane] = mv;
+      units_Jx(w.search, w.u_v, w.c_v, false);
+      const real qg0 = gauss;
+      const real qg1 = warp_sum((lane < NV) ? w.search[lane] * (w.Ma[lane] - w.fsm[lane]) : real(0));
+      const real qg2 = warp_sum((lane < NV) ? real(0.5) * w.search[lane] * mv : real(0));
+      real alpha = 0;
+      {
+        LsPoint p0 = ls_eval(0, qg0, qg1, qg2);
+        real a1 = -p0.d1 / p0.d2;
+        LsPoint p1 = ls_eval(a1, qg0, qg1, qg2);
+        if (p0.cost < p1.cost) { p1 = p0; a1 = 0; }
+        bool done = N::abs(p1.d1) < gtol;
+        alpha = a1;
+        if (!done) {
+          const int dir = p1.d1 < 0 ? 1 : -1;
+          int it = 0;
+          LsPoint p2 = p1;
+          real a2 = a1;
+          while (p1.d1 * dir <= -gtol && it < m.ls_iterations) {
+            p2 = p1; a2 = a1;
+            a1 = a1 - p1.d1 / p1.d2;
+            p1 = ls_eval(a1, qg0, qg1, qg2);
+            it++;
+            if (N::abs(p1.d1) < gtol) { done = true; break; }
+          }
+          alpha = a1;
+          if (!done && it < m.ls_iterations) {
+            real lo = a2, hi = a1;
+            LsPoint plo = p2, phi = p1;
+            bool found = false;
+            while (it < m.ls_iterations && !found) {
+              const real cand[3] = {lo - plo.d1 / plo.d2, hi - phi.d1 / phi.d2, real(0.5) * (lo + hi)};
+              bool moved = false;
+              for (int q = 0; q < 3; q++) {
+                const real a = cand[q];
+                if (!((a > lo && a < hi) || (a < lo && a > hi))) continue;
+                LsPoint p = ls_eval(a, qg0, qg1, qg2);
+                it++;
+                if (N::abs(p.d1) < gtol) { alpha = a; found = true; break; }
+                if ((p.d1 < 0) == (plo.d1 < 0)) { lo = a; plo = p; } else { hi = a; phi = p; }
+                moved = true;
+              }
+              if (!moved) break;
+            }
+            if (!found) alpha = plo.cost < phi.cost ? lo : hi;
+          }
+        }
+      }
+      if (alpha == 0) break;
+      // ---- move
+      if (lane < NV) { w.qacc[lane] += alpha * w.search[lane]; w.Ma[lane] += alpha * w.Mv[lane]; }
+      if (lane < NFL + NLIM) w.u_r[lane] += alpha * w.u_v[lane];
+      for (int it2 = lane; it2 < w.ncon * MAXDIM; it2 += 32) (&w.c_r[0][0])[it2] += alpha * (&w.c_v[0][0])[it2];
+      syncwarp();
+      const real oldcost = cost;
+      ccost = units_update();
+      gauss = warp_sum((lane < NV) ? real(0.5) * (w.Ma[lane] - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
+      cost = gauss + ccost;
+      constraint_force_and_grad();
+      iter++;
+      const real gn = N::sqrt(warp_sum((lane < NV) ? w.grad[lane] * w.grad[lane] : real(0)));
+      if (scale * (oldcost - cost) < tol || scale * gn < tol) break;
+    }
+    solver_iter = iter;
+  }
+
+  // accelerometer / gyro at the IMU site. [MJ] mj_rnePostConstraint + mj_objectAcceleration
+  QS_DEV void sensors() {
+    if (lane == 0) {
+      real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+      for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d] + w.cdof[d][i] * w.qacc[d];
+      const real* cv = w.cvel[1];
+      real spos[3], tmp[3], R[9];
+      mul_mv(tmp, w.xmat[1], m.imu_pos);
+      for (int i = 0; i < 3; i++) spos[i] = w.xpos[1][i] + tmp[i] - w.com[i];
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = w.xmat[1][3 * r] * m.imu_mat[c] + w.xmat[1][3 * r + 1] * m.imu_mat[3 + c] + w.xmat[1][3 * r + 2] * m.imu_mat[6 + c];
+      real vl[3], al[3], c1[3];
+      cross3(c1, cv, spos);
+      for (int i = 0; i < 3; i++) vl[i] = cv[3 + i] + c1[i];
+      cross3(c1, ca, spos);
+      for (int i = 0; i < 3; i++) al[i] = ca[3 + i] + c1[i];
+      cross3(c1, cv, vl);
+      for (int i = 0; i < 3; i++) al[i] += c1[i];
+      mul_mtv(w.sens, R, al);
+      mul_mtv(w.sens + 3, R, cv);
+    }
+    syncwarp();
+  }
+
+  // forward dynamics up to the solver acceleration ("mj_forward")
+  QS_DEV void forward(int max_iter, real tol) {
+    kinematics();
+    com_inertia();
+    cdof_and_mass();
+    collide_floor();
+    bias_and_smooth();
+    make_constraints();
+    solve(max_iter, tol);
+    if (m.has_imu) sensors();
+  }
+
+  // [MJ] mj_Euler with implicit joint damping. org = internal-frame origin for the fp64 base position.
+  QS_DEV void integrate(double* base64) {
+    const real h = m.timestep;
+    copy_M_to_H(h);
+    factor_H();
+    if (lane < NV) w.rhs[lane] = w.fsm[lane] + w.fcon[lane];
+    syncwarp();
+    solve_H();
+    if (lane < NV) w.qvel[lane] += h * w.sol[lane];
+    syncwarp();
+    if (lane < 3) {
+      const double p = (lane < 2 ? w.org[lane] : 0.0) + double(w.qpos[lane]) + double(h) * double(w.qvel[lane]);
+      base64[lane] = p;
+      w.qpos[lane] = real(p - (lane < 2 ? w.org[lane] : 0.0));
+    } else if (lane == 3) {
+      const real wx = w.qvel[3], wy = w.qvel[4], wz = w.qvel[5];
+      const real nrm = N::sqrt(wx * wx + wy * wy + wz * wz), ang = h * nrm;
+      real q[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]};
+      if (ang > 0) {
+        real s, c;
+        N::sincos(real(0.5) * ang, &s, &c);
+        const real qr[4] = {c, s * wx / nrm, s * wy / nrm, s * wz / nrm};
+        real q2[4];
+        quat_mul(q2, q, qr);
+        for (int i = 0; i < 4; i++) q[i] = q2[i];
+      }
+      quat_normalize(q);
+      for (int i = 0; i < 4; i++) w.qpos[3 + i] = q[i];
+    } else if (lane >= 7 && lane < NQ) {
+      w.qpos[lane] += h * w.qvel[lane - 1];
+    }
+    syncwarp();
+  }
+
+  // ------------------------------------------------------------------ env side: flags + ALL_OBS (quadruped_env.py:1146-1257)
+  struct Flags { unsigned contact_mask; unsigned invalid_mask; bool out_of_bounds; };
+  QS_DEV Flags flags() const {
+    unsigned cm = 0, im = 0;
+    for (int c = lane; c < w.ncon; c += 32) {
+      const int b = w.c_body[c];
+      if (b >= 2 && (b - 2) % 3 == 2) cm |= 1u << ((b - 2) / 3); else im |= 1u << b;
+    }
+    for (int o = 16; o > 0; o >>= 1) { cm |= shfl_xor(cm, o); im |= shfl_xor(im, o); }
+    Flags f;
+    f.contact_mask = cm; f.invalid_mask = im;
+    const double x = w.org[0] + double(w.qpos[0]), y = w.org[1] + double(w.qpos[1]);
+    f.out_of_bounds = x > double(m.terrain_limits[0]) || x < double(m.terrain_limits[1]) || y > double(m.terrain_limits[2]) || y < double(m.terrain_limits[3]);
+    return f;
+  }
+
+  // Packs the 227 ALL_OBS scalars into w.obs (layout: SURVEY.md section 8a). Mixed time levels as in the reference
+  // (App. B.1): qpos/qvel are post-integration, foot positions / Jacobians / contacts / qacc / M are from the forward pass.
+  QS_DEV void pack_obs(const real* command, unsigned contact_mask) {
+    real q[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]}, R[9];
+    quat_normalize(q);
+    quat_to_mat(R, q);
+    const real yaw = N::atan2(R[3], R[0]);
+    real sy, cy;
+    N::sincos(yaw, &sy, &cy);
+    const real vref[3] = {cy * command[0] - sy * command[1], sy * command[0] + cy * command[1], command[2]};
+    const real wref[3] = {0, 0, command[3]};
+    const real* v = w.qvel;
+    const real* wb = w.qvel + 3;
+    real* o = w.obs;
+    const real ox = real(w.org[0]), oy = real(w.org[1]);
+    if (lane == 0) {
+      real t[3], t2[3];
+      o[0] = real(w.org[0] + double(w.qpos[0])); o[1] = real(w.org[1] + double(w.qpos[1])); o[2] = w.qpos[2];
+      for (int i = 0; i < 3; i++) { o[3 + i] = v[i]; o[6 + i] = vref[i] - v[i]; o[9 + i] = w.qacc[i]; }
+      mul_mv(t, R, wb);
+      for (int i = 0; i < 3; i++) { o[12 + i] = t[i]; o[15 + i] = wref[i] - t[i]; }
+      o[18] = N::atan2(R[7], R[8]); o[19] = -N::asin(N::max(real(-1), N::min(real(1), R[6]))); o[20] = yaw;
+      for (int i = 0; i < 4; i++) o[21 + i] = w.qpos[3 + i];
+      for (int i = 0; i < 9; i++) o[25 + i] = R[i];
+      o[34] = -R[6]; o[35] = -R[7]; o[36] = -R[8];
+      mul_mtv(t, R, v);
+      mul_mtv(t2, R, vref);
+      for (int i = 0; i < 3; i++) { o[37 + i] = t[i]; o[40 + i] = t2[i] - t[i]; }
+      mul_mtv(t, R, w.qacc);
+      for (int i = 0; i < 3; i++) { o[43 + i] = t[i]; o[46 + i] = wb[i]; }
+      mul_mtv(t, R, wref);
+      for (int i = 0; i < 3; i++) o[49 + i] = t[i] - wb[i];
+    }
+    if (lane < NQ) o[52 + lane] = (lane < 2) ? real(w.org[lane] + double(w.qpos[lane])) : w.qpos[lane];
+    if (lane < NV) o[71 + lane] = w.qvel[lane];
+    if (lane < NU) { o[89 + lane] = w.ctrl[lane]; o[101 + lane] = w.qpos[7 + lane]; o[113 + lane] = w.qvel[6 + lane]; }
+    {
+      const real mvv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qvel), maa = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+      const real ke = warp_sum((lane < NV) ? real(0.5) * w.qvel[lane] * mvv : real(0));
+      const real wk = warp_sum((lane < NV) ? maa * w.qvel[lane] : real(0));
+      if (lane == 0) { o[125] = ke; o[126] = wk; }
+    }
+    if (lane < 4) {
+      const int l = lane;
+      real cv6[6] = {0, 0, 0, 0, 0, 0};
+      for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d];
+      for (int k = 0; k < 3; k++) { const int d = 6 + 3 * l + k; for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d]; }
+      const real* p = w.footpos[l];
+      const real off[3] = {p[0] - w.com[0], p[1] - w.com[1], p[2] - w.com[2]};
+      real cr[3], fv[3], fr[3], t[3];
+      cross3(cr, cv6, off);
+      for (int i = 0; i < 3; i++) fv[i] = cv6[3 + i] + cr[i];
+      const real rb[3] = {p[0] - w.qpos[0], p[1] - w.qpos[1], p[2] - w.qpos[2]};
+      cross3(cr, wb, rb);
+      for (int i = 0; i < 3; i++) fr[i] = fv[i] - v[i] - cr[i];
+      o[127 + 3 * l] = p[0] + ox; o[128 + 3 * l] = p[1] + oy; o[129 + 3 * l] = p[2];
+      mul_mtv(t, R, rb);
+      for (int i = 0; i < 3; i++) { o[139 + 3 * l + i] = t[i]; o[151 + 3 * l + i] = fv[i]; o[163 + 3 * l + i] = fr[i]; }
+      mul_mtv(t, R, fv);
+      for (int i = 0; i < 3; i++) o[175 + 3 * l + i] = t[i];
+      mul_mtv(t, R, fr);
+      for (int i = 0; i < 3; i++) o[187 + 3 * l + i] = t[i];
+      o[199 + l] = (contact_mask >> l) & 1u ? real(1) : real(0);
+      real cf[3] = {0, 0, 0};
+      for (int c = 0; c < w.ncon; c++) {
+        if (w.c_body[c] != 4 + 3 * l) continue;
+        const int dim = w.c_dim[c];
+        const real F0 = w.c_F[c][0], F1 = dim > 1 ? w.c_F[c][1] : real(0), F2 = dim > 1 ? w.c_F[c][2] : real(0);
+        for (int i = 0; i < 3; i++) cf[i] += w.c_frame[c][i] * F0 + w.c_frame[c][3 + i] * F1 + w.c_frame[c][6 + i] * F2;
+      }
+      mul_mtv(t, R, cf);
+      for (int i = 0; i < 3; i++) { o[203 + 3 * l + i] = cf[i]; o[215 + 3 * l + i] = t[i]; }
+    }
+    syncwarp();
+  }
+};
+
+}  // namespace qs

@@ -1,0 +1,104 @@
+// emu_main.cpp -- TEST INFRASTRUCTURE. Host build of the fused-step device code (see warp_emu.h).
+// Exposes one C entry point that advances a single environment by one step with 32 host threads acting as the warp.
+#include "warp_emu.h"
+
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "../../gym_quadruped_b200/csrc/qs_host_model.h"
+
+namespace {
+template <typename real, int MAXDIM>
+int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, const double* ctrl, const double* envp, double* obs,
+             double* misc, int max_iter, double tol, int mode) {
+  using namespace qs;
+  constexpr int NCON = 16;
+  auto dm = std::make_unique<DModel<real>>();
+  std::vector<Vert4<real>> verts;
+  std::string err = build_dmodel<real>(*model, *dm, verts);
+  if (!err.empty()) return -1;
+  auto ws = std::make_unique<WS<real, NCON, MAXDIM>>();
+  std::memset(ws.get(), 0, sizeof(*ws));
+  const bool flat = model->terrain_type == QS_TERRAIN_FLAT;
+  ws->org[0] = flat ? std::nearbyint(qpos[0]) : 0.0;
+  ws->org[1] = flat ? std::nearbyint(qpos[1]) : 0.0;
+  for (int i = 0; i < 19; i++) ws->qpos[i] = real(i < 2 ? qpos[i] - ws->org[i] : qpos[i]);
+  for (int i = 0; i < 18; i++) { ws->qvel[i] = real(qvel[i]); ws->warm[i] = real(warm[i]); }
+  for (int i = 0; i < 12; i++) ws->ctrl[i] = real(ctrl[i]);
+  ws->mu_floor = real(envp[0]); ws->mu_feet = real(envp[1]);
+  real command[4];
+  for (int i = 0; i < 4; i++) command[i] = real(envp[2 + i]);
+  for (int i = 0; i < 6; i++) ws->applied[i] = real(envp[6 + i]);
+  double base64[3] = {qpos[0], qpos[1], qpos[2]};
+  WarpCtx ctx;
+  int iters = 0, maxed = 0;
+  unsigned cmask = 0, imask = 0;
+  bool oob = false;
+  std::vector<std::thread> th;
+  for (int lane = 0; lane < 32; lane++) {
+    th.emplace_back([&, lane]() {
+      g_ctx = &ctx;
+      g_lane = lane;
+      Env<real, NCON, MAXDIM> e(*dm, *ws, verts.data(), lane);
+      e.forward(max_iter, real(tol));
+      auto f = e.flags();
+      if (mode == 1) {
+        e.integrate(base64);
+        f.out_of_bounds = e.flags().out_of_bounds;
+        e.pack_obs(command, f.contact_mask);
+      }
+      if (lane == 0) { iters = e.solver_iter; maxed = e.solver_maxed; cmask = f.contact_mask; imask = f.invalid_mask; oob = f.out_of_bounds; }
+    });
+  }
+  for (auto& t : th) t.join();
+  // results
+  for (int i = 0; i < 19; i++) qpos[i] = double(ws->qpos[i]) + (i < 2 ? ws->org[i] : 0.0);
+  if (mode == 1) for (int i = 0; i < 3; i++) qpos[i] = base64[i];
+  for (int i = 0; i < 18; i++) { qvel[i] = double(ws->qvel[i]); warm[i] = double(ws->qacc[i]); }
+  if (obs) for (int i = 0; i < 227; i++) obs[i] = double(ws->obs[i]);
+  if (misc) {
+    int k = 0;
+    misc[k++] = iters; misc[k++] = maxed; misc[k++] = cmask; misc[k++] = imask; misc[k++] = oob; misc[k++] = ws->ncon; misc[k++] = ws->overflow;
+    k = 8;
+    for (int i = 0; i < 18; i++) misc[k++] = double(ws->qacc[i]);      // 8
+    for (int i = 0; i < 18; i++) misc[k++] = double(ws->bias[i]);      // 26
+    for (int i = 0; i < 18; i++) misc[k++] = double(ws->fsm[i]);       // 44
+    for (int i = 0; i < 18; i++) misc[k++] = double(ws->asmooth[i]);   // 62
+    for (int i = 0; i < 18; i++) misc[k++] = double(ws->fcon[i]);      // 80
+    // dense M, 98
+    for (int i = 0; i < 18; i++)
+      for (int j = 0; j < 18; j++) {
+        double v = 0;
+        if (i < 6 && j < 6) v = ws->Mbb[i][j];
+        else if (i >= 6 && j < 6) v = ws->Mlb[(i - 6) / 3][(i - 6) % 3][j];
+        else if (i < 6 && j >= 6) v = ws->Mlb[(j - 6) / 3][(j - 6) % 3][i];
+        else if ((i - 6) / 3 == (j - 6) / 3) v = ws->Mll[(i - 6) / 3][(i - 6) % 3][(j - 6) % 3];
+        misc[k++] = v;
+      }
+    // contacts, 422: per contact dist,pos3,frame9,F3,geom,body,mu,dim
+    for (int c = 0; c < ws->ncon; c++) {
+      misc[k++] = ws->c_dist[c];
+      misc[k++] = ws->c_pos[c][0] + ws->org[0]; misc[k++] = ws->c_pos[c][1] + ws->org[1]; misc[k++] = ws->c_pos[c][2];
+      for (int i = 0; i < 9; i++) misc[k++] = ws->c_frame[c][i];
+      for (int i = 0; i < 3; i++) misc[k++] = (i < ws->c_dim[c]) ? double(ws->c_F[c][i]) : 0.0;
+      misc[k++] = ws->c_geom[c]; misc[k++] = ws->c_body[c]; misc[k++] = ws->c_fri[c][0]; misc[k++] = ws->c_dim[c];
+    }
+    // sensors at 422 + 20*16 = 742
+    k = 742;
+    for (int i = 0; i < 6; i++) misc[k++] = double(ws->sens[i]);
+  }
+  return 0;
+}
+}  // namespace
+
+// mode 0: forward only; mode 1: forward + integrate + obs. precision 0: fp32, 1: fp64.
+// envp = {mu_floor, mu_feet, command[4], applied[6]}; misc has room for 1024 doubles.
+extern "C" int emu_step(const QsModel* model, int precision, double* qpos, double* qvel, double* warm, const double* ctrl,
+                        const double* envp, double* obs, double* misc, int max_iter, double tol, int mode) {
+  const int md = qs::model_max_dim(*model);
+  if (precision == 0) return md > 3 ? run_step<float, 6>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
+                                    : run_step<float, 3>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode);
+  return md > 3 ? run_step<double, 6>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
+                : run_step<double, 3>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode);
+}
