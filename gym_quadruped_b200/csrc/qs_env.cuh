@@ -56,6 +56,7 @@ template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
   real qpos[20], qvel[NV], ctrl[NU], warm[NV], applied[6];
   real mu_floor, mu_feet;
   double org[2];
+  double tmpd[2];
   // position stage
   real xpos[NB][3], xquat[NB][4], xmat[NB][9], xaxis[NJ][3], xanchor[NJ][3], com[4];
   real cdof[NV][6], cdofdot[NV][6], cinert[NB][10], crb[NB][10], cvel[NB][6], cfrc[NB][6];

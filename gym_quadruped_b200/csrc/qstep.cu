@@ -1,0 +1,587 @@
+// qstep.cu -- libqstep: the C-ABI of include/qstep.h on top of one fused sm_100a kernel family.
+//
+//   env_kernel<real, NCON, MAXDIM, MODE>: one environment per warp, WARPS warps per CTA.
+//     MODE_STEP    ctrl -> forward dynamics -> Euler -> ALL_OBS / termination      (quadruped_env.py:251-307)
+//     MODE_RESET   masked reset: keyframe + noise, lift loop, one step, command / friction resampling (:309-406)
+//     MODE_FORWARD forward pass only, dumping accessor tables (mj_forward / mj_fullM / mj_jac users, :543-929)
+//   The robot/scene constants (DModel, ~10 KB) are staged global->shared once per CTA by a single TMA bulk copy
+//   (cp.async.bulk + mbarrier) that overlaps with the per-warp state loads; hull vertices stay in global/L2.
+//
+// No torch types cross this boundary; PyTorch only owns the device buffers whose pointers arrive in QsBuffers.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "qs_host_model.h"
+
+namespace {
+using namespace qs;
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
+constexpr int NCON_MAX = 16;
+constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6;  // 992
+constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_JACP = 360, AUX_OFF_FEETPOS = 576, AUX_OFF_COM = 588,
+              AUX_OFF_CONTACTS = 591, AUX_OFF_SMOOTH = 591 + QS_CONTACT_STRIDE * NCON_MAX, AUX_OFF_CONSTRAINT = AUX_OFF_SMOOTH + 18,
+              AUX_OFF_XPOS = AUX_OFF_CONSTRAINT + 18, AUX_OFF_IMU = AUX_OFF_XPOS + 39;
+
+struct KParams {
+  const void* dm;      // DModel<real>
+  const void* vert;    // Vert4<real>[nvert]
+  int num_envs, obs_dim, use_imu, max_iter, env_id_offset;
+  float tol;
+  unsigned seed_lo, seed_hi;
+  float imu_an, imu_gn, imu_abr, imu_gbr;
+  QsBuffers b;
+  unsigned* episode;  // per-env reset counter (keys the reset RNG)
+  unsigned* tick;     // per-env step counter  (keys the IMU noise RNG)
+  const float* ctrl;
+  float* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  // reset
+  const uint8_t* mask;
+  const float* in_qpos;
+  const float* in_qvel;
+  QsResetOptions ro;
+  // forward
+  float* aux;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// one TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar) {
+  const uint32_t bar = smem_u32(mbar), dst = smem_u32(dst_smem);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src_gmem), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  const uint32_t bar = smem_u32(mbar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+template <typename real> __device__ __forceinline__ void euler_to_quat(real roll, real pitch, real yaw, real* q) {
+  real sr, cr, sp, cp, sy, cy;
+  Num<real>::sincos(roll * real(0.5), &sr, &cr);
+  Num<real>::sincos(pitch * real(0.5), &sp, &cp);
+  Num<real>::sincos(yaw * real(0.5), &sy, &cy);
+  q[0] = cr * cp * cy + sr * sp * sy; q[1] = sr * cp * cy - cr * sp * sy; q[2] = cr * sp * cy + sr * cp * sy; q[3] = cr * cp * sy - sr * sp * cy;
+}
+
+template <typename real, int NCON, int MAXDIM, int MODE>
+__global__ void __launch_bounds__(256) env_kernel(const KParams p) {
+  using W = WS<real, NCON, MAXDIM>;
+  using DM = DModel<real>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr size_t DM_BYTES = (sizeof(DM) + 127) & ~size_t(127);
+  DM* dm = reinterpret_cast<DM*>(smem);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + DM_BYTES);
+  W* wsbase = reinterpret_cast<W*>(smem + DM_BYTES + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int env = blockIdx.x * nwarp + warp;
+
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_bulk_load(dm, p.dm, static_cast<uint32_t>(sizeof(DM)), mbar);
+
+  bool active = env < p.num_envs;
+  if (MODE == MODE_RESET && active && p.mask) active = p.mask[env] != 0;
+  W& w = wsbase[warp];
+  const QsBuffers& B = p.b;
+
+  // ---- state load (overlaps with the TMA copy of the model)
+  bool given_state = false;
+  if (active) {
+    const float* qp = B.qpos + size_t(env) * NQ;
+    const float* qv = B.qvel + size_t(env) * NV;
+    if (MODE == MODE_RESET && p.in_qpos && p.in_qvel) { qp = p.in_qpos + size_t(env) * NQ; qv = p.in_qvel + size_t(env) * NV; given_state = true; }
+    if (lane < NQ) w.qpos[lane] = real(qp[lane]);
+    if (lane < NV) { w.qvel[lane] = real(qv[lane]); w.warm[lane] = real(B.qacc_warmstart[size_t(env) * NV + lane]); }
+    if (lane < NU) w.ctrl[lane] = (MODE == MODE_STEP) ? real(p.ctrl[size_t(env) * NU + lane]) : real(0);
+    if (lane < 6) w.applied[lane] = (MODE == MODE_RESET) ? real(0) : real(B.qfrc_applied[size_t(env) * 6 + lane]);
+    if (lane == 0) { w.mu_floor = real(B.friction[2 * env]); w.mu_feet = real(B.friction[2 * env + 1]); }
+  }
+  mbar_wait(mbar, 0);
+  if (!active) return;
+  const DM& m = *dm;
+  const bool flat = m.terrain_type == 0;
+  double* base64 = B.base_pos64 + size_t(env) * 3;
+  if (lane < 2) {
+    // fp64 master copy of the base position; internal frame is re-centred on flat terrain (resets scatter envs over +-1e4 m)
+    double x = (MODE == MODE_RESET && given_state) ? double(w.qpos[lane]) : base64[lane];
+    if (MODE == MODE_RESET && given_state) base64[lane] = x;
+    const double o = flat ? rint(x) : 0.0;
+    w.org[lane] = o;
+    w.qpos[lane] = real(x - o);
+  } else if (lane == 2) {
+    if (MODE == MODE_RESET && given_state) base64[2] = double(w.qpos[2]); else w.qpos[2] = real(base64[2]);
+  }
+  syncwarp();
+
+  Env<real, NCON, MAXDIM> e(m, w, reinterpret_cast<const Vert4<real>*>(p.vert), lane);
+  const unsigned env_g = unsigned(env + p.env_id_offset);
+  unsigned status = 0;
+  real command[4] = {real(B.command[4 * env]), real(B.command[4 * env + 1]), real(B.command[4 * env + 2]), real(B.command[4 * env + 3])};
+
+  if (MODE == MODE_RESET) {
+    const QsResetOptions& ro = p.ro;
+    const unsigned ep = p.episode[env];
+    real* u = w.obs;  // scratch for the uniforms (obs is packed at the very end)
+    if (lane < 10) {
+      uint32_t r[4];
+      philox4x32(env_g, ep, unsigned(lane), 0x5EEDu, p.seed_lo, p.seed_hi, r);
+      for (int i = 0; i < 4; i++) u[4 * lane + i] = real(u32_to_unit(r[i]));
+      if (lane == 9) {  // two 53-bit uniforms for the fp64 base xy
+        double ux = (double(r[0]) * 4294967296.0 + double(r[1])) * (1.0 / 18446744073709551616.0);
+        double uy = (double(r[2]) * 4294967296.0 + double(r[3])) * (1.0 / 18446744073709551616.0);
+        w.tmpd[0] = ux; w.tmpd[1] = uy;
+      }
+    }
+    syncwarp();
+    if (!given_state) {
+      if (lane < NQ) w.qpos[lane] = m.key_qpos[lane];
+      if (lane < NV) w.qvel[lane] = 0;
+      syncwarp();
+      double bx = double(m.key_qpos[0]), by = double(m.key_qpos[1]);
+      if (ro.randomize) {
+        if (lane < NJ) {
+          w.qpos[7 + lane] += real(-ro.angle_sweep + 2 * ro.angle_sweep * double(u[lane]));
+          w.qvel[6 + lane] += real(-ro.vel_sweep + 2 * ro.vel_sweep * double(u[12 + lane]));
+        }
+        // np.random.uniform(limits[0], limits[1]) = lo + (hi - lo) * u with lo = x_max, hi = x_min (quadruped_env.py:352-356)
+        bx = double(m.terrain_limits[0]) + (double(m.terrain_limits[1]) - double(m.terrain_limits[0])) * w.tmpd[0];
+        by = double(m.terrain_limits[2]) + (double(m.terrain_limits[3]) - double(m.terrain_limits[2])) * w.tmpd[1];
+        if (lane == 0) {
+          const real roll = real(-ro.roll_sweep + 2 * ro.roll_sweep * double(u[24])), pitch = real(-ro.pitch_sweep + 2 * ro.pitch_sweep * double(u[25]));
+          const real yaw = real(atan2(-by, -bx));  // angle_between_vectors(xy, 0) math_utils.py:50-51
+          real q[4];
+          euler_to_quat(roll, pitch, yaw, q);
+          for (int i = 0; i < 4; i++) w.qpos[3 + i] = q[i];
+          w.qpos[2] = real(ro.hip_height);
+        }
+      }
+      syncwarp();
+      if (lane == 0) {
+        const double ox = flat ? rint(bx) : 0.0, oy = flat ? rint(by) : 0.0;
+        w.org[0] = ox; w.org[1] = oy;
+        w.qpos[0] = real(bx - ox); w.qpos[1] = real(by - oy);
+      }
+      syncwarp();
+      // lift until no foot (calf-body) contact, quadruped_env.py:376-388
+      bool cleared = false;
+      for (int c = 0; c <= 100; c++) {
+        e.kinematics();
+        e.collide_floor();
+        real pen = 0;
+        bool any = false;
+        for (int k = lane; k < w.ncon; k += 32) {
+          const int bdy = w.c_body[k];
+          if (bdy >= 2 && (bdy - 2) % 3 == 2) { any = true; pen = Num<real>::max(pen, Num<real>::abs(w.c_dist[k])); }
+        }
+        any = qs::ballot(any) != 0;
+        pen = warp_max(pen);
+        if (!any) { cleared = true; break; }
+        if (c == 100) break;
+        if (lane == 0) w.qpos[2] += pen * real(1.1);
+        syncwarp();
+      }
+      if (!cleared) status |= 8u;
+    } else {
+      if (lane == 0) { /* state taken verbatim, :389-391 */ }
+    }
+    if (lane < NV) w.warm[lane] = 0;
+    syncwarp();
+  }
+
+  // ---- forward dynamics
+  e.forward(p.max_iter, real(p.tol));
+  typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
+
+  if (MODE == MODE_FORWARD) {
+    if (lane < NV) B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
+    if (p.aux) {
+      float* a = p.aux + size_t(env) * AUX_STRIDE;
+      for (int it = lane; it < 324; it += 32) {
+        const int i = it / 18, j = it % 18;
+        real v = 0;
+        if (i < 6 && j < 6) v = w.Mbb[i][j];
+        else if (i >= 6 && j < 6) v = w.Mlb[(i - 6) / 3][(i - 6) % 3][j];
+        else if (i < 6 && j >= 6) v = w.Mlb[(j - 6) / 3][(j - 6) % 3][i];
+        else if ((i - 6) / 3 == (j - 6) / 3) v = w.Mll[(i - 6) / 3][(i - 6) % 3][(j - 6) % 3];
+        a[AUX_OFF_M + it] = float(v);
+      }
+      if (lane < NV) {
+        a[AUX_OFF_BIAS + lane] = float(w.bias[lane]);
+        a[AUX_OFF_PASSIVE + lane] = float(-m.dof_damping[lane] * w.qvel[lane]);
+        a[AUX_OFF_SMOOTH + lane] = float(w.fsm[lane]);
+        a[AUX_OFF_CONSTRAINT + lane] = float(w.fcon[lane]);
+      }
+      for (int it = lane; it < 216; it += 32) {
+        const int l = it / 54, i = (it % 54) / 18, d = it % 18;
+        real v = 0;
+        if (d < 6 || (d - 6) / 3 == l) {
+          const real off[3] = {w.footpos[l][0] - w.com[0], w.footpos[l][1] - w.com[1], w.footpos[l][2] - w.com[2]};
+          real cr[3];
+          cross3(cr, w.cdof[d], off);
+          v = w.cdof[d][3 + i] + cr[i];
+        }
+        a[AUX_OFF_JACP + it] = float(v);
+      }
+      if (lane < 12) a[AUX_OFF_FEETPOS + lane] = float(w.footpos[lane / 3][lane % 3] + (lane % 3 < 2 ? real(w.org[lane % 3]) : real(0)));
+      if (lane < 3) a[AUX_OFF_COM + lane] = float(w.com[lane] + (lane < 2 ? real(w.org[lane]) : real(0)));
+      for (int it = lane; it < 39; it += 32) a[AUX_OFF_XPOS + it] = float(w.xpos[1 + it / 3][it % 3] + (it % 3 < 2 ? real(w.org[it % 3]) : real(0)));
+      if (lane < 6) a[AUX_OFF_IMU + lane] = m.has_imu ? float(w.sens[lane]) : 0.f;
+      for (int c = lane; c < NCON; c += 32) {
+        float* o = a + AUX_OFF_CONTACTS + QS_CONTACT_STRIDE * c;
+        if (c < w.ncon) {
+          o[0] = float(w.c_dist[c]);
+          o[1] = float(w.c_pos[c][0] + real(w.org[0])); o[2] = float(w.c_pos[c][1] + real(w.org[1])); o[3] = float(w.c_pos[c][2]);
+          for (int i = 0; i < 9; i++) o[4 + i] = float(w.c_frame[c][i]);
+          for (int i = 0; i < 3; i++) o[13 + i] = (i < w.c_dim[c]) ? float(w.c_F[c][i]) : 0.f;
+          o[16] = float(w.c_geom[c]); o[17] = float(w.c_body[c]); o[18] = float(w.c_fri[c][0]); o[19] = float(w.c_dim[c]);
+        } else {
+          for (int i = 0; i < QS_CONTACT_STRIDE; i++) o[i] = 0.f;
+        }
+      }
+    }
+    if (lane == 0) {
+      B.ncon[env] = w.ncon;
+      B.solver_iter[env] = e.solver_iter;
+      B.invalid_body_mask[2 * env] = uint8_t(fl.invalid_mask & 0xff); B.invalid_body_mask[2 * env + 1] = uint8_t((fl.invalid_mask >> 8) & 0xff);
+    }
+    return;
+  }
+
+  // ---- integrate, then env-side bookkeeping
+  e.integrate(base64);
+  fl.out_of_bounds = e.flags().out_of_bounds;  // bounds are tested on the post-step base position (:1252-1256)
+
+  float sim_time = (MODE == MODE_RESET) ? 0.f : B.sim_time[env];
+  sim_time += float(m.timestep);
+  if (MODE == MODE_RESET) {
+    // command + friction resampling happen after the step inside reset (:397-404)
+    const QsResetOptions& ro = p.ro;
+    const real* u = w.obs;
+    const real vn = real(ro.lin_vel_range[0] + (ro.lin_vel_range[1] - ro.lin_vel_range[0]) * double(u[26]));
+    real hx = 1, hy = 0, vnorm = vn;
+    if (ro.command_mode & 2) { real ang = real(-3.14159265358979323846 + 2 * 3.14159265358979323846 * double(u[27])); Num<real>::sincos(ang, &hy, &hx); }
+    if (!(ro.command_mode & 3)) vnorm = 0;  // 'human'
+    command[0] = vnorm * hx; command[1] = vnorm * hy; command[2] = 0;
+    command[3] = (ro.command_mode & 4) ? real(ro.ang_vel_range[0] + (ro.ang_vel_range[1] - ro.ang_vel_range[0]) * double(u[28])) : real(0);
+    const float mu = float(ro.friction_range[0] + (ro.friction_range[1] - ro.friction_range[0]) * double(u[29]));
+    if (lane < 4) B.command[4 * env + lane] = float(command[lane]);
+    if (lane < 2) B.friction[2 * env + lane] = mu;
+    if (lane == 0) p.episode[env] = p.episode[env] + 1;
+  }
+  syncwarp();
+  e.pack_obs(command, fl.contact_mask);
+
+  // ---- write back
+  const bool finite_ok = [&] {
+    bool ok = true;
+    if (lane < NQ) ok = ok && isfinite(double(w.qpos[lane]));
+    if (lane < NV) ok = ok && isfinite(double(w.qvel[lane]));
+    return qs::ballot(!ok) == 0;
+  }();
+  if (!finite_ok) status |= 1u;
+  if (w.overflow) status |= 2u;
+  if (e.solver_maxed) status |= 4u;
+  if (lane < NQ) B.qpos[size_t(env) * NQ + lane] = (lane < 3) ? float(base64[lane]) : float(w.qpos[lane]);
+  if (lane < NV) {
+    B.qvel[size_t(env) * NV + lane] = float(w.qvel[lane]);
+    B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
+    B.qacc_warmstart[size_t(env) * NV + lane] = float(w.qacc[lane]);
+  }
+  if (MODE == MODE_RESET && lane < 6) B.qfrc_applied[size_t(env) * 6 + lane] = 0.f;
+  float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
+  if (obs)
+    for (int i = lane; i < NOBS_BASE; i += 32) obs[i] = float(w.obs[i]);
+  if (p.use_imu) {
+    // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals
+    unsigned tk = p.tick[env];
+    if (lane < 3) {
+      uint32_t r[4];
+      philox4x32(env_g, tk, unsigned(lane), 0x1A2Bu, p.seed_lo ^ 0x9E3779B9u, p.seed_hi, r);
+      const float u1 = fmaxf(u32_to_unit(r[0]), 5.9604645e-8f), u2 = u32_to_unit(r[1]), u3 = fmaxf(u32_to_unit(r[2]), 5.9604645e-8f), u4 = u32_to_unit(r[3]);
+      const float ra = sqrtf(-2.f * logf(u1)), rb = sqrtf(-2.f * logf(u3));
+      float s1, c1, s2, c2;
+      sincosf(6.28318530717958647692f * u2, &s1, &c1);
+      sincosf(6.28318530717958647692f * u4, &s2, &c2);
+      const float n_acc = ra * c1 * p.imu_an, n_ab = ra * s1 * p.imu_abr, n_gyr = rb * c2 * p.imu_gn, n_gb = rb * s2 * p.imu_gbr;
+      float* bias = B.imu_bias + size_t(env) * 6;
+      const float ab = bias[lane] + n_ab, gb = bias[3 + lane] + n_gb;
+      bias[lane] = ab; bias[3 + lane] = gb;
+      if (obs) {
+        float* io = obs + NOBS_BASE;
+        io[lane] = float(w.sens[lane]) + ab + n_acc; io[3 + lane] = n_acc; io[6 + lane] = ab;
+        io[9 + lane] = float(w.sens[3 + lane]) + gb + n_gyr; io[12 + lane] = n_gyr; io[15 + lane] = gb;
+      }
+    }
+    if (lane == 0) p.tick[env] = tk + 1;
+  }
+  if (lane == 0) {
+    B.sim_time[env] = sim_time;
+    B.step_count[env] = (MODE == MODE_RESET) ? 0 : B.step_count[env] + 1;
+    B.status[env] = uint8_t(status);
+    B.ncon[env] = w.ncon;
+    B.solver_iter[env] = e.solver_iter;
+    B.invalid_body_mask[2 * env] = uint8_t(fl.invalid_mask & 0xff); B.invalid_body_mask[2 * env + 1] = uint8_t((fl.invalid_mask >> 8) & 0xff);
+    if (MODE == MODE_STEP) {
+      if (p.reward) p.reward[env] = 0.f;  // _compute_reward, quadruped_env.py:1141-1144
+      if (p.terminated) p.terminated[env] = uint8_t(fl.invalid_mask != 0 || fl.out_of_bounds);
+      if (p.truncated) p.truncated[env] = 0;
+    }
+  }
+}
+
+using KernelFn = void (*)(const KParams);
+
+template <typename real, int MAXDIM> struct Variant {
+  static KernelFn fn(int mode) {
+    switch (mode) {
+      case MODE_STEP: return env_kernel<real, NCON_MAX, MAXDIM, MODE_STEP>;
+      case MODE_RESET: return env_kernel<real, NCON_MAX, MAXDIM, MODE_RESET>;
+      default: return env_kernel<real, NCON_MAX, MAXDIM, MODE_FORWARD>;
+    }
+  }
+  static size_t ws_bytes() { return sizeof(WS<real, NCON_MAX, MAXDIM>); }
+  static size_t dm_bytes() { return (sizeof(DModel<real>) + 127) & ~size_t(127); }
+};
+
+}  // namespace
+
+struct QsHandle_ {
+  QsConfig cfg{};
+  int maxdim = 3;
+  int obs_dim = 0;
+  void* d_dm = nullptr;
+  void* d_vert = nullptr;
+  unsigned* d_episode = nullptr;
+  unsigned* d_tick = nullptr;
+  float* d_aux = nullptr;
+  // staging for the host-buffer entry point
+  float* d_ctrl = nullptr; float* d_obs = nullptr; float* d_reward = nullptr; uint8_t* d_term = nullptr; uint8_t* d_trunc = nullptr;
+  QsBuffers buf{};
+  bool bound = false;
+  KernelFn k_step = nullptr, k_reset = nullptr, k_forward = nullptr;
+  int warps_per_cta = 8;
+  size_t smem_bytes = 0;
+  double timestep = 0.002;
+  int64_t launches = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(QsHandle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define QS_CUDA(h, call)                                                                         \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(h, 100 + int(e_), std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const QsModel* model) {
+  auto dm = std::make_unique<DModel<real>>();
+  std::vector<Vert4<real>> verts;
+  std::string err = build_dmodel<real>(*model, *dm, verts);
+  if (!err.empty()) return fail(h, 2, err);
+  QS_CUDA(h, cudaMalloc(&h->d_dm, sizeof(DModel<real>)));
+  QS_CUDA(h, cudaMemcpy(h->d_dm, dm.get(), sizeof(DModel<real>), cudaMemcpyHostToDevice));
+  QS_CUDA(h, cudaMalloc(&h->d_vert, sizeof(Vert4<real>) * verts.size()));
+  QS_CUDA(h, cudaMemcpy(h->d_vert, verts.data(), sizeof(Vert4<real>) * verts.size(), cudaMemcpyHostToDevice));
+  using V = Variant<real, MAXDIM>;
+  h->k_step = V::fn(MODE_STEP); h->k_reset = V::fn(MODE_RESET); h->k_forward = V::fn(MODE_FORWARD);
+  int dev = 0, max_smem = 0;
+  QS_CUDA(h, cudaGetDevice(&dev));
+  QS_CUDA(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int warps = 8;
+  while (warps > 1 && V::dm_bytes() + 128 + warps * V::ws_bytes() > size_t(max_smem)) warps >>= 1;
+  h->warps_per_cta = warps;
+  h->smem_bytes = V::dm_bytes() + 128 + warps * V::ws_bytes();
+  if (h->smem_bytes > size_t(max_smem)) return fail(h, 3, "workspace does not fit in shared memory");
+  for (KernelFn f : {h->k_step, h->k_reset, h->k_forward})
+    QS_CUDA(h, cudaFuncSetAttribute(reinterpret_cast<const void*>(f), cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  return 0;
+}
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+int qs_model_sizeof(void) { return int(sizeof(QsModel)); }
+int qs_config_sizeof(void) { return int(sizeof(QsConfig)); }
+int qs_buffers_sizeof(void) { return int(sizeof(QsBuffers)); }
+int qs_obs_dim(const QsConfig* cfg) { return QS_NOBS_BASE + (cfg->use_imu ? QS_NOBS_IMU : 0) + cfg->hm_rows * cfg->hm_cols * 3; }
+const char* qs_last_error(QsHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int qs_max_contacts(QsHandle*) { return NCON_MAX; }
+int64_t qs_launch_count(QsHandle* h) { return h ? h->launches : 0; }
+
+int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
+  if (!model || !cfg || !out) return fail(nullptr, 1, "null argument");
+  if (cfg->num_envs <= 0) return fail(nullptr, 1, "num_envs must be positive");
+  if (model->terrain_type != QS_TERRAIN_FLAT) return fail(nullptr, 4, "only the flat scene is built in this version of libqstep");
+  if (cfg->hm_rows * cfg->hm_cols != 0) return fail(nullptr, 4, "height-map columns are not built in this version of libqstep");
+  QsHandle* h = new (std::nothrow) QsHandle_();
+  if (!h) return fail(nullptr, 1, "out of host memory");
+  h->cfg = *cfg;
+  h->timestep = model->timestep;
+  h->obs_dim = qs_obs_dim(cfg);
+  cudaError_t ce = cudaSetDevice(cfg->device);
+  if (ce != cudaSuccess) { int rc = fail(nullptr, 100 + int(ce), std::string("cudaSetDevice: ") + cudaGetErrorString(ce)); delete h; return rc; }
+  h->maxdim = model_max_dim(*model) > 3 ? 6 : 3;
+  int rc;
+  if (cfg->precision == 0) rc = h->maxdim == 3 ? setup_variant<float, 3>(h, model) : setup_variant<float, 6>(h, model);
+  else rc = h->maxdim == 3 ? setup_variant<double, 3>(h, model) : setup_variant<double, 6>(h, model);
+  if (rc == 0) {
+    cudaError_t e1 = cudaMalloc(&h->d_episode, sizeof(unsigned) * cfg->num_envs), e2 = cudaMalloc(&h->d_tick, sizeof(unsigned) * cfg->num_envs);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(h, 5, "cudaMalloc failed");
+    else { cudaMemset(h->d_episode, 0, sizeof(unsigned) * cfg->num_envs); cudaMemset(h->d_tick, 0, sizeof(unsigned) * cfg->num_envs); }
+  }
+  if (rc != 0) { g_create_error = h->err; qs_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+void qs_destroy(QsHandle* h) {
+  if (!h) return;
+  cudaFree(h->d_dm); cudaFree(h->d_vert); cudaFree(h->d_episode); cudaFree(h->d_tick); cudaFree(h->d_aux);
+  cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
+  delete h;
+}
+
+int qs_bind(QsHandle* h, const QsBuffers* b) {
+  if (!h || !b) return fail(h, 1, "null argument");
+  const void* const* ptrs = reinterpret_cast<const void* const*>(b);
+  for (size_t i = 0; i < sizeof(QsBuffers) / sizeof(void*); i++)
+    if (!ptrs[i]) return fail(h, 1, "QsBuffers has a null pointer");
+  h->buf = *b;
+  h->bound = true;
+  return 0;
+}
+
+static KParams base_params(QsHandle* h) {
+  KParams p{};
+  p.dm = h->d_dm; p.vert = h->d_vert;
+  p.num_envs = h->cfg.num_envs; p.obs_dim = h->obs_dim; p.use_imu = h->cfg.use_imu;
+  p.max_iter = h->cfg.solver_max_iter > 0 ? h->cfg.solver_max_iter : (h->cfg.precision == 0 ? 12 : 100);
+  p.tol = h->cfg.precision == 0 ? 1e-6f : 1e-8f;
+  p.env_id_offset = h->cfg.env_id_offset;
+  p.seed_lo = unsigned(h->cfg.seed & 0xffffffffu); p.seed_hi = unsigned(h->cfg.seed >> 32);
+  p.imu_an = float(h->cfg.imu_accel_noise); p.imu_gn = float(h->cfg.imu_gyro_noise);
+  p.imu_abr = float(h->cfg.imu_accel_bias_rate); p.imu_gbr = float(h->cfg.imu_gyro_bias_rate);
+  p.b = h->buf; p.episode = h->d_episode; p.tick = h->d_tick;
+  return p;
+}
+
+static int launch(QsHandle* h, KernelFn fn, const KParams& p, cudaStream_t s) {
+  const int warps = h->warps_per_cta, grid = (h->cfg.num_envs + warps - 1) / warps;
+  fn<<<grid, warps * 32, h->smem_bytes, s>>>(p);
+  h->launches++;
+  QS_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int qs_step(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!h || !h->bound) return fail(h, 1, "qs_step: handle not bound");
+  if (!ctrl) return fail(h, 1, "qs_step: ctrl is null");
+  KParams p = base_params(h);
+  p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
+  return launch(h, h->k_step, p, static_cast<cudaStream_t>(stream));
+}
+
+int qs_step_host(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (!h || !h->bound) return fail(h, 1, "qs_step_host: handle not bound");
+  const size_t n = size_t(h->cfg.num_envs);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->d_ctrl) {
+    QS_CUDA(h, cudaMalloc(&h->d_ctrl, n * NU * sizeof(float)));
+    QS_CUDA(h, cudaMalloc(&h->d_obs, n * h->obs_dim * sizeof(float)));
+    QS_CUDA(h, cudaMalloc(&h->d_reward, n * sizeof(float)));
+    QS_CUDA(h, cudaMalloc(&h->d_term, n));
+    QS_CUDA(h, cudaMalloc(&h->d_trunc, n));
+  }
+  QS_CUDA(h, cudaMemcpyAsync(h->d_ctrl, ctrl, n * NU * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = qs_step(h, h->d_ctrl, h->d_obs, h->d_reward, h->d_term, h->d_trunc, stream);
+  if (rc) return rc;
+  if (obs) QS_CUDA(h, cudaMemcpyAsync(obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward) QS_CUDA(h, cudaMemcpyAsync(reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (terminated) QS_CUDA(h, cudaMemcpyAsync(terminated, h->d_term, n, cudaMemcpyDeviceToHost, s));
+  if (truncated) QS_CUDA(h, cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
+  QS_CUDA(h, cudaStreamSynchronize(s));
+  return 0;
+}
+
+static int reset_impl(QsHandle* h, const uint8_t* mask, const float* qpos, const float* qvel, const QsResetOptions* opt, float* obs, void* stream) {
+  if (!h || !h->bound) return fail(h, 1, "qs_reset: handle not bound");
+  if (!opt) return fail(h, 1, "qs_reset: options are null");
+  if ((qpos == nullptr) != (qvel == nullptr)) return fail(h, 1, "qs_reset: qpos and qvel must be given together");
+  KParams p = base_params(h);
+  p.mask = mask; p.in_qpos = qpos; p.in_qvel = qvel; p.ro = *opt; p.obs = obs;
+  return launch(h, h->k_reset, p, static_cast<cudaStream_t>(stream));
+}
+
+int qs_reset(QsHandle* h, const uint8_t* mask, const float* qpos, const float* qvel, const QsResetOptions* opt, float* obs, void* stream) {
+  return reset_impl(h, mask, qpos, qvel, opt, obs, stream);
+}
+
+int qs_reset_done(QsHandle* h, const uint8_t* terminated, const QsResetOptions* opt, float* obs, void* stream) {
+  if (!terminated) return fail(h, 1, "qs_reset_done: terminated is null");
+  return reset_impl(h, terminated, nullptr, nullptr, opt, obs, stream);
+}
+
+int qs_forward(QsHandle* h, void* stream) {
+  if (!h || !h->bound) return fail(h, 1, "qs_forward: handle not bound");
+  if (!h->d_aux) QS_CUDA(h, cudaMalloc(&h->d_aux, size_t(h->cfg.num_envs) * AUX_STRIDE * sizeof(float)));
+  KParams p = base_params(h);
+  p.aux = h->d_aux;
+  return launch(h, h->k_forward, p, static_cast<cudaStream_t>(stream));
+}
+
+int qs_get(QsHandle* h, int field, float* dst, void* stream) {
+  if (!h || !h->d_aux) return fail(h, 1, "qs_get: call qs_forward first");
+  int off, width;
+  switch (field) {
+    case QS_FIELD_MASS_MATRIX: off = AUX_OFF_M; width = 324; break;
+    case QS_FIELD_QFRC_BIAS: off = AUX_OFF_BIAS; width = 18; break;
+    case QS_FIELD_QFRC_PASSIVE: off = AUX_OFF_PASSIVE; width = 18; break;
+    case QS_FIELD_FEET_JACP: off = AUX_OFF_JACP; width = 216; break;
+    case QS_FIELD_FEET_POS: off = AUX_OFF_FEETPOS; width = 12; break;
+    case QS_FIELD_COM: off = AUX_OFF_COM; width = 3; break;
+    case QS_FIELD_CONTACTS: off = AUX_OFF_CONTACTS; width = QS_CONTACT_STRIDE * NCON_MAX; break;
+    case QS_FIELD_QFRC_SMOOTH: off = AUX_OFF_SMOOTH; width = 18; break;
+    case QS_FIELD_QFRC_CONSTRAINT: off = AUX_OFF_CONSTRAINT; width = 18; break;
+    case QS_FIELD_XPOS: off = AUX_OFF_XPOS; width = 39; break;
+    case QS_FIELD_SENSOR_IMU: off = AUX_OFF_IMU; width = 6; break;
+    default: return fail(h, 1, "qs_get: unknown field");
+  }
+  QS_CUDA(h, cudaMemcpy2DAsync(dst, width * sizeof(float), h->d_aux + off, AUX_STRIDE * sizeof(float), width * sizeof(float), h->cfg.num_envs,
+                               cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int qs_raycast_heightmap(QsHandle* h, int, int, double, double, float*, void*) {
+  return fail(h, 4, "qs_raycast_heightmap: not built in this version of libqstep");
+}
+
+}  // extern "C"

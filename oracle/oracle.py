@@ -55,6 +55,8 @@ def lib():
         L.orc_get.restype = C.c_int
         L.orc_rollout.argtypes = [C.c_void_p, dp, C.c_int, dp]
         L.orc_rollout.restype = C.c_int
+        L.orc_rollout_autoreset.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int)]
+        L.orc_rollout_autoreset.restype = C.c_int
         assert L.orc_model_sizeof() == C.sizeof(QsModel), 'QsModel layout mismatch between ctypes and C'
         _lib = L
     return _lib
@@ -105,6 +107,13 @@ class Oracle:
     def rollout(self, ctrl_table):
         c = np.ascontiguousarray(ctrl_table, dtype=np.float64)
         return self.L.orc_rollout(self.h, _p(c), len(c), None)
+
+    def rollout_autoreset(self, ctrl_table, reset_states, cursor=0):
+        c = np.ascontiguousarray(ctrl_table, dtype=np.float64)
+        r = np.ascontiguousarray(reset_states, dtype=np.float64)
+        cur = C.c_int(cursor)
+        n = self.L.orc_rollout_autoreset(self.h, _p(c), len(c), _p(r), len(r), C.byref(cur))
+        return n, cur.value
 
     def lift(self):
         return self.L.orc_lift(self.h)

@@ -1174,3 +1174,26 @@ int orc_rollout(void* h, const double* ctrl, int K, double* obs_last) {
   if (obs_last) memcpy(obs_last, obs, sizeof(obs));
   return term;
 }
+
+/* Rollout with auto-reset for CPU-baseline timing: on termination the env is re-initialised from the next entry of a
+ * table of pre-lifted start states (nreset x (19 qpos + 18 qvel)), mirroring the GPU benchmark loop. Returns #resets. */
+int orc_rollout_autoreset(void* h, const double* ctrl, int K, const double* reset_states, int nreset, int* cursor) {
+  OData* d = (OData*)h;
+  int resets = 0;
+  double obs[QS_NOBS_BASE + 6];
+  for (int k = 0; k < K; k++) {
+    if (orc_step(h, ctrl + NU * k, obs)) {
+      const double* s = reset_states + (size_t)((*cursor) % nreset) * (NQ + NV);
+      (*cursor)++;
+      memcpy(d->qpos, s, sizeof(d->qpos));
+      memcpy(d->qvel, s + NQ, sizeof(d->qvel));
+      memset(d->qacc_warmstart, 0, sizeof(d->qacc_warmstart));
+      memset(d->ctrl, 0, sizeof(d->ctrl));
+      d->time = 0;
+      forward(d);
+      euler(d); /* reset() performs one full step, quadruped_env.py:397 */
+      resets++;
+    }
+  }
+  return resets;
+}
