@@ -50,7 +50,8 @@ def load_library() -> C.CDLL:
     L.qs_last_error.restype = C.c_char_p
     L.qs_bind.argtypes = [vp, C.POINTER(QsBuffers)]
     L.qs_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
-    L.qs_step_host.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
+    L.qs_step_host.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
+    L.qs_step_autoreset.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
     L.qs_reset.argtypes = [vp, u8p, fp, fp, C.POINTER(QsResetOptions), fp, vp]
     L.qs_reset_done.argtypes = [vp, u8p, C.POINTER(QsResetOptions), fp, vp]
     L.qs_forward.argtypes = [vp, vp]
@@ -198,10 +199,18 @@ class BatchSim:
                                    self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated
 
+    def step_autoreset(self, ctrl: torch.Tensor, options: QsResetOptions | None = None):
+        """`step` plus, in the same launch, a random reset of every env that just terminated (post-reset obs/state returned)."""
+        o = options or self.reset_options
+        self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), self.obs.data_ptr(), self.reward.data_ptr(),
+                                             self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
+        return self.obs, self.reward, self.terminated, self.truncated
+
     def step_host(self, ctrl_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
-                  terminated_host: torch.Tensor, truncated_host: torch.Tensor):
+                  terminated_host: torch.Tensor, truncated_host: torch.Tensor, auto_reset: QsResetOptions | None = None):
         """Same step through HOST buffers (pinned CPU tensors): H2D ctrl, kernel, D2H results, stream-synchronised."""
-        self._check(self.L.qs_step_host(self.h, ctrl_host.data_ptr(), obs_host.data_ptr(), reward_host.data_ptr(),
+        self._check(self.L.qs_step_host(self.h, ctrl_host.data_ptr(), C.byref(auto_reset) if auto_reset is not None else None,
+                                        obs_host.data_ptr(), reward_host.data_ptr(),
                                         terminated_host.data_ptr(), truncated_host.data_ptr(), self._stream()))
 
     def reset(self, mask: torch.Tensor | None = None, qpos: torch.Tensor | None = None, qvel: torch.Tensor | None = None,

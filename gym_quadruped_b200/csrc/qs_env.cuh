@@ -35,12 +35,12 @@ template <typename real> struct alignas(16) DModel {
   real imu_pos[4];
   real imu_mat[12];
   real mass_total, pad_r[3];
-  real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_iquat[NB][4], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
+  real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_imat[NB][9], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
   real jnt_pos[NJ][3], jnt_axis[NJ][3], jnt_range[NJ][2], jnt_K[NJ], jnt_B[NJ], jnt_solimp[NJ][5], jnt_margin[NJ];
   real qpos0[20], key_qpos[20];
   real dof_damping[NV], dof_armature[NV], dof_floss[NV], dof_iw[NV], dof_B[NV], dof_R[NV], dof_D[NV];
   real act_clo[NU], act_chi[NU], act_flo[NU], act_fhi[NU];
-  real geom_pos[MAXGEOM][3], geom_mat[MAXGEOM][9], geom_size[MAXGEOM][3], geom_bcenter[MAXGEOM][3], geom_rbound[MAXGEOM],
+  real geom_pos[MAXGEOM][3], geom_mat[MAXGEOM][9], geom_size[MAXGEOM][3], geom_bcenter[MAXGEOM][3], geom_bhalf[MAXGEOM][3], geom_rbound[MAXGEOM],
       geom_fri[MAXGEOM][3], geom_margin[MAXGEOM], geom_incmargin[MAXGEOM], geom_K[MAXGEOM], geom_B[MAXGEOM], geom_solimp[MAXGEOM][5];
   int cone, iterations, ls_iterations, ngeom, nvert, terrain_type, nbox, has_imu;
   int jnt_limited[NJ];
@@ -50,65 +50,81 @@ template <typename real> struct alignas(16) DModel {
   int pad_i[4];
 };
 
-// Per-warp workspace (shared memory).
+// Per-warp workspace (shared memory).  Arrays with disjoint lifetimes share storage so that 28 warps (= 28 envs) fit in
+// one SM's 227 KB next to the staged model:  4096 envs -> 147 CTAs of 28 warps -> a single wave on 148 SMs.
+//   kin  (body poses)          : kinematics .. collision / cdof        | hes (Hessian blocks + factors): solver .. Euler
+//   tmp  (velocity-stage data) : com_inertia .. mass matrix            | Jc  (contact Jacobians)       : constraints .. solver
+//                                                                      | obs (staged observation row)  : after Euler
 template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
+  static constexpr int NW = MAXDIM * (MAXDIM + 1) / 2;  // packed symmetric contact weight
   // state (internal frame: base xy relative to the per-env origin `org`)
   real qpos[20], qvel[NV], ctrl[NU], warm[NV], applied[6];
   real mu_floor, mu_feet;
   double org[2];
   double tmpd[2];
-  // position stage
-  real xpos[NB][3], xquat[NB][4], xmat[NB][9], xaxis[NJ][3], xanchor[NJ][3], com[4];
-  real cdof[NV][6], cdofdot[NV][6], cinert[NB][10], crb[NB][10], cvel[NB][6], cfrc[NB][6];
-  real footpos[4][3];
-  // block mass matrix / Hessian: base-base, leg-base, leg-leg
+  // persistent kinematic results
+  real com[4], cdof[NV][6], footpos[4][3];
+  union {
+    struct { real xpos[NB][3], xmat[NB][9], xaxis[NJ][3]; } kin;
+    struct { real Hbb[6][6], Hlb[4][3][6], Hll[4][3][3], Ci[4][3][3], Y[4][3][6], SL[6][6], SLinv[8]; } hes;
+  };
+  union {
+    struct { real cdofdot[NV][6], cinert[NB][10], cvel[NB][6], cfrc[NB][6]; } tmp;
+    real Jc[NCON][MAXDIM][9];
+    real obs[NOBS_BASE + 5];
+  };
+  // block mass matrix: base-base, leg-base, leg-leg
   real Mbb[6][6], Mlb[4][3][6], Mll[4][3][3];
-  real Hbb[6][6], Hlb[4][3][6], Hll[4][3][3];
-  real Ci[4][3][3], Y[4][3][6], SL[6][6], SLinv[8];
   // dof vectors
-  real bias[NV], fsm[NV], asmooth[NV], qacc[NV], fcon[NV], grad[NV], search[NV], Mv[NV], Ma[NV], rhs[NV], sol[NV];
+  real fsm[NV], asmooth[NV], qacc[NV], fcon[NV], grad[NV], search[NV], Mv[NV], Ma[NV];
   // constraint units: [0,12) friction loss, [12,24) joint limits, then contacts
-  real u_ar[NFL + NLIM], u_D[NFL + NLIM], u_R[NFL + NLIM], u_sign[NFL + NLIM], u_r[NFL + NLIM], u_v[NFL + NLIM], u_F[NFL + NLIM],
-      u_W[NFL + NLIM];
+  real u_ar[NFL + NLIM], u_D[NFL + NLIM], u_sign[NFL + NLIM], u_r[NFL + NLIM], u_F[NFL + NLIM];
+  union { real u_v[NFL + NLIM]; real u_W[NFL + NLIM]; };
   int ncon, overflow;
-  real c_dist[NCON], c_pos[NCON][3], c_frame[NCON][9], c_fri[NCON][3], c_mu[NCON], c_sign[NCON];
-  int c_geom[NCON], c_body[NCON], c_dim[NCON];
-  real c_D[NCON][MAXDIM], c_ar[NCON][MAXDIM], c_r[NCON][MAXDIM], c_v[NCON][MAXDIM], c_F[NCON][MAXDIM], c_W[NCON][MAXDIM][MAXDIM];
-  real Jc[NCON][MAXDIM][9], Tc[NCON][MAXDIM][9];
-  real sens[8];
-  real obs[NOBS_BASE + 5];
+  real c_dist[NCON], c_pos[NCON][3], c_frame[NCON][6], c_fri[NCON][3], c_mu[NCON], c_sign[NCON];
+  int c_info[NCON];  // geom | body << 8 | dim << 16
+  real c_D[NCON][MAXDIM], c_ar[NCON][MAXDIM], c_r[NCON][MAXDIM], c_F[NCON][MAXDIM];
+  union { real c_v[NCON][MAXDIM]; real c_W[NCON][NW]; };
+  real sens[8], sens_tmp[24];
 };
 
 template <typename real, int NCON, int MAXDIM> struct Env {
   using N = Num<real>;
   using W = WS<real, NCON, MAXDIM>;
+  static constexpr int NW = W::NW;
   const DModel<real>& m;
   W& w;
   const Vert4<real>* vert;
   const int lane;
-  int solver_iter;
+  int solver_iter, ls_evals;
   bool solver_maxed;
+  float* bias_out;  // optional destination for qfrc_bias (accessor dump), else nullptr
 
-  QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_) : m(m_), w(w_), vert(v_), lane(lane_), solver_iter(0), solver_maxed(false) {}
+  QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_)
+      : m(m_), w(w_), vert(v_), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {}
+
+  QS_DEV static int info_geom(int info) { return info & 0xff; }
+  QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
+  QS_DEV static int info_dim(int info) { return info >> 16; }
+  QS_DEV static int widx(int a, int b) { return a <= b ? a * MAXDIM - (a * (a - 1)) / 2 + (b - a) : b * MAXDIM - (b * (b - 1)) / 2 + (a - b); }
 
   // ------------------------------------------------------------------ position stage
   // [MJ] mj_kinematics: lane j<12 walks the chain base -> ... -> body j+2 on its own, lane 12 owns the base.
+  // Joint anchors coincide with the body origins in every supported model (jnt_pos = 0, checked at model build).
   QS_DEV void kinematics() {
     real qb[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]};
     quat_normalize(qb);
     real Rb[9];
     quat_to_mat(Rb, qb);
     if (lane == 12) {
-      for (int i = 0; i < 3; i++) w.xpos[1][i] = w.qpos[i];
-      for (int i = 0; i < 4; i++) w.xquat[1][i] = qb[i];
-      for (int i = 0; i < 9; i++) w.xmat[1][i] = Rb[i];
+      for (int i = 0; i < 3; i++) w.kin.xpos[1][i] = w.qpos[i];
+      for (int i = 0; i < 9; i++) w.kin.xmat[1][i] = Rb[i];
     } else if (lane == 13) {
-      for (int i = 0; i < 3; i++) w.xpos[0][i] = 0;
-      w.xquat[0][0] = 1; w.xquat[0][1] = w.xquat[0][2] = w.xquat[0][3] = 0;
-      for (int i = 0; i < 9; i++) w.xmat[0][i] = (i % 4 == 0) ? real(1) : real(0);
+      for (int i = 0; i < 3; i++) w.kin.xpos[0][i] = 0;
+      for (int i = 0; i < 9; i++) w.kin.xmat[0][i] = (i % 4 == 0) ? real(1) : real(0);
     } else if (lane < 12) {
       const int l = lane / 3, k = lane % 3;
-      real pos[3] = {w.qpos[0], w.qpos[1], w.qpos[2]}, quat[4] = {qb[0], qb[1], qb[2], qb[3]}, R[9], anchor[3] = {0, 0, 0}, axis[3] = {0, 0, 0};
+      real pos[3] = {w.qpos[0], w.qpos[1], w.qpos[2]}, quat[4] = {qb[0], qb[1], qb[2], qb[3]}, R[9], axis[3] = {0, 0, 0};
       for (int i = 0; i < 9; i++) R[i] = Rb[i];
       for (int t = 0; t < 3; t++) {
         if (t > k) break;
@@ -117,44 +133,42 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         mul_mv(tmp, R, m.body_pos[b]);
         for (int i = 0; i < 3; i++) pos[i] += tmp[i];
         quat_mul(q2, quat, m.body_quat[b]);
-        quat_to_mat(R, q2);
-        mul_mv(tmp, R, m.jnt_pos[j]);
-        for (int i = 0; i < 3; i++) anchor[i] = pos[i] + tmp[i];
-        mul_mv(axis, R, m.jnt_axis[j]);
+        if (t == k) { quat_to_mat(R, q2); mul_mv(axis, R, m.jnt_axis[j]); }
         real s, c;
         N::sincos(real(0.5) * (w.qpos[7 + j] - m.qpos0[7 + j]), &s, &c);
         real qloc[4] = {c, s * m.jnt_axis[j][0], s * m.jnt_axis[j][1], s * m.jnt_axis[j][2]};
         quat_mul(quat, q2, qloc);
-        quat_to_mat(R, quat);
-        mul_mv(tmp, R, m.jnt_pos[j]);
-        for (int i = 0; i < 3; i++) pos[i] = anchor[i] - tmp[i];
         quat_normalize(quat);
         quat_to_mat(R, quat);
       }
       const int b = lane + 2;
-      for (int i = 0; i < 3; i++) { w.xpos[b][i] = pos[i]; w.xanchor[lane][i] = anchor[i]; w.xaxis[lane][i] = axis[i]; }
-      for (int i = 0; i < 4; i++) w.xquat[b][i] = quat[i];
-      for (int i = 0; i < 9; i++) w.xmat[b][i] = R[i];
+      for (int i = 0; i < 3; i++) { w.kin.xpos[b][i] = pos[i]; w.kin.xaxis[lane][i] = axis[i]; }
+      for (int i = 0; i < 9; i++) w.kin.xmat[b][i] = R[i];
     }
     syncwarp();
   }
 
-  // [MJ] mj_comPos + mj_crb: body lanes 0..12 (body = lane+1); composite inertias by shuffles.
+  // [MJ] mj_comPos: subtree centre of mass and per-body spatial inertias about it; body lanes 0..12 (body = lane+1)
   QS_DEV void com_inertia() {
     const int b = lane + 1;
     const bool isb = lane < 13;
     const int bb = isb ? b : 1;
-    real xipos[3], Ri[9], qi[4], tmp[3];
-    mul_mv(tmp, w.xmat[bb], m.body_ipos[bb]);
-    for (int i = 0; i < 3; i++) xipos[i] = w.xpos[bb][i] + tmp[i];
-    quat_mul(qi, w.xquat[bb], m.body_iquat[bb]);
-    quat_to_mat(Ri, qi);
+    real xipos[3], Ri[9], tmp[3];
+    mul_mv(tmp, w.kin.xmat[bb], m.body_ipos[bb]);
+    for (int i = 0; i < 3; i++) xipos[i] = w.kin.xpos[bb][i] + tmp[i];
+    {
+      const real* A = w.kin.xmat[bb];
+      const real* Bm = m.body_imat[bb];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Ri[3 * r + c] = A[3 * r] * Bm[c] + A[3 * r + 1] * Bm[3 + c] + A[3 * r + 2] * Bm[6 + c];
+    }
     const real mass = isb ? m.body_mass[bb] : real(0);
     real c[3];
-    for (int i = 0; i < 3; i++) c[i] = warp_sum(mass * xipos[i]) / m.mass_total;
-    real I[10];
-    {
+    const real inv_mass = N::rcp(m.mass_total);
+    for (int i = 0; i < 3; i++) c[i] = warp_sum(mass * xipos[i]) * inv_mass;
+    if (isb) {
       const real* in = m.body_inertia[bb];
+      real* I = w.tmp.cinert[b];
       real o[3] = {xipos[0] - c[0], xipos[1] - c[1], xipos[2] - c[2]};
       real A00 = Ri[0] * in[0] * Ri[0] + Ri[1] * in[1] * Ri[1] + Ri[2] * in[2] * Ri[2];
       real A11 = Ri[3] * in[0] * Ri[3] + Ri[4] * in[1] * Ri[4] + Ri[5] * in[2] * Ri[5];
@@ -166,25 +180,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       I[0] = A00 + mass * (oo - o[0] * o[0]); I[1] = A11 + mass * (oo - o[1] * o[1]); I[2] = A22 + mass * (oo - o[2] * o[2]);
       I[3] = A01 - mass * o[0] * o[1]; I[4] = A02 - mass * o[0] * o[2]; I[5] = A12 - mass * o[1] * o[2];
       I[6] = mass * o[0]; I[7] = mass * o[1]; I[8] = mass * o[2]; I[9] = mass;
-      if (!isb) for (int i = 0; i < 10; i++) I[i] = 0;
-    }
-    // composite: base = sum of all; hip = self+thigh+calf; thigh = self+calf
-    const int k = (lane >= 1 && lane < 13) ? (lane - 1) % 3 : 3;
-    real cr[10];
-    for (int i = 0; i < 10; i++) {
-      real tot = warp_sum(I[i]);
-      real t1 = shfl(I[i], (lane + 1) & 31), t2 = shfl(I[i], (lane + 2) & 31);
-      cr[i] = (lane == 0) ? tot : I[i] + (k <= 1 ? t1 : real(0)) + (k == 0 ? t2 : real(0));
-    }
-    if (isb) {
-      for (int i = 0; i < 10; i++) { w.cinert[b][i] = I[i]; w.crb[b][i] = cr[i]; }
     }
     if (lane == 13) for (int i = 0; i < 3; i++) w.com[i] = c[i];
     syncwarp();
   }
 
-  // [MJ] cdof (mj_comPos) then M (mj_crb) in block form; dof lanes 0..17
-  QS_DEV void cdof_and_mass() {
+  // [MJ] cdof (mj_comPos); dof lanes 0..17
+  QS_DEV void cdof() {
     if (lane < NV) {
       const int d = lane;
       real ax[3], off[3], cd[6];
@@ -193,10 +195,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       } else {
         if (d < 6) {
           const int kk = d - 3;
-          ax[0] = w.xmat[1][kk]; ax[1] = w.xmat[1][3 + kk]; ax[2] = w.xmat[1][6 + kk];
-          for (int i = 0; i < 3; i++) off[i] = w.com[i] - w.xpos[1][i];
+          ax[0] = w.kin.xmat[1][kk]; ax[1] = w.kin.xmat[1][3 + kk]; ax[2] = w.kin.xmat[1][6 + kk];
+          for (int i = 0; i < 3; i++) off[i] = w.com[i] - w.kin.xpos[1][i];
         } else {
-          for (int i = 0; i < 3; i++) { ax[i] = w.xaxis[d - 6][i]; off[i] = w.com[i] - w.xanchor[d - 6][i]; }
+          for (int i = 0; i < 3; i++) { ax[i] = w.kin.xaxis[d - 6][i]; off[i] = w.com[i] - w.kin.xpos[d - 4][i]; }
         }
         cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
         cross3(cd + 3, ax, off);
@@ -204,11 +206,30 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int i = 0; i < 6; i++) w.cdof[d][i] = cd[i];
     }
     syncwarp();
+  }
+
+  // [MJ] mj_crb: composite inertias (in place, by shuffles) then M in block form; must run after bias_and_smooth
+  QS_DEV void mass_matrix() {
+    {
+      const bool isb = lane < 13;
+      const int b = lane + 1;
+      const int k = (lane >= 1 && isb) ? (lane - 1) % 3 : 3;
+      real cr[10];
+      for (int i = 0; i < 10; i++) {
+        const real v = isb ? w.tmp.cinert[b][i] : real(0);
+        const real tot = warp_sum(v);
+        const real t1 = shfl(v, (lane + 1) & 31), t2 = shfl(v, (lane + 2) & 31);
+        cr[i] = (lane == 0) ? tot : v + (k <= 1 ? t1 : real(0)) + (k == 0 ? t2 : real(0));
+      }
+      syncwarp();
+      if (isb) for (int i = 0; i < 10; i++) w.tmp.cinert[b][i] = cr[i];
+    }
+    syncwarp();
     if (lane < NV) {
       const int d = lane, body = d < 6 ? 1 : d - 4;
       real buf[6], cd[6];
       for (int i = 0; i < 6; i++) cd[i] = w.cdof[d][i];
-      mul_inert_vec(buf, w.crb[body], cd);
+      mul_inert_vec(buf, w.tmp.cinert[body], cd);
       if (d < 6) {
         for (int j = 0; j <= d; j++) {
           real v = 0;
@@ -247,25 +268,34 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int i = 0; i < 6; i++) cv[i] = vt[i];
       for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) cv[i] += w.cdof[d][i] * w.qvel[d];
       if (lane == 0) {
-        for (int d = 0; d < 3; d++) for (int i = 0; i < 6; i++) w.cdofdot[d][i] = 0;
-        for (int d = 3; d < 6; d++) { real t[6]; cross_motion(t, vt, w.cdof[d]); for (int i = 0; i < 6; i++) w.cdofdot[d][i] = t[i]; }
+        for (int d = 0; d < 3; d++) for (int i = 0; i < 6; i++) w.tmp.cdofdot[d][i] = 0;
+        for (int d = 3; d < 6; d++) { real t[6]; cross_motion(t, vt, w.cdof[d]); for (int i = 0; i < 6; i++) w.tmp.cdofdot[d][i] = t[i]; }
       } else {
         for (int t = 0; t <= k; t++) {
           const int d = 6 + 3 * l + t;
-          if (t == k) { real cdd[6]; cross_motion(cdd, cv, w.cdof[d]); for (int i = 0; i < 6; i++) w.cdofdot[d][i] = cdd[i]; }
+          if (t == k) { real cdd[6]; cross_motion(cdd, cv, w.cdof[d]); for (int i = 0; i < 6; i++) w.tmp.cdofdot[d][i] = cdd[i]; }
           for (int i = 0; i < 6; i++) cv[i] += w.cdof[d][i] * w.qvel[d];
         }
       }
-      for (int i = 0; i < 6; i++) w.cvel[b][i] = cv[i];
+      for (int i = 0; i < 6; i++) w.tmp.cvel[b][i] = cv[i];
     }
     syncwarp();
     real f[6] = {0, 0, 0, 0, 0, 0};
     if (isb) {
       real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-      for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d];
-      for (int t = 0; t <= k; t++) { const int d = 6 + 3 * l + t; for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d]; }
+      for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.tmp.cdofdot[d][i] * w.qvel[d];
+      for (int t = 0; t <= k; t++) { const int d = 6 + 3 * l + t; for (int i = 0; i < 6; i++) ca[i] += w.tmp.cdofdot[d][i] * w.qvel[d]; }
+      if (lane == 0 && m.has_imu) {
+        // IMU pre-computation (everything except the cdof*qacc term), kept because kin/tmp storage is recycled by the solver
+        real* st = w.sens_tmp;
+        for (int i = 0; i < 6; i++) { st[i] = cv[i]; st[6 + i] = ca[i]; }
+        real tmp[3];
+        mul_mv(tmp, w.kin.xmat[1], m.imu_pos);
+        for (int i = 0; i < 3; i++) st[12 + i] = w.kin.xpos[1][i] + tmp[i] - w.com[i];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) st[15 + 3 * r + c] = w.kin.xmat[1][3 * r] * m.imu_mat[c] + w.kin.xmat[1][3 * r + 1] * m.imu_mat[3 + c] + w.kin.xmat[1][3 * r + 2] * m.imu_mat[6 + c];
+      }
       real I[10], t1[6], t2[6];
-      for (int i = 0; i < 10; i++) I[i] = w.cinert[b][i];
+      for (int i = 0; i < 10; i++) I[i] = w.tmp.cinert[b][i];
       mul_inert_vec(t1, I, ca);
       mul_inert_vec(t2, I, cv);
       cross_force(f, cv, t2);
@@ -276,14 +306,14 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       real tot = warp_sum(f[i]);
       real t1 = shfl(f[i], (lane + 1) & 31), t2 = shfl(f[i], (lane + 2) & 31);
       real s = (lane == 0) ? tot : f[i] + (kk <= 1 ? t1 : real(0)) + (kk == 0 ? t2 : real(0));
-      if (isb) w.cfrc[b][i] = s;
+      if (isb) w.tmp.cfrc[b][i] = s;
     }
     syncwarp();
     if (lane < NV) {
       const int d = lane, body = d < 6 ? 1 : d - 4;
       real s = 0;
-      for (int i = 0; i < 6; i++) s += w.cdof[d][i] * w.cfrc[body][i];
-      w.bias[d] = s;
+      for (int i = 0; i < 6; i++) s += w.cdof[d][i] * w.tmp.cfrc[body][i];
+      if (bias_out) bias_out[d] = float(s);
       real act;
       if (d < 6) act = w.applied[d];
       else {
@@ -313,27 +343,27 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     return s;
   }
 
-  // Factor the block matrix currently in (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
+  // Factor the block matrix in w.hes (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
   // Schur complement S = A - sum B_l^T Y_l -> Cholesky SL (lower) with reciprocal diagonal.
-  QS_DEV void factor_H() {
+  QS_NOINLINE static void factor_H(W& w, const int lane) {
+    auto& h = w.hes;
     if (lane < 24) {
       const int l = lane / 6, c = lane % 6;
       // LDL^T of the 3x3 leg block, done redundantly by the 6 column lanes of a leg
-      const real c00 = w.Hll[l][0][0], c10 = w.Hll[l][1][0], c20 = w.Hll[l][2][0], c11 = w.Hll[l][1][1], c21 = w.Hll[l][2][1], c22 = w.Hll[l][2][2];
-      const real id0 = real(1) / c00, l10 = c10 * id0, l20 = c20 * id0;
-      const real d1 = c11 - l10 * c10, id1 = real(1) / d1;
+      const real c00 = h.Hll[l][0][0], c10 = h.Hll[l][1][0], c20 = h.Hll[l][2][0], c11 = h.Hll[l][1][1], c21 = h.Hll[l][2][1], c22 = h.Hll[l][2][2];
+      const real id0 = N::rcp(c00), l10 = c10 * id0, l20 = c20 * id0;
+      const real d1 = c11 - l10 * c10, id1 = N::rcp(d1);
       const real l21 = (c21 - l20 * c10) * id1;
-      const real d2 = c22 - l20 * c20 - l21 * l21 * d1, id2 = real(1) / d2;
-      // solve C y = b for b = B_l[:, c]
-      real b0 = w.Hlb[l][0][c], b1 = w.Hlb[l][1][c], b2 = w.Hlb[l][2][c];
+      const real d2 = c22 - l20 * c20 - l21 * l21 * d1, id2 = N::rcp(d2);
+      real b0 = h.Hlb[l][0][c], b1 = h.Hlb[l][1][c], b2 = h.Hlb[l][2][c];
       real z0 = b0, z1 = b1 - l10 * z0, z2 = b2 - l20 * z0 - l21 * z1;
       real y2 = z2 * id2, y1 = z1 * id1 - l21 * y2, y0 = z0 * id0 - l10 * y1 - l20 * y2;
-      w.Y[l][0][c] = y0; w.Y[l][1][c] = y1; w.Y[l][2][c] = y2;
+      h.Y[l][0][c] = y0; h.Y[l][1][c] = y1; h.Y[l][2][c] = y2;
       if (c < 3) {  // column c of the explicit inverse
         real e0 = c == 0, e1 = c == 1, e2 = c == 2;
         real u0 = e0, u1 = e1 - l10 * u0, u2 = e2 - l20 * u0 - l21 * u1;
         real v2 = u2 * id2, v1 = u1 * id1 - l21 * v2, v0 = u0 * id0 - l10 * v1 - l20 * v2;
-        w.Ci[l][0][c] = v0; w.Ci[l][1][c] = v1; w.Ci[l][2][c] = v2;
+        h.Ci[l][0][c] = v0; h.Ci[l][1][c] = v1; h.Ci[l][2][c] = v2;
       }
     }
     syncwarp();
@@ -341,10 +371,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (lane < 21) {
       int i = 0, j = lane;
       while (j > i) { j -= i + 1; i++; }
-      real s = w.Hbb[i][j];
+      real s = h.Hbb[i][j];
       for (int l = 0; l < 4; l++)
-        for (int k = 0; k < 3; k++) s -= w.Hlb[l][k][i] * w.Y[l][k][j];
-      w.SL[i][j] = s;
+        for (int k = 0; k < 3; k++) s -= h.Hlb[l][k][i] * h.Y[l][k][j];
+      h.SL[i][j] = s;
     }
     syncwarp();
     // every lane runs the 6x6 Cholesky redundantly in registers (6 dependent pivots, no further synchronisation)
@@ -352,7 +382,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 #pragma unroll
     for (int i = 0; i < 6; i++)
 #pragma unroll
-      for (int j = 0; j <= i; j++) S[i][j] = w.SL[i][j];
+      for (int j = 0; j <= i; j++) S[i][j] = h.SL[i][j];
     syncwarp();
     real inv[6];
 #pragma unroll
@@ -361,9 +391,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 #pragma unroll
       for (int k = 0; k < j; k++) s -= S[j][k] * S[j][k];
       s = N::max(s, N::minval);
-      real r = N::sqrt(s);
-      S[j][j] = r;
-      inv[j] = real(1) / r;
+      inv[j] = N::rsqrt(s);
+      S[j][j] = s * inv[j];
 #pragma unroll
       for (int i = j + 1; i < 6; i++) {
         real t = S[i][j];
@@ -376,19 +405,23 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 #pragma unroll
       for (int i = 0; i < 6; i++) {
 #pragma unroll
-        for (int j = 0; j <= i; j++) w.SL[i][j] = S[i][j];
-        w.SLinv[i] = inv[i];
+        for (int j = 0; j <= i; j++) h.SL[i][j] = S[i][j];
+        h.SLinv[i] = inv[i];
       }
     }
     syncwarp();
   }
 
-  // solve (factored H) x = rhs; rhs in w.rhs, result in w.sol (both shared); all lanes participate
-  QS_DEV void solve_H() {
-    real t = 0;
+  // solve (factored H) x = rhs for shared-memory vectors rhs, out (may alias); out = scale * x; all lanes participate
+  QS_NOINLINE static void solve_H(W& w, const int lane, const real* rhs, real* out, const real scale) {
+    auto& h = w.hes;
+    real t = 0, rl = 0;
     if (lane < 6) {
-      t = w.rhs[lane];
-      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) t -= w.Y[l][k][lane] * w.rhs[6 + 3 * l + k];
+      t = rhs[lane];
+      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) t -= h.Y[l][k][lane] * rhs[6 + 3 * l + k];
+    } else if (lane < NV) {
+      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
+      for (int k2 = 0; k2 < 3; k2++) rl += h.Ci[l][k][k2] * rhs[6 + 3 * l + k2];
     }
     real tb[6], xb[6];
 #pragma unroll
@@ -397,32 +430,32 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     for (int i = 0; i < 6; i++) {
       real s = tb[i];
 #pragma unroll
-      for (int k = 0; k < i; k++) s -= w.SL[i][k] * xb[k];
-      xb[i] = s * w.SLinv[i];
+      for (int k = 0; k < i; k++) s -= h.SL[i][k] * xb[k];
+      xb[i] = s * h.SLinv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
       real s = xb[i];
 #pragma unroll
-      for (int k = i + 1; k < 6; k++) s -= w.SL[k][i] * xb[k];
-      xb[i] = s * w.SLinv[i];
+      for (int k = i + 1; k < 6; k++) s -= h.SL[k][i] * xb[k];
+      xb[i] = s * h.SLinv[i];
     }
-    if (lane < 6) w.sol[lane] = xb[lane];
+    syncwarp();  // rhs fully consumed before out (possibly the same array) is written
+    if (lane < 6) out[lane] = scale * xb[lane];
     else if (lane < NV) {
       const int l = (lane - 6) / 3, k = (lane - 6) % 3;
-      real s = 0;
-      for (int k2 = 0; k2 < 3; k2++) s += w.Ci[l][k][k2] * w.rhs[6 + 3 * l + k2];
-      for (int j = 0; j < 6; j++) s -= w.Y[l][k][j] * xb[j];
-      w.sol[lane] = s;
+      real s = rl;
+      for (int j = 0; j < 6; j++) s -= h.Y[l][k][j] * xb[j];
+      out[lane] = scale * s;
     }
     syncwarp();
   }
 
   QS_DEV void copy_M_to_H(real h_damp) {
     for (int e = lane; e < 144; e += 32) {
-      if (e < 36) { const int i = e / 6, j = e % 6; w.Hbb[i][j] = w.Mbb[i][j] + ((i == j) ? h_damp * m.dof_damping[i] : real(0)); }
-      else if (e < 108) { const int q = e - 36; (&w.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
-      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? h_damp * m.dof_damping[6 + 3 * l + k] : real(0)); }
+      if (e < 36) { const int i = e / 6, j = e % 6; w.hes.Hbb[i][j] = w.Mbb[i][j] + ((i == j) ? h_damp * m.dof_damping[i] : real(0)); }
+      else if (e < 108) { const int q = e - 36; (&w.hes.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
+      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.hes.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? h_damp * m.dof_damping[6 + 3 * l + k] : real(0)); }
     }
     syncwarp();
   }
@@ -440,22 +473,29 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
   }
 
-  // store one contact (called by a single lane); frame[0:3] = normal, yhint optional
+  // store one contact (called by a single lane); normal given, yhint optional second-axis guess
   QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, bool world_is_floor) {
-    w.c_dist[slot] = dist; w.c_geom[slot] = g; w.c_body[slot] = m.geom_body[g]; w.c_sign[slot] = sign; w.c_dim[slot] = m.geom_dim[g];
-    real f[9];
+    w.c_dist[slot] = dist; w.c_sign[slot] = sign;
+    w.c_info[slot] = g | (m.geom_body[g] << 8) | (m.geom_dim[g] << 16);
+    real f[6];
     for (int i = 0; i < 3; i++) { w.c_pos[slot][i] = pos[i]; f[i] = normal[i]; f[3 + i] = yhint ? yhint[i] : real(0); }
-    // [MJ] mju_makeFrame
+    // [MJ] mju_makeFrame (third axis = normal x second axis, rebuilt on demand)
     if (dot3(f + 3, f + 3) < real(0.25)) { f[3] = f[4] = f[5] = 0; if (f[1] < real(0.5) && f[1] > real(-0.5)) f[4] = 1; else f[5] = 1; }
     real dd = dot3(f, f + 3);
     for (int i = 0; i < 3; i++) f[3 + i] -= dd * f[i];
-    real inv = real(1) / N::sqrt(dot3(f + 3, f + 3));
+    real inv = N::rsqrt(dot3(f + 3, f + 3));
     for (int i = 0; i < 3; i++) f[3 + i] *= inv;
-    cross3(f + 6, f, f + 3);
-    for (int i = 0; i < 9; i++) w.c_frame[slot][i] = f[i];
+    for (int i = 0; i < 6; i++) w.c_frame[slot][i] = f[i];
     real fri[3];
     contact_friction(g, world_is_floor, fri);
     for (int i = 0; i < 3; i++) w.c_fri[slot][i] = fri[i];
+  }
+  // row k (0 normal, 1, 2 tangents) of the contact frame
+  QS_DEV void frame_row(int c, int k, real* out) const {
+    const real* f = w.c_frame[c];
+    if (k == 0) { out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; }
+    else if (k == 1) { out[0] = f[3]; out[1] = f[4]; out[2] = f[5]; }
+    else cross3(out, f, f + 3);
   }
 
   // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
@@ -468,8 +508,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (g < m.ngeom && m.geom_type[g] != GEOM_MESH) {
       const int b = m.geom_body[g];
       real gx[3], tmp[3];
-      mul_mv(tmp, w.xmat[b], m.geom_pos[g]);
-      for (int i = 0; i < 3; i++) gx[i] = w.xpos[b][i] + tmp[i];
+      mul_mv(tmp, w.kin.xmat[b], m.geom_pos[g]);
+      for (int i = 0; i < 3; i++) gx[i] = w.kin.xpos[b][i] + tmp[i];
       const real margin = m.geom_margin[g];
       const real* sz = m.geom_size[g];
       const int type = m.geom_type[g];
@@ -480,7 +520,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       } else if (type == GEOM_CAPSULE) {
         // capsule axis = third column of (R_body * R_geom)
         real gz[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]}, axis[3];
-        mul_mv(axis, w.xmat[b], gz);
+        mul_mv(axis, w.kin.xmat[b], gz);
         for (int i = 0; i < 3; i++) yh[i] = axis[i];
         for (int s = 1; s >= -1; s -= 2) {
           real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
@@ -490,7 +530,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         }
       } else if (type == GEOM_BOX) {
         real gm[9];
-        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.xmat[b][3 * r] * m.geom_mat[g][c] + w.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.kin.xmat[b][3 * r] * m.geom_mat[g][c] + w.kin.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.kin.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
         for (int i = 0; i < 8; i++) {
           if (nc >= 4) break;
           real v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, corner[3];
@@ -513,14 +553,26 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       ncon += popc(mask);
     }
-    // convex meshes: the whole warp scans the hull vertices of each mesh that passes the bounding-sphere test
-    for (int gm_ = 0; gm_ < m.ngeom; gm_++) {
-      if (m.geom_type[gm_] != GEOM_MESH) continue;
+    // convex meshes. Broad phase: lanes test the body-frame bounding box of every mesh against the plane (a lower bound of the
+    // hull's lowest point, tight for long thin links); only the survivors are scanned, by the whole warp, for their support vertex.
+    unsigned cand;
+    {
+      bool near = false;
+      if (g < m.ngeom && m.geom_type[g] == GEOM_MESH) {
+        const int b = m.geom_body[g];
+        const real* R = w.kin.xmat[b];
+        const real cz = w.kin.xpos[b][2] + R[6] * m.geom_bcenter[g][0] + R[7] * m.geom_bcenter[g][1] + R[8] * m.geom_bcenter[g][2];
+        const real ext = N::abs(R[6]) * m.geom_bhalf[g][0] + N::abs(R[7]) * m.geom_bhalf[g][1] + N::abs(R[8]) * m.geom_bhalf[g][2];
+        near = !(cz - ext > m.geom_margin[g] + real(1e-5));  // slack: the box is only a filter, never the decision
+      }
+      cand = ballot(near);
+    }
+    while (cand) {
+      const int gm_ = ctz(cand);
+      cand &= cand - 1;
       const int b = m.geom_body[gm_];
       const real margin = m.geom_margin[gm_];
-      const real* R = w.xmat[b];
-      const real cz = w.xpos[b][2] + R[6] * m.geom_bcenter[gm_][0] + R[7] * m.geom_bcenter[gm_][1] + R[8] * m.geom_bcenter[gm_][2];
-      if (cz - m.geom_rbound[gm_] > margin) continue;
+      const real* R = w.kin.xmat[b];
       const real dx = -R[6], dy = -R[7], dz = -R[8];  // R^T * (-normal)
       const Vert4<real>* v = vert + m.geom_vertadr[gm_];
       const int nv = m.geom_vertnum[gm_];
@@ -537,8 +589,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       const Vert4<real> p = v[bi];
-      const real pw[3] = {w.xpos[b][0] + R[0] * p.x + R[1] * p.y + R[2] * p.z, w.xpos[b][1] + R[3] * p.x + R[4] * p.y + R[5] * p.z,
-                          w.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};
+      const real pw[3] = {w.kin.xpos[b][0] + R[0] * p.x + R[1] * p.y + R[2] * p.z, w.kin.xpos[b][1] + R[3] * p.x + R[4] * p.y + R[5] * p.z,
+                          w.kin.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};
       const real dist = pw[2];
       if (dist > margin) continue;
       if (lane == 0 && ncon < NCON) {
@@ -568,7 +620,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     return d0 + y * (d1 - d0);
   }
 
-  // selected generalized-velocity-like vector entry for contact-Jacobian column col (0..5 base, 6..8 leg of the contact body)
+  // generalized-velocity index of contact-Jacobian column col (0..5 base, 6..8 leg of the contact body)
   QS_DEV static int col_dof(int body, int col) { return col < 6 ? col : 6 + 3 * ((body - 2) / 3) + (col - 6); }
 
   // [MJ] mj_makeConstraint / mj_makeImpedance / mj_referenceConstraint in "unit" form:
@@ -578,7 +630,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     const int ncon = w.ncon;
     // contact Jacobians: item (c, col)
     for (int it = lane; it < ncon * 9; it += 32) {
-      const int c = it / 9, col = it % 9, body = w.c_body[c], dim = w.c_dim[c];
+      const int c = it / 9, col = it % 9, info = w.c_info[c], body = info_body(info), dim = info_dim(info);
       bool on = col < 6;
       if (!on && body >= 2) on = (col - 6) <= (body - 2) % 3;
       real jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
@@ -590,45 +642,51 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         for (int i = 0; i < 3; i++) { jp[i] = w.cdof[d][3 + i] + cr[i]; jr[i] = w.cdof[d][i]; }
       }
       const real sg = w.c_sign[c];
-      for (int k = 0; k < 3; k++) if (k < dim) w.Jc[c][k][col] = sg * dot3(&w.c_frame[c][3 * k], jp);
-      if (MAXDIM > 3) for (int k = 3; k < MAXDIM; k++) if (k < dim) w.Jc[c][k][col] = sg * dot3(&w.c_frame[c][3 * (k - 3)], jr);
+      for (int k = 0; k < 3; k++) {
+        real fr[3];
+        frame_row(c, k, fr);
+        if (k < dim) w.Jc[c][k][col] = sg * dot3(fr, jp);
+        if (MAXDIM > 3 && 3 + k < dim) w.Jc[c][MAXDIM > 3 ? 3 + k : 0][col] = sg * dot3(fr, jr);
+      }
     }
     // scalar units
     if (lane < NFL) {
       const int d = 6 + lane;
       w.u_D[lane] = m.dof_floss[d] > 0 ? m.dof_D[d] : real(0);
-      w.u_R[lane] = m.dof_R[d];
       w.u_sign[lane] = 1;
       w.u_ar[lane] = -m.dof_B[d] * w.qvel[d];
     } else if (lane < NFL + NLIM) {
       const int j = lane - NFL;
-      real D = 0, R = 1, ar = 0, sign = 0;
+      real D = 0, ar = 0, sign = 0;
       if (m.jnt_limited[j]) {
         const real value = w.qpos[7 + j], dlo = value - m.jnt_range[j][0], dhi = m.jnt_range[j][1] - value, margin = m.jnt_margin[j];
         real pos = 0;
         if (dlo < margin) { sign = 1; pos = dlo; } else if (dhi < margin) { sign = -1; pos = dhi; }
         if (sign != 0) {
           const real imp = impedance(m.jnt_solimp[j], pos - margin);
-          R = N::max(N::minval, (1 - imp) * m.dof_iw[6 + j] / imp);
-          D = 1 / R;
+          D = 1 / N::max(N::minval, (1 - imp) * m.dof_iw[6 + j] / imp);
           ar = -m.jnt_B[j] * (sign * w.qvel[6 + j]) - m.jnt_K[j] * imp * (pos - margin);
         }
       }
-      w.u_D[lane] = D; w.u_R[lane] = R; w.u_sign[lane] = sign; w.u_ar[lane] = ar;
+      w.u_D[lane] = D; w.u_sign[lane] = sign; w.u_ar[lane] = ar;
     }
     syncwarp();
     for (int c = lane; c < ncon; c += 32) {
-      const int g = w.c_geom[c], body = w.c_body[c], dim = w.c_dim[c];
+      const int info = w.c_info[c], g = info_geom(info), body = info_body(info), dim = info_dim(info);
       real velc[MAXDIM];
       for (int k = 0; k < MAXDIM; k++) {
         real s = 0;
-        if (k < dim) for (int col = 0; col < 9; col++) { if (col >= 6 && body < 2) break; s += w.Jc[c][k][col] * w.qvel[col_dof(body, col)]; }
+        if (k < dim) {
+          const real* J = w.Jc[c][k];
+          s = J[0] * w.qvel[0] + J[1] * w.qvel[1] + J[2] * w.qvel[2] + J[3] * w.qvel[3] + J[4] * w.qvel[4] + J[5] * w.qvel[5];
+          if (body >= 2) { const real* xl = w.qvel + 6 + 3 * ((body - 2) / 3); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
+        }
         velc[k] = s;
       }
       const real x = w.c_dist[c] - m.geom_incmargin[g];
       const bool active = w.c_dist[c] < m.geom_incmargin[g];
       const real imp = impedance(m.geom_solimp[g], x);
-      const real tran = m.body_iw[body][0], rot = m.body_iw[body][1];
+      const real tran = m.body_iw[body][0];
       const real K = m.geom_K[g], B = m.geom_B[g];
       const real f0 = w.c_fri[c][0];
       for (int k = 0; k < MAXDIM; k++) { w.c_D[c][k] = 0; w.c_ar[c][k] = -B * velc[k]; }
@@ -653,7 +711,6 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           w.c_D[c][MAXDIM > 4 ? 4 : 0] = 1 / (R1 * f0 * f0 / (f2 * f2));
           w.c_D[c][MAXDIM > 5 ? 5 : 0] = 1 / (R1 * f0 * f0 / (f2 * f2));
         }
-        (void)rot;
       }
     }
     syncwarp();
@@ -663,16 +720,15 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV real fri_k(int c, int k) const { return k <= 2 ? w.c_fri[c][0] : (k == 3 ? w.c_fri[c][1] : w.c_fri[c][2]); }
 
   // ------------------------------------------------------------------ per-unit cost model  [MJ] mj_constraintUpdate
-  // one-sided quadratic row
   QS_DEV static void row_q(real x, real v, real D, real& cost, real& d1, real& d2) {
     if (x < 0) { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
   }
   // scalar unit u at residual x with direction v
   QS_DEV void scalar_unit_eval(int u, real x, real v, real& cost, real& d1, real& d2) const {
     const real D = w.u_D[u];
+    if (D == 0) return;
     if (u < NFL) {
-      const real f = m.dof_floss[6 + u], rf = w.u_R[u] * f;
-      if (D == 0) return;
+      const real f = m.dof_floss[6 + u], rf = N::div(f, D);
       if (x <= -rf) { cost += -f * (real(0.5) * rf + x); d1 += -f * v; }
       else if (x >= rf) { cost += -f * (real(0.5) * rf - x); d1 += f * v; }
       else { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
@@ -680,19 +736,18 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   }
   // contact unit c at contact-frame residual r[] with direction v[]
   QS_DEV void contact_unit_eval(int c, const real* r, const real* v, real& cost, real& d1, real& d2) const {
-    const int dim = w.c_dim[c];
+    const int dim = info_dim(w.c_info[c]);
     const real D0 = w.c_D[c][0];
     if (D0 == 0) return;
     if (dim == 1) { row_q(r[0], v[0], D0, cost, d1, d2); return; }
+    const real mu = w.c_mu[c];
     if (m.cone == 0) {
-      const real mu = w.c_mu[c];
       for (int j = 1; j < 3; j++) {
         row_q(r[0] + mu * r[j], v[0] + mu * v[j], D0, cost, d1, d2);
         row_q(r[0] - mu * r[j], v[0] - mu * v[j], D0, cost, d1, d2);
       }
       return;
     }
-    const real mu = w.c_mu[c];
     const real Nn = r[0] * mu, N1 = v[0] * mu;
     real T2 = 0, UV = 0, VV = 0;
     for (int k = 1; k < MAXDIM; k++) if (k < dim) { const real f = fri_k(c, k), U = r[k] * f, V = v[k] * f; T2 += U * U; UV += U * V; VV += V * V; }
@@ -708,21 +763,23 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     d1 += Dm * NmT * e1;
     d2 += Dm * (e1 * e1 - NmT * mu * T2d);
   }
-  // contact unit c: contact-frame force F and Hessian weight W at residual r; returns cost
+  // contact unit c: contact-frame force F and packed-symmetric Hessian weight Wt at residual r; returns cost
   QS_DEV real contact_unit_update(int c) {
-    const int dim = w.c_dim[c];
-    real* r = w.c_r[c];
+    const int dim = info_dim(w.c_info[c]);
+    const real* r = w.c_r[c];
     real* F = w.c_F[c];
-    for (int a = 0; a < MAXDIM; a++) { F[a] = 0; for (int b = 0; b < MAXDIM; b++) w.c_W[c][a][b] = 0; }
+    real* Wt = w.c_W[c];
+    for (int a = 0; a < MAXDIM; a++) F[a] = 0;
+    for (int a = 0; a < NW; a++) Wt[a] = 0;
     const real D0 = w.c_D[c][0];
     if (D0 == 0) return 0;
     real cost = 0;
     if (dim == 1) {
-      if (r[0] < 0) { F[0] = -D0 * r[0]; w.c_W[c][0][0] = D0; cost = real(0.5) * D0 * r[0] * r[0]; }
+      if (r[0] < 0) { F[0] = -D0 * r[0]; Wt[0] = D0; cost = real(0.5) * D0 * r[0] * r[0]; }
       return cost;
     }
+    const real mu = w.c_mu[c];
     if (m.cone == 0) {
-      const real mu = w.c_mu[c];
       real fe[4], de[4];
       for (int e = 0; e < 4; e++) {
         const real x = r[0] + ((e & 1) ? -mu : mu) * r[1 + e / 2];
@@ -732,14 +789,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         if (act) cost += real(0.5) * D0 * x * x;
       }
       F[0] = fe[0] + fe[1] + fe[2] + fe[3]; F[1] = mu * (fe[0] - fe[1]); F[2] = mu * (fe[2] - fe[3]);
-      w.c_W[c][0][0] = de[0] + de[1] + de[2] + de[3];
-      w.c_W[c][0][1] = w.c_W[c][1][0] = mu * (de[0] - de[1]);
-      w.c_W[c][0][2] = w.c_W[c][2][0] = mu * (de[2] - de[3]);
-      w.c_W[c][1][1] = mu * mu * (de[0] + de[1]);
-      w.c_W[c][2][2] = mu * mu * (de[2] + de[3]);
+      Wt[widx(0, 0)] = de[0] + de[1] + de[2] + de[3];
+      Wt[widx(0, 1)] = mu * (de[0] - de[1]);
+      Wt[widx(0, 2)] = mu * (de[2] - de[3]);
+      Wt[widx(1, 1)] = mu * mu * (de[0] + de[1]);
+      Wt[widx(2, 2)] = mu * mu * (de[2] + de[3]);
       return cost;
     }
-    const real mu = w.c_mu[c];
     real U[MAXDIM], fk[MAXDIM];
     U[0] = r[0] * mu; fk[0] = mu;
     real T2 = 0;
@@ -747,7 +803,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     const real Nn = U[0], T = N::sqrt(T2);
     if (Nn >= mu * T || (T <= 0 && Nn >= 0)) return 0;
     if (mu * Nn + T <= 0 || (T <= 0 && Nn < 0)) {
-      for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; F[k] = -Dk * r[k]; w.c_W[c][k][k] = Dk; cost += real(0.5) * Dk * r[k] * r[k]; }
+      for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; F[k] = -Dk * r[k]; Wt[widx(k, k)] = Dk; cost += real(0.5) * Dk * r[k] * r[k]; }
       return cost;
     }
     const real Dm = D0 / N::max(N::minval, mu * mu * (1 + mu * mu)), NmT = Nn - mu * T;
@@ -757,11 +813,11 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     de[0] = mu;
     for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? -mu * fk[k] * U[k] / T : real(0); if (k < dim) F[k] = -F[0] / T * U[k] * fk[k]; }
     for (int a = 0; a < MAXDIM; a++)
-      for (int b = 0; b < MAXDIM; b++) {
+      for (int b = a; b < MAXDIM; b++) {
         if (a >= dim || b >= dim) continue;
         real h = Dm * de[a] * de[b];
-        if (a > 0 && b > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? 1 / T : real(0)) - U[a] * U[b] / (T * T * T));
-        w.c_W[c][a][b] = h;
+        if (a > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? 1 / T : real(0)) - U[a] * U[b] / (T * T * T));
+        Wt[widx(a, b)] = h;
       }
     return cost;
   }
@@ -774,16 +830,27 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
     const int ncon = w.ncon;
     for (int it = lane; it < ncon * MAXDIM; it += 32) {
-      const int c = it / MAXDIM, k = it % MAXDIM, body = w.c_body[c];
+      const int c = it / MAXDIM, k = it % MAXDIM, info = w.c_info[c], body = info_body(info);
       real s = 0;
-      if (k < w.c_dim[c]) {
-        const int ncol = body < 2 ? 6 : 9;
-        for (int col = 0; col < ncol; col++) s += w.Jc[c][k][col] * x[col_dof(body, col)];
+      if (k < info_dim(info)) {
+        const real* J = w.Jc[c][k];
+        s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
+        if (body >= 2) { const real* xl = x + 6 + 3 * ((body - 2) / 3); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
         if (minus_ar) s -= w.c_ar[c][k];
       }
       out_c[c][k] = s;
     }
     syncwarp();
+  }
+
+  // constraint cost at the current residuals (no side effects); warp-uniform result
+  QS_DEV real units_cost() {
+    real cost = 0, d1 = 0, d2 = 0;
+    if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane], real(0), cost, d1, d2);
+    real zero[MAXDIM];
+    for (int k = 0; k < MAXDIM; k++) zero[k] = 0;
+    for (int c = lane; c < w.ncon; c += 32) contact_unit_eval(c, w.c_r[c], zero, cost, d1, d2);
+    return warp_sum(cost);
   }
 
   // states / forces / weights at the current residuals (w.u_r, w.c_r); returns the constraint cost (warp-uniform)
@@ -795,7 +862,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       real F = 0, Wt = 0;
       if (D != 0) {
         if (u < NFL) {
-          const real f = m.dof_floss[6 + u], rf = w.u_R[u] * f;
+          const real f = m.dof_floss[6 + u], rf = N::div(f, D);
           if (x <= -rf) { F = f; cost = -f * (real(0.5) * rf + x); }
           else if (x >= rf) { F = -f; cost = -f * (real(0.5) * rf - x); }
           else { F = -D * x; Wt = D; cost = real(0.5) * D * x * x; }
@@ -820,13 +887,15 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         const int j = d - 6, l = j / 3, k = j % 3;
         s += w.u_F[j] + w.u_sign[NFL + j] * w.u_F[NFL + j];
         for (int c = 0; c < ncon; c++) {
-          const int body = w.c_body[c];
+          const int info = w.c_info[c], body = info_body(info);
           if (body < 2 || (body - 2) / 3 != l) continue;
-          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.c_F[c][a];
+          for (int a = 0; a < MAXDIM; a++) if (a < info_dim(info)) s += w.Jc[c][a][6 + k] * w.c_F[c][a];
         }
       } else {
-        for (int c = 0; c < ncon; c++)
-          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][d] * w.c_F[c][a];
+        for (int c = 0; c < ncon; c++) {
+          const int dim = info_dim(w.c_info[c]);
+          for (int a = 0; a < MAXDIM; a++) if (a < dim) s += w.Jc[c][a][d] * w.c_F[c][a];
+        }
       }
       w.fcon[d] = s;
       w.grad[d] = w.Ma[d] - w.fsm[d] - s;
@@ -834,48 +903,51 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
   }
 
-  // H = M + J^T W J in block form
+  // H = M + J^T W J in block form.  Only the entries the factorisation reads are produced (lower triangle of the base
+  // block, the full leg-base couplings, lower triangle of the leg blocks).  Contacts are accumulated one after the other;
+  // lane e owns entry (i,j), i>=j, of the contact-local symmetric 9x9 matrix Jc^T W Jc (45 entries -> two passes), so the
+  // same lane always touches the same shared-memory word and no synchronisation is needed between contacts.
   QS_DEV void build_hessian() {
-    const int ncon = w.ncon;
-    for (int it = lane; it < ncon * MAXDIM * 9; it += 32) {
-      const int c = it / (MAXDIM * 9), a = (it / 9) % MAXDIM, col = it % 9;
-      real s = 0;
-      const int dim = w.c_dim[c];
-      if (a < dim) for (int b = 0; b < MAXDIM; b++) if (b < dim) s += w.c_W[c][a][b] * w.Jc[c][b][col];
-      w.Tc[c][a][col] = s;
+    for (int e = lane; e < 144; e += 32) {
+      if (e < 36) { const int i = e / 6, j = e % 6; w.hes.Hbb[i][j] = w.Mbb[i][j]; }
+      else if (e < 108) { const int q = e - 36; (&w.hes.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
+      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.hes.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0)); }
     }
     syncwarp();
-    for (int e = lane; e < 144; e += 32) {
-      if (e < 36) {
-        const int i = e / 6, j = e % 6;
-        real s = w.Mbb[i][j];
-        for (int c = 0; c < ncon; c++) for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][i] * w.Tc[c][a][j];
-        w.Hbb[i][j] = s;
-      } else if (e < 108) {
-        const int q = e - 36, l = q / 18, k = (q % 18) / 6, j = q % 6;
-        real s = w.Mlb[l][k][j];
-        for (int c = 0; c < ncon; c++) {
-          const int body = w.c_body[c];
-          if (body < 2 || (body - 2) / 3 != l) continue;
-          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.Tc[c][a][j];
+    const int ncon = w.ncon;
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
+      const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
+      const real* Wt = w.c_W[c];
+      if (Wt[0] == 0) continue;  // no active row in this contact (W00 sums the active regularisers)
+      const int nloc = body < 2 ? 21 : 45;
+      const int leg = body < 2 ? 0 : (body - 2) / 3;
+#pragma unroll 1
+      for (int e = lane; e < nloc; e += 32) {
+        int i = 0, j = e;
+        while (j > i) { j -= i + 1; i++; }  // e -> (i, j), i >= j
+        real h = 0;
+        if (MAXDIM == 3 && m.cone == 0 && dim == 3) {
+          const real a0 = w.Jc[c][0][i], a1 = w.Jc[c][1][i], a2 = w.Jc[c][2][i], b0 = w.Jc[c][0][j], b1 = w.Jc[c][1][j], b2 = w.Jc[c][2][j];
+          h = Wt[widx(0, 0)] * a0 * b0 + Wt[widx(0, 1)] * (a0 * b1 + a1 * b0) + Wt[widx(0, 2)] * (a0 * b2 + a2 * b0) + Wt[widx(1, 1)] * a1 * b1 +
+              Wt[widx(2, 2)] * a2 * b2;
+        } else {
+          for (int a = 0; a < MAXDIM; a++) {
+            if (a >= dim) break;
+            real t = 0;
+            for (int b = 0; b < MAXDIM; b++) { if (b >= dim) break; t += Wt[widx(a, b)] * w.Jc[c][b][j]; }
+            h += w.Jc[c][a][i] * t;
+          }
         }
-        w.Hlb[l][k][j] = s;
-      } else {
-        const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3;
-        real s = w.Mll[l][k][k2];
-        if (k == k2) { const int j = 3 * l + k; s += w.u_W[j] + w.u_W[NFL + j]; }
-        for (int c = 0; c < ncon; c++) {
-          const int body = w.c_body[c];
-          if (body < 2 || (body - 2) / 3 != l) continue;
-          for (int a = 0; a < MAXDIM; a++) if (a < w.c_dim[c]) s += w.Jc[c][a][6 + k] * w.Tc[c][a][6 + k2];
-        }
-        w.Hll[l][k][k2] = s;
+        if (i < 6) w.hes.Hbb[i][j] += h;
+        else if (j < 6) w.hes.Hlb[leg][i - 6][j] += h;
+        else w.hes.Hll[leg][i - 6][j - 6] += h;
       }
     }
     syncwarp();
   }
 
-  struct LsPoint { real cost, d1, d2; };
+  struct LsPoint { real alpha, cost, d1, d2; };
 
   // cost and derivatives along qacc + alpha*search (warp-uniform result)
   QS_DEV LsPoint ls_eval(real alpha, real qg0, real qg1, real qg2) {
@@ -888,128 +960,139 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       contact_unit_eval(c, r, w.c_v[c], cost, d1, d2);
     }
     LsPoint p;
+    p.alpha = alpha;
     p.cost = warp_sum(cost) + alpha * alpha * qg2 + alpha * qg1 + qg0;
     p.d1 = warp_sum(d1) + 2 * alpha * qg2 + qg1;
     p.d2 = warp_sum(d2) + 2 * qg2;
     return p;
   }
 
+  // [MJ] PrimalSearch: exact line search by safeguarded 1-D Newton with bracketing.  Written as a state machine around a
+  // single evaluation site to keep the code footprint (and I-cache pressure) small.
+  //   state 0: value at 0; 1: first Newton point; 2: one-sided Newton until the derivative changes sign; 3: bracketed
+  //   refinement with Newton steps from both ends plus the midpoint.
+  QS_DEV real line_search(real gtol, real qg0, real qg1, real qg2) {
+    constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);
+    int state = 0, it = 0, dir = 1, ci = 3;
+    real a = 0;
+    LsPoint p0{}, p1{}, p2{}, lo{}, hi{};
+    real cand[3] = {0, 0, 0};
+    bool moved = true;
+    const int ls_iter = m.ls_iterations;
+    for (;;) {
+      const LsPoint p = ls_eval(a, qg0, qg1, qg2);
+      ls_evals++;
+      if (state == 0) {
+        p0 = p;
+        // the slope cannot be resolved below a few ulps of its initial magnitude in this precision
+        gtol = N::max(gtol, kNoise * N::abs(p.d1));
+        a = -N::div(p.d1, p.d2);
+        state = 1;
+        continue;
+      }
+      if (state == 1) {
+        p1 = (p0.cost < p.cost) ? p0 : p;
+        if (N::abs(p1.d1) < gtol) return p1.alpha;
+        dir = p1.d1 < 0 ? 1 : -1;
+        p2 = p1;
+        state = 2;
+      } else if (state == 2) {
+        p2 = p1; p1 = p; it++;
+        if (N::abs(p1.d1) < gtol) return p1.alpha;
+      } else {
+        it++;
+        if (N::abs(p.d1) < gtol) return p.alpha;
+        if ((p.d1 < 0) == (lo.d1 < 0)) lo = p; else hi = p;
+        moved = true;
+      }
+      if (state == 2) {
+        if (p1.d1 * dir <= -gtol && it < ls_iter) { a = p1.alpha - N::div(p1.d1, p1.d2); continue; }
+        if (it >= ls_iter) return p1.alpha;
+        lo = p2; hi = p1; state = 3; ci = 3; moved = true;
+      }
+      bool have = false;
+      while (!have) {
+        if (ci >= 3) {
+          if (!moved || it >= ls_iter) return lo.cost < hi.cost ? lo.alpha : hi.alpha;
+          cand[0] = lo.alpha - N::div(lo.d1, lo.d2); cand[1] = hi.alpha - N::div(hi.d1, hi.d2); cand[2] = real(0.5) * (lo.alpha + hi.alpha);
+          ci = 0;
+          moved = false;
+        }
+        const real c = cand[ci++];
+        if ((c > lo.alpha && c < hi.alpha) || (c < lo.alpha && c > hi.alpha)) { a = c; have = true; }
+      }
+    }
+  }
+
   // [MJ] mj_fwdConstraint + mj_solNewton
   QS_DEV void solve(int max_iter, real tol) {
     // qacc_smooth = M^-1 qfrc_smooth
     copy_M_to_H(real(0));
-    factor_H();
-    if (lane < NV) w.rhs[lane] = w.fsm[lane];
-    syncwarp();
-    solve_H();
-    if (lane < NV) w.asmooth[lane] = w.sol[lane];
-    syncwarp();
+    factor_H(w, lane);
+    solve_H(w, lane, w.fsm, w.asmooth, real(1));
     // warm start: cheaper of qacc_warmstart and qacc_smooth
-    real cost_w, cost_s;
+    units_Jx(w.warm, w.u_r, w.c_r, true);
+    real cost_w = units_cost();
     {
-      units_Jx(w.warm, w.u_r, w.c_r, true);
-      real cc = units_update();
-      real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.warm);
-      real g = (lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.warm[lane] - w.asmooth[lane]) : real(0);
-      cost_w = cc + warp_sum(g);
-      units_Jx(w.asmooth, w.u_r, w.c_r, true);
-      cost_s = units_update();
+      const real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.warm);
+      cost_w += warp_sum((lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.warm[lane] - w.asmooth[lane]) : real(0));
     }
+    units_Jx(w.asmooth, w.u_r, w.c_r, true);
+    const real cost_s = units_cost();
     const bool use_warm = cost_w < cost_s;
     if (lane < NV) w.qacc[lane] = use_warm ? w.warm[lane] : w.asmooth[lane];
     syncwarp();
     if (use_warm) units_Jx(w.qacc, w.u_r, w.c_r, true);
-    real ccost = use_warm ? units_update() : cost_s;
-    real gauss;
     {
-      real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+      const real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
       if (lane < NV) w.Ma[lane] = ma;
-      gauss = warp_sum((lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
     }
-    real cost = gauss + ccost;
     syncwarp();
-    constraint_force_and_grad();
     const real scale = real(1) / (m.meaninertia * NV);
     int iter = 0;
+    real cost = 0, oldcost = 0;
     solver_maxed = false;
     while (true) {
+      // cost, forces, gradient at the current point
+      const real ccost = units_update();
+      const real gauss = warp_sum((lane < NV) ? real(0.5) * (w.Ma[lane] - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
+      oldcost = cost;
+      cost = gauss + ccost;
+      constraint_force_and_grad();
+      if (iter > 0) {
+        // [MJ] stop on small scaled improvement or gradient; in addition stop when either is below what this precision can
+        // resolve (a few ulps of the cost / of the force balance) -- otherwise fp32 rounding noise of random sign keeps the
+        // loop alive with ~50% probability per iteration.
+        constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);    // ~16 ulp: force-balance residual floor
+        constexpr real kNoiseCost = sizeof(real) == 4 ? real(1e-7) : real(1e-15);  // ~2 ulp: cost did not move at all
+        const real gn2 = warp_sum((lane < NV) ? w.grad[lane] * w.grad[lane] : real(0));
+        const real fn2 = warp_sum((lane < NV) ? w.Ma[lane] * w.Ma[lane] + w.fsm[lane] * w.fsm[lane] + w.fcon[lane] * w.fcon[lane] : real(0));
+        const real imp = oldcost - cost;
+        if (scale * imp < tol || imp < kNoiseCost * (N::abs(cost) + N::abs(oldcost))) break;
+        if (scale * scale * gn2 < tol * tol || gn2 < kNoise * kNoise * fn2) break;
+      }
       if (iter >= max_iter) { solver_maxed = true; break; }
       // Newton direction
       build_hessian();
-      factor_H();
-      if (lane < NV) w.rhs[lane] = w.grad[lane];
-      syncwarp();
-      solve_H();
-      if (lane < NV) w.search[lane] = -w.sol[lane];
-      syncwarp();
-      // ---- exact line search, [MJ] PrimalSearch
-      real sn = (lane < NV) ? w.search[lane] * w.search[lane] : real(0);
-      const real snorm = N::sqrt(warp_sum(sn));
+      factor_H(w, lane);
+      solve_H(w, lane, w.grad, w.search, real(-1));
+      // exact line search
+      const real snorm = N::sqrt(warp_sum((lane < NV) ? w.search[lane] * w.search[lane] : real(0)));
       if (snorm < N::minval) break;
       const real gtol = tol * m.ls_tolerance * snorm / scale;
-      real mv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.search);
+      const real mv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.search);
       if (lane < NV) w.Mv[lane] = mv;
       units_Jx(w.search, w.u_v, w.c_v, false);
-      const real qg0 = gauss;
       const real qg1 = warp_sum((lane < NV) ? w.search[lane] * (w.Ma[lane] - w.fsm[lane]) : real(0));
       const real qg2 = warp_sum((lane < NV) ? real(0.5) * w.search[lane] * mv : real(0));
-      real alpha = 0;
-      {
-        LsPoint p0 = ls_eval(0, qg0, qg1, qg2);
-        real a1 = -p0.d1 / p0.d2;
-        LsPoint p1 = ls_eval(a1, qg0, qg1, qg2);
-        if (p0.cost < p1.cost) { p1 = p0; a1 = 0; }
-        bool done = N::abs(p1.d1) < gtol;
-        alpha = a1;
-        if (!done) {
-          const int dir = p1.d1 < 0 ? 1 : -1;
-          int it = 0;
-          LsPoint p2 = p1;
-          real a2 = a1;
-          while (p1.d1 * dir <= -gtol && it < m.ls_iterations) {
-            p2 = p1; a2 = a1;
-            a1 = a1 - p1.d1 / p1.d2;
-            p1 = ls_eval(a1, qg0, qg1, qg2);
-            it++;
-            if (N::abs(p1.d1) < gtol) { done = true; break; }
-          }
-          alpha = a1;
-          if (!done && it < m.ls_iterations) {
-            real lo = a2, hi = a1;
-            LsPoint plo = p2, phi = p1;
-            bool found = false;
-            while (it < m.ls_iterations && !found) {
-              const real cand[3] = {lo - plo.d1 / plo.d2, hi - phi.d1 / phi.d2, real(0.5) * (lo + hi)};
-              bool moved = false;
-              for (int q = 0; q < 3; q++) {
-                const real a = cand[q];
-                if (!((a > lo && a < hi) || (a < lo && a > hi))) continue;
-                LsPoint p = ls_eval(a, qg0, qg1, qg2);
-                it++;
-                if (N::abs(p.d1) < gtol) { alpha = a; found = true; break; }
-                if ((p.d1 < 0) == (plo.d1 < 0)) { lo = a; plo = p; } else { hi = a; phi = p; }
-                moved = true;
-              }
-              if (!moved) break;
-            }
-            if (!found) alpha = plo.cost < phi.cost ? lo : hi;
-          }
-        }
-      }
+      const real alpha = line_search(gtol, gauss, qg1, qg2);
       if (alpha == 0) break;
-      // ---- move
+      // move
       if (lane < NV) { w.qacc[lane] += alpha * w.search[lane]; w.Ma[lane] += alpha * w.Mv[lane]; }
       if (lane < NFL + NLIM) w.u_r[lane] += alpha * w.u_v[lane];
       for (int it2 = lane; it2 < w.ncon * MAXDIM; it2 += 32) (&w.c_r[0][0])[it2] += alpha * (&w.c_v[0][0])[it2];
       syncwarp();
-      const real oldcost = cost;
-      ccost = units_update();
-      gauss = warp_sum((lane < NV) ? real(0.5) * (w.Ma[lane] - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
-      cost = gauss + ccost;
-      constraint_force_and_grad();
       iter++;
-      const real gn = N::sqrt(warp_sum((lane < NV) ? w.grad[lane] * w.grad[lane] : real(0)));
-      if (scale * (oldcost - cost) < tol || scale * gn < tol) break;
     }
     solver_iter = iter;
   }
@@ -1017,13 +1100,12 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // accelerometer / gyro at the IMU site. [MJ] mj_rnePostConstraint + mj_objectAcceleration
   QS_DEV void sensors() {
     if (lane == 0) {
-      real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-      for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.cdofdot[d][i] * w.qvel[d] + w.cdof[d][i] * w.qacc[d];
-      const real* cv = w.cvel[1];
-      real spos[3], tmp[3], R[9];
-      mul_mv(tmp, w.xmat[1], m.imu_pos);
-      for (int i = 0; i < 3; i++) spos[i] = w.xpos[1][i] + tmp[i] - w.com[i];
-      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = w.xmat[1][3 * r] * m.imu_mat[c] + w.xmat[1][3 * r + 1] * m.imu_mat[3 + c] + w.xmat[1][3 * r + 2] * m.imu_mat[6 + c];
+      const real* st = w.sens_tmp;
+      real cv[6], ca[6];
+      for (int i = 0; i < 6; i++) { cv[i] = st[i]; ca[i] = st[6 + i]; }
+      for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.cdof[d][i] * w.qacc[d];
+      const real* spos = st + 12;
+      const real* R = st + 15;
       real vl[3], al[3], c1[3];
       cross3(c1, cv, spos);
       for (int i = 0; i < 3; i++) vl[i] = cv[3 + i] + c1[i];
@@ -1037,27 +1119,35 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
   }
 
-  // forward dynamics up to the solver acceleration ("mj_forward")
-  QS_DEV void forward(int max_iter, real tol) {
+  // position-dependent half of the forward pass (body poses stay valid in w.kin until forward_dynamics starts the solver)
+  QS_DEV void forward_position() {
     kinematics();
     com_inertia();
-    cdof_and_mass();
+    cdof();
     collide_floor();
+  }
+  // velocity / force half: bias, mass matrix, constraints, solver
+  QS_DEV void forward_dynamics(int max_iter, real tol) {
     bias_and_smooth();
+    mass_matrix();
     make_constraints();
     solve(max_iter, tol);
     if (m.has_imu) sensors();
+  }
+  QS_DEV void forward(int max_iter, real tol) {
+    forward_position();
+    forward_dynamics(max_iter, tol);
   }
 
   // [MJ] mj_Euler with implicit joint damping. org = internal-frame origin for the fp64 base position.
   QS_DEV void integrate(double* base64) {
     const real h = m.timestep;
     copy_M_to_H(h);
-    factor_H();
-    if (lane < NV) w.rhs[lane] = w.fsm[lane] + w.fcon[lane];
+    factor_H(w, lane);
+    if (lane < NV) w.grad[lane] = w.fsm[lane] + w.fcon[lane];
     syncwarp();
-    solve_H();
-    if (lane < NV) w.qvel[lane] += h * w.sol[lane];
+    solve_H(w, lane, w.grad, w.search, real(1));
+    if (lane < NV) w.qvel[lane] += h * w.search[lane];
     syncwarp();
     if (lane < 3) {
       const double p = (lane < 2 ? w.org[lane] : 0.0) + double(w.qpos[lane]) + double(h) * double(w.qvel[lane]);
@@ -1088,7 +1178,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV Flags flags() const {
     unsigned cm = 0, im = 0;
     for (int c = lane; c < w.ncon; c += 32) {
-      const int b = w.c_body[c];
+      const int b = info_body(w.c_info[c]);
       if (b >= 2 && (b - 2) % 3 == 2) cm |= 1u << ((b - 2) / 3); else im |= 1u << b;
     }
     for (int o = 16; o > 0; o >>= 1) { cm |= shfl_xor(cm, o); im |= shfl_xor(im, o); }
@@ -1101,6 +1191,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   // Packs the 227 ALL_OBS scalars into w.obs (layout: SURVEY.md section 8a). Mixed time levels as in the reference
   // (App. B.1): qpos/qvel are post-integration, foot positions / Jacobians / contacts / qacc / M are from the forward pass.
+  // w.obs recycles the contact-Jacobian storage, so this must be the last consumer of the solver state.
   QS_DEV void pack_obs(const real* command, unsigned contact_mask) {
     real q[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]}, R[9];
     quat_normalize(q);
@@ -1114,6 +1205,11 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     const real* wb = w.qvel + 3;
     real* o = w.obs;
     const real ox = real(w.org[0]), oy = real(w.org[1]);
+    // kinetic energy / work first: they need nothing from the recycled region
+    const real mvv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qvel), maa = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+    const real ke = warp_sum((lane < NV) ? real(0.5) * w.qvel[lane] * mvv : real(0));
+    const real wk = warp_sum((lane < NV) ? maa * w.qvel[lane] : real(0));
+    syncwarp();
     if (lane == 0) {
       real t[3], t2[3];
       o[0] = real(w.org[0] + double(w.qpos[0])); o[1] = real(w.org[1] + double(w.qpos[1])); o[2] = w.qpos[2];
@@ -1131,18 +1227,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int i = 0; i < 3; i++) { o[43 + i] = t[i]; o[46 + i] = wb[i]; }
       mul_mtv(t, R, wref);
       for (int i = 0; i < 3; i++) o[49 + i] = t[i] - wb[i];
+      o[125] = ke; o[126] = wk;
     }
     if (lane < NQ) o[52 + lane] = (lane < 2) ? real(w.org[lane] + double(w.qpos[lane])) : w.qpos[lane];
     if (lane < NV) o[71 + lane] = w.qvel[lane];
     if (lane < NU) { o[89 + lane] = w.ctrl[lane]; o[101 + lane] = w.qpos[7 + lane]; o[113 + lane] = w.qvel[6 + lane]; }
-    {
-      const real mvv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qvel), maa = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
-      const real ke = warp_sum((lane < NV) ? real(0.5) * w.qvel[lane] * mvv : real(0));
-      const real wk = warp_sum((lane < NV) ? maa * w.qvel[lane] : real(0));
-      if (lane == 0) { o[125] = ke; o[126] = wk; }
-    }
-    if (lane < 4) {
-      const int l = lane;
+    if (lane >= 4 && lane < 8) {
+      const int l = lane - 4;
       real cv6[6] = {0, 0, 0, 0, 0, 0};
       for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d];
       for (int k = 0; k < 3; k++) { const int d = 6 + 3 * l + k; for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d]; }
@@ -1162,12 +1253,18 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       mul_mtv(t, R, fr);
       for (int i = 0; i < 3; i++) o[187 + 3 * l + i] = t[i];
       o[199 + l] = (contact_mask >> l) & 1u ? real(1) : real(0);
-      real cf[3] = {0, 0, 0};
+    }
+    if (lane >= 8 && lane < 12) {
+      const int l = lane - 8;
+      real cf[3] = {0, 0, 0}, t[3];
       for (int c = 0; c < w.ncon; c++) {
-        if (w.c_body[c] != 4 + 3 * l) continue;
-        const int dim = w.c_dim[c];
+        const int info = w.c_info[c];
+        if (info_body(info) != 4 + 3 * l) continue;
+        const int dim = info_dim(info);
         const real F0 = w.c_F[c][0], F1 = dim > 1 ? w.c_F[c][1] : real(0), F2 = dim > 1 ? w.c_F[c][2] : real(0);
-        for (int i = 0; i < 3; i++) cf[i] += w.c_frame[c][i] * F0 + w.c_frame[c][3 + i] * F1 + w.c_frame[c][6 + i] * F2;
+        real t2[3];
+        cross3(t2, w.c_frame[c], w.c_frame[c] + 3);
+        for (int i = 0; i < 3; i++) cf[i] += w.c_frame[c][i] * F0 + w.c_frame[c][3 + i] * F1 + t2[i] * F2;
       }
       mul_mtv(t, R, cf);
       for (int i = 0; i < 3; i++) { o[203 + 3 * l + i] = cf[i]; o[215 + 3 * l + i] = t[i]; }

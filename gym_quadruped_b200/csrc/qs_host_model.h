@@ -46,7 +46,8 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   for (int b = 0; b < QS_NBODY; b++) {
     mass += s.body_mass[b];
     for (int i = 0; i < 3; i++) { d.body_pos[b][i] = real(s.body_pos[b][i]); d.body_ipos[b][i] = real(s.body_ipos[b][i]); d.body_inertia[b][i] = real(s.body_inertia[b][i]); }
-    for (int i = 0; i < 4; i++) { d.body_quat[b][i] = real(s.body_quat[b][i]); d.body_iquat[b][i] = real(s.body_iquat[b][i]); }
+    for (int i = 0; i < 4; i++) d.body_quat[b][i] = real(s.body_quat[b][i]);
+    { double m9[9]; quat2mat(s.body_iquat[b], m9); for (int i = 0; i < 9; i++) d.body_imat[b][i] = real(m9[i]); }
     d.body_mass[b] = real(s.body_mass[b]);
     d.body_iw[b][0] = real(s.body_invweight0[b][0]); d.body_iw[b][1] = real(s.body_invweight0[b][1]);
     const int expect = b <= 1 ? 0 : ((b - 2) % 3 == 0 ? 1 : b - 1);
@@ -54,7 +55,10 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   }
   d.mass_total = real(mass);
   for (int j = 0; j < QS_NJNT; j++) {
-    for (int i = 0; i < 3; i++) { d.jnt_pos[j][i] = real(s.jnt_pos[j][i]); d.jnt_axis[j][i] = real(s.jnt_axis[j][i]); }
+    for (int i = 0; i < 3; i++) {
+      if (s.jnt_pos[j][i] != 0.0) return "joint anchors offset from the body origin (jnt_pos != 0) are not supported";
+      d.jnt_pos[j][i] = real(s.jnt_pos[j][i]); d.jnt_axis[j][i] = real(s.jnt_axis[j][i]);
+    }
     d.jnt_range[j][0] = real(s.jnt_range[j][0]); d.jnt_range[j][1] = real(s.jnt_range[j][1]);
     double K, B;
     if (s.jnt_solref[j][0] <= 0) return "direct (negative) solref not supported";
@@ -100,6 +104,12 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
       d.geom_fri[g][i] = real(gp.friction[i]);
     }
     d.geom_rbound[g] = real(s.geom_rbound[g]);
+    if (t == QS_GEOM_MESH) {  // body-frame bounding box of the hull (broad phase)
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int v = s.geom_vertadr[g]; v < s.geom_vertadr[g] + s.geom_vertnum[g]; v++)
+        for (int i = 0; i < 3; i++) { lo[i] = std::min(lo[i], s.vert[3 * v + i]); hi[i] = std::max(hi[i], s.vert[3 * v + i]); }
+      for (int i = 0; i < 3; i++) { d.geom_bcenter[g][i] = real(0.5 * (lo[i] + hi[i])); d.geom_bhalf[g][i] = real(0.5 * (hi[i] - lo[i]) * (1 + 1e-6) + 1e-9); }
+    }
     // mj_contactParam against a default-parameter world geom
     double solref[2], solimp[5];
     int dim;

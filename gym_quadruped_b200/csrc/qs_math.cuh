@@ -10,12 +10,14 @@
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define QS_DEV __device__ __forceinline__
+#define QS_NOINLINE __device__ __noinline__
 namespace qs {
 QS_DEV void syncwarp() { __syncwarp(); }
 template <typename T> QS_DEV T shfl_xor(T v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 template <typename T> QS_DEV T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 QS_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 QS_DEV int popc(unsigned x) { return __popc(x); }
+QS_DEV int ctz(unsigned x) { return __ffs(int(x)) - 1; }
 QS_DEV uint32_t umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 }  // namespace qs
 #else
@@ -29,7 +31,17 @@ namespace qs {
 template <typename T> struct Num;
 template <> struct Num<float> {
   static QS_DEV float sqrt(float x) { return sqrtf(x); }
+#if defined(__CUDA_ARCH__)
+  // fp32 product path: MUFU-based reciprocal / rsqrt (<= 2 ulp) instead of the IEEE division subroutine; the fp64
+  // instantiation (parity build) and the host emulator keep exact division.
+  static QS_DEV float rsqrt(float x) { return rsqrtf(x); }
+  static QS_DEV float rcp(float x) { return __fdividef(1.0f, x); }
+  static QS_DEV float div(float a, float b) { return __fdividef(a, b); }
+#else
   static QS_DEV float rsqrt(float x) { return 1.0f / sqrtf(x); }
+  static QS_DEV float rcp(float x) { return 1.0f / x; }
+  static QS_DEV float div(float a, float b) { return a / b; }
+#endif
   static QS_DEV void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
   static QS_DEV float atan2(float y, float x) { return atan2f(y, x); }
   static QS_DEV float asin(float x) { return asinf(x); }
@@ -44,6 +56,8 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static QS_DEV double sqrt(double x) { return ::sqrt(x); }
   static QS_DEV double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static QS_DEV double rcp(double x) { return 1.0 / x; }
+  static QS_DEV double div(double a, double b) { return a / b; }
   static QS_DEV void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
   static QS_DEV double atan2(double y, double x) { return ::atan2(y, x); }
   static QS_DEV double asin(double x) { return ::asin(x); }

@@ -32,7 +32,7 @@ constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_
 struct KParams {
   const void* dm;      // DModel<real>
   const void* vert;    // Vert4<real>[nvert]
-  int num_envs, obs_dim, use_imu, max_iter, env_id_offset;
+  int num_envs, obs_dim, use_imu, max_iter, env_id_offset, auto_reset;
   float tol;
   unsigned seed_lo, seed_hi;
   float imu_an, imu_gn, imu_abr, imu_gbr;
@@ -87,8 +87,13 @@ template <typename real> __device__ __forceinline__ void euler_to_quat(real roll
   q[0] = cr * cp * cy + sr * sp * sy; q[1] = sr * cp * cy - cr * sp * sy; q[2] = cr * sp * cy + sr * cp * sy; q[3] = cr * cp * sy - sr * sp * cy;
 }
 
+// Threads per CTA: 28 warps of fp32 envs share one SM (single wave for 4096 envs on 148 SMs, 72 registers/thread);
+// the fp64 parity build of the same kernel runs 8 warps per CTA.
+template <typename real> struct LaunchCfg { static constexpr int kMaxWarps = 28; };
+template <> struct LaunchCfg<double> { static constexpr int kMaxWarps = 8; };
+
 template <typename real, int NCON, int MAXDIM, int MODE>
-__global__ void __launch_bounds__(256) env_kernel(const KParams p) {
+__global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(const KParams p) {
   using W = WS<real, NCON, MAXDIM>;
   using DM = DModel<real>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -139,217 +144,243 @@ __global__ void __launch_bounds__(256) env_kernel(const KParams p) {
 
   Env<real, NCON, MAXDIM> e(m, w, reinterpret_cast<const Vert4<real>*>(p.vert), lane);
   const unsigned env_g = unsigned(env + p.env_id_offset);
-  unsigned status = 0;
   real command[4] = {real(B.command[4 * env]), real(B.command[4 * env + 1]), real(B.command[4 * env + 2]), real(B.command[4 * env + 3])};
+  float sim_time = B.sim_time[env];
+  int step_count = B.step_count[env];
 
-  if (MODE == MODE_RESET) {
-    const QsResetOptions& ro = p.ro;
-    const unsigned ep = p.episode[env];
-    real* u = w.obs;  // scratch for the uniforms (obs is packed at the very end)
-    if (lane < 10) {
-      uint32_t r[4];
-      philox4x32(env_g, ep, unsigned(lane), 0x5EEDu, p.seed_lo, p.seed_hi, r);
-      for (int i = 0; i < 4; i++) u[4 * lane + i] = real(u32_to_unit(r[i]));
-      if (lane == 9) {  // two 53-bit uniforms for the fp64 base xy
-        double ux = (double(r[0]) * 4294967296.0 + double(r[1])) * (1.0 / 18446744073709551616.0);
-        double uy = (double(r[2]) * 4294967296.0 + double(r[3])) * (1.0 / 18446744073709551616.0);
-        w.tmpd[0] = ux; w.tmpd[1] = uy;
-      }
-    }
-    syncwarp();
-    if (!given_state) {
-      if (lane < NQ) w.qpos[lane] = m.key_qpos[lane];
-      if (lane < NV) w.qvel[lane] = 0;
-      syncwarp();
-      double bx = double(m.key_qpos[0]), by = double(m.key_qpos[1]);
-      if (ro.randomize) {
-        if (lane < NJ) {
-          w.qpos[7 + lane] += real(-ro.angle_sweep + 2 * ro.angle_sweep * double(u[lane]));
-          w.qvel[6 + lane] += real(-ro.vel_sweep + 2 * ro.vel_sweep * double(u[12 + lane]));
-        }
-        // np.random.uniform(limits[0], limits[1]) = lo + (hi - lo) * u with lo = x_max, hi = x_min (quadruped_env.py:352-356)
-        bx = double(m.terrain_limits[0]) + (double(m.terrain_limits[1]) - double(m.terrain_limits[0])) * w.tmpd[0];
-        by = double(m.terrain_limits[2]) + (double(m.terrain_limits[3]) - double(m.terrain_limits[2])) * w.tmpd[1];
-        if (lane == 0) {
-          const real roll = real(-ro.roll_sweep + 2 * ro.roll_sweep * double(u[24])), pitch = real(-ro.pitch_sweep + 2 * ro.pitch_sweep * double(u[25]));
-          const real yaw = real(atan2(-by, -bx));  // angle_between_vectors(xy, 0) math_utils.py:50-51
-          real q[4];
-          euler_to_quat(roll, pitch, yaw, q);
-          for (int i = 0; i < 4; i++) w.qpos[3 + i] = q[i];
-          w.qpos[2] = real(ro.hip_height);
+  // One pass = one "mj_step" with its env-side bookkeeping.  A reset is the same pass preceded by state sampling and the
+  // lift loop; MODE_STEP with auto_reset runs a second (reset) pass for envs that just terminated, in the same warp.
+  bool resetting = (MODE == MODE_RESET);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    unsigned status = 0;
+    real u_late[4] = {0, 0, 0, 0};
+    if (MODE != MODE_FORWARD && resetting) {
+      const QsResetOptions& ro = p.ro;
+      const unsigned ep = p.episode[env];
+      real* u = w.obs;  // scratch for the uniforms (this storage is recycled by the solver later on)
+      if (lane < 10) {
+        uint32_t r[4];
+        philox4x32(env_g, ep, unsigned(lane), 0x5EEDu, p.seed_lo, p.seed_hi, r);
+        for (int i = 0; i < 4; i++) u[4 * lane + i] = real(u32_to_unit(r[i]));
+        if (lane == 9) {  // two 53-bit uniforms for the fp64 base xy
+          w.tmpd[0] = (double(r[0]) * 4294967296.0 + double(r[1])) * (1.0 / 18446744073709551616.0);
+          w.tmpd[1] = (double(r[2]) * 4294967296.0 + double(r[3])) * (1.0 / 18446744073709551616.0);
         }
       }
       syncwarp();
-      if (lane == 0) {
-        const double ox = flat ? rint(bx) : 0.0, oy = flat ? rint(by) : 0.0;
-        w.org[0] = ox; w.org[1] = oy;
-        w.qpos[0] = real(bx - ox); w.qpos[1] = real(by - oy);
-      }
-      syncwarp();
-      // lift until no foot (calf-body) contact, quadruped_env.py:376-388
-      bool cleared = false;
-      for (int c = 0; c <= 100; c++) {
-        e.kinematics();
-        e.collide_floor();
-        real pen = 0;
-        bool any = false;
-        for (int k = lane; k < w.ncon; k += 32) {
-          const int bdy = w.c_body[k];
-          if (bdy >= 2 && (bdy - 2) % 3 == 2) { any = true; pen = Num<real>::max(pen, Num<real>::abs(w.c_dist[k])); }
-        }
-        any = qs::ballot(any) != 0;
-        pen = warp_max(pen);
-        if (!any) { cleared = true; break; }
-        if (c == 100) break;
-        if (lane == 0) w.qpos[2] += pen * real(1.1);
+      for (int i = 0; i < 4; i++) u_late[i] = u[26 + i];  // consumed after the step
+      if (!given_state) {
+        const real dq = (lane < NJ && ro.randomize) ? real(-ro.angle_sweep + 2 * ro.angle_sweep * double(u[lane])) : real(0);
+        const real dv = (lane < NJ && ro.randomize) ? real(-ro.vel_sweep + 2 * ro.vel_sweep * double(u[12 + lane])) : real(0);
+        const real roll = real(-ro.roll_sweep + 2 * ro.roll_sweep * double(u[24])), pitch = real(-ro.pitch_sweep + 2 * ro.pitch_sweep * double(u[25]));
         syncwarp();
+        if (lane < NQ) w.qpos[lane] = m.key_qpos[lane];
+        if (lane < NV) w.qvel[lane] = 0;
+        syncwarp();
+        double bx = double(m.key_qpos[0]), by = double(m.key_qpos[1]);
+        if (ro.randomize) {
+          if (lane < NJ) { w.qpos[7 + lane] += dq; w.qvel[6 + lane] += dv; }
+          // np.random.uniform(limits[0], limits[1]) = lo + (hi - lo) * u with lo = x_max, hi = x_min (quadruped_env.py:352-356)
+          bx = double(m.terrain_limits[0]) + (double(m.terrain_limits[1]) - double(m.terrain_limits[0])) * w.tmpd[0];
+          by = double(m.terrain_limits[2]) + (double(m.terrain_limits[3]) - double(m.terrain_limits[2])) * w.tmpd[1];
+          if (lane == 0) {
+            const real yaw = real(atan2(-by, -bx));  // angle_between_vectors(xy, 0) math_utils.py:50-51
+            real q[4];
+            euler_to_quat(roll, pitch, yaw, q);
+            for (int i = 0; i < 4; i++) w.qpos[3 + i] = q[i];
+            w.qpos[2] = real(ro.hip_height);
+          }
+        }
+        syncwarp();
+        if (lane == 0) {
+          const double ox = flat ? rint(bx) : 0.0, oy = flat ? rint(by) : 0.0;
+          w.org[0] = ox; w.org[1] = oy;
+          w.qpos[0] = real(bx - ox); w.qpos[1] = real(by - oy);
+        }
+        syncwarp();
+        // lift until no foot (calf-body) contact, quadruped_env.py:376-388
+        bool cleared = false;
+#pragma unroll 1
+        for (int c = 0; c <= 100; c++) {
+          e.kinematics();
+          e.collide_floor();
+          real pen = 0;
+          bool any = false;
+          for (int k = lane; k < w.ncon; k += 32) {
+            const int bdy = (w.c_info[k] >> 8) & 0xff;
+            if (bdy >= 2 && (bdy - 2) % 3 == 2) { any = true; pen = Num<real>::max(pen, Num<real>::abs(w.c_dist[k])); }
+          }
+          any = qs::ballot(any) != 0;
+          pen = warp_max(pen);
+          if (!any) { cleared = true; break; }
+          if (c == 100) break;
+          if (lane == 0) w.qpos[2] += pen * real(1.1);
+          syncwarp();
+        }
+        if (!cleared) status |= 8u;
       }
-      if (!cleared) status |= 8u;
-    } else {
-      if (lane == 0) { /* state taken verbatim, :389-391 */ }
+      // zero ctrl / applied wrench / warm start / clock (quadruped_env.py:332-335, :394-395)
+      if (lane < NV) w.warm[lane] = 0;
+      if (lane < NU) w.ctrl[lane] = 0;
+      if (lane < 6) w.applied[lane] = 0;
+      sim_time = 0.f;
+      syncwarp();
     }
-    if (lane < NV) w.warm[lane] = 0;
+
+    // ---- forward dynamics
+    e.forward_position();
+    if (MODE == MODE_FORWARD && p.aux) {
+      float* a = p.aux + size_t(env) * AUX_STRIDE;  // body poses are only valid until the solver recycles their storage
+      for (int it = lane; it < 39; it += 32) a[AUX_OFF_XPOS + it] = float(w.kin.xpos[1 + it / 3][it % 3] + (it % 3 < 2 ? real(w.org[it % 3]) : real(0)));
+      syncwarp();
+      e.bias_out = a + AUX_OFF_BIAS;
+    }
+    e.forward_dynamics(p.max_iter, real(p.tol));
+    typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
+
+    if (MODE == MODE_FORWARD) {
+      if (lane < NV) B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
+      if (p.aux) {
+        float* a = p.aux + size_t(env) * AUX_STRIDE;
+        for (int it = lane; it < 324; it += 32) {
+          const int i = it / 18, j = it % 18;
+          real v = 0;
+          if (i < 6 && j < 6) v = w.Mbb[i][j];
+          else if (i >= 6 && j < 6) v = w.Mlb[(i - 6) / 3][(i - 6) % 3][j];
+          else if (i < 6 && j >= 6) v = w.Mlb[(j - 6) / 3][(j - 6) % 3][i];
+          else if ((i - 6) / 3 == (j - 6) / 3) v = w.Mll[(i - 6) / 3][(i - 6) % 3][(j - 6) % 3];
+          a[AUX_OFF_M + it] = float(v);
+        }
+        if (lane < NV) {
+          a[AUX_OFF_PASSIVE + lane] = float(-m.dof_damping[lane] * w.qvel[lane]);
+          a[AUX_OFF_SMOOTH + lane] = float(w.fsm[lane]);
+          a[AUX_OFF_CONSTRAINT + lane] = float(w.fcon[lane]);
+        }
+        for (int it = lane; it < 216; it += 32) {
+          const int l = it / 54, i = (it % 54) / 18, d = it % 18;
+          real v = 0;
+          if (d < 6 || (d - 6) / 3 == l) {
+            const real off[3] = {w.footpos[l][0] - w.com[0], w.footpos[l][1] - w.com[1], w.footpos[l][2] - w.com[2]};
+            real cr[3];
+            cross3(cr, w.cdof[d], off);
+            v = w.cdof[d][3 + i] + cr[i];
+          }
+          a[AUX_OFF_JACP + it] = float(v);
+        }
+        if (lane < 12) a[AUX_OFF_FEETPOS + lane] = float(w.footpos[lane / 3][lane % 3] + (lane % 3 < 2 ? real(w.org[lane % 3]) : real(0)));
+        if (lane < 3) a[AUX_OFF_COM + lane] = float(w.com[lane] + (lane < 2 ? real(w.org[lane]) : real(0)));
+        if (lane < 6) a[AUX_OFF_IMU + lane] = m.has_imu ? float(w.sens[lane]) : 0.f;
+        for (int c = lane; c < NCON; c += 32) {
+          float* o = a + AUX_OFF_CONTACTS + QS_CONTACT_STRIDE * c;
+          if (c < w.ncon) {
+            const int info = w.c_info[c], dim = info >> 16;
+            o[0] = float(w.c_dist[c]);
+            o[1] = float(w.c_pos[c][0] + real(w.org[0])); o[2] = float(w.c_pos[c][1] + real(w.org[1])); o[3] = float(w.c_pos[c][2]);
+            real t2[3];
+            cross3(t2, w.c_frame[c], w.c_frame[c] + 3);
+            for (int i = 0; i < 6; i++) o[4 + i] = float(w.c_frame[c][i]);
+            for (int i = 0; i < 3; i++) o[10 + i] = float(t2[i]);
+            for (int i = 0; i < 3; i++) o[13 + i] = (i < dim) ? float(w.c_F[c][i]) : 0.f;
+            o[16] = float(info & 0xff); o[17] = float((info >> 8) & 0xff); o[18] = float(w.c_fri[c][0]); o[19] = float(dim);
+          } else {
+            for (int i = 0; i < QS_CONTACT_STRIDE; i++) o[i] = 0.f;
+          }
+        }
+      }
+      if (lane == 0) {
+        B.ncon[env] = w.ncon;
+        B.solver_iter[env] = e.solver_iter | (e.ls_evals << 8);
+        B.invalid_body_mask[2 * env] = uint8_t(fl.invalid_mask & 0xff); B.invalid_body_mask[2 * env + 1] = uint8_t((fl.invalid_mask >> 8) & 0xff);
+      }
+      return;
+    }
+
+    // ---- integrate, then env-side bookkeeping
+    e.integrate(base64);
+    fl.out_of_bounds = e.flags().out_of_bounds;  // bounds are tested on the post-step base position (:1252-1256)
+    const bool terminated = fl.invalid_mask != 0 || fl.out_of_bounds;
+    sim_time += float(m.timestep);
+    step_count = resetting ? 0 : step_count + 1;
+    if (resetting) {
+      // command + friction resampling happen after the step inside reset (:397-404)
+      const QsResetOptions& ro = p.ro;
+      const real vn = real(ro.lin_vel_range[0] + (ro.lin_vel_range[1] - ro.lin_vel_range[0]) * double(u_late[0]));
+      real hx = 1, hy = 0, vnorm = vn;
+      if (ro.command_mode & 2) { real ang = real(-3.14159265358979323846 + 2 * 3.14159265358979323846 * double(u_late[1])); Num<real>::sincos(ang, &hy, &hx); }
+      if (!(ro.command_mode & 3)) vnorm = 0;  // 'human'
+      command[0] = vnorm * hx; command[1] = vnorm * hy; command[2] = 0;
+      command[3] = (ro.command_mode & 4) ? real(ro.ang_vel_range[0] + (ro.ang_vel_range[1] - ro.ang_vel_range[0]) * double(u_late[2])) : real(0);
+      const float mu = float(ro.friction_range[0] + (ro.friction_range[1] - ro.friction_range[0]) * double(u_late[3]));
+      if (lane < 4) B.command[4 * env + lane] = float(command[lane]);
+      if (lane < 2) B.friction[2 * env + lane] = mu;
+      if (lane == 0) { p.episode[env] = p.episode[env] + 1; w.mu_floor = real(mu); w.mu_feet = real(mu); }
+      if (lane < 6) B.qfrc_applied[size_t(env) * 6 + lane] = 0.f;
+    }
     syncwarp();
-  }
+    e.pack_obs(command, fl.contact_mask);
 
-  // ---- forward dynamics
-  e.forward(p.max_iter, real(p.tol));
-  typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
-
-  if (MODE == MODE_FORWARD) {
-    if (lane < NV) B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
-    if (p.aux) {
-      float* a = p.aux + size_t(env) * AUX_STRIDE;
-      for (int it = lane; it < 324; it += 32) {
-        const int i = it / 18, j = it % 18;
-        real v = 0;
-        if (i < 6 && j < 6) v = w.Mbb[i][j];
-        else if (i >= 6 && j < 6) v = w.Mlb[(i - 6) / 3][(i - 6) % 3][j];
-        else if (i < 6 && j >= 6) v = w.Mlb[(j - 6) / 3][(j - 6) % 3][i];
-        else if ((i - 6) / 3 == (j - 6) / 3) v = w.Mll[(i - 6) / 3][(i - 6) % 3][(j - 6) % 3];
-        a[AUX_OFF_M + it] = float(v);
-      }
-      if (lane < NV) {
-        a[AUX_OFF_BIAS + lane] = float(w.bias[lane]);
-        a[AUX_OFF_PASSIVE + lane] = float(-m.dof_damping[lane] * w.qvel[lane]);
-        a[AUX_OFF_SMOOTH + lane] = float(w.fsm[lane]);
-        a[AUX_OFF_CONSTRAINT + lane] = float(w.fcon[lane]);
-      }
-      for (int it = lane; it < 216; it += 32) {
-        const int l = it / 54, i = (it % 54) / 18, d = it % 18;
-        real v = 0;
-        if (d < 6 || (d - 6) / 3 == l) {
-          const real off[3] = {w.footpos[l][0] - w.com[0], w.footpos[l][1] - w.com[1], w.footpos[l][2] - w.com[2]};
-          real cr[3];
-          cross3(cr, w.cdof[d], off);
-          v = w.cdof[d][3 + i] + cr[i];
-        }
-        a[AUX_OFF_JACP + it] = float(v);
-      }
-      if (lane < 12) a[AUX_OFF_FEETPOS + lane] = float(w.footpos[lane / 3][lane % 3] + (lane % 3 < 2 ? real(w.org[lane % 3]) : real(0)));
-      if (lane < 3) a[AUX_OFF_COM + lane] = float(w.com[lane] + (lane < 2 ? real(w.org[lane]) : real(0)));
-      for (int it = lane; it < 39; it += 32) a[AUX_OFF_XPOS + it] = float(w.xpos[1 + it / 3][it % 3] + (it % 3 < 2 ? real(w.org[it % 3]) : real(0)));
-      if (lane < 6) a[AUX_OFF_IMU + lane] = m.has_imu ? float(w.sens[lane]) : 0.f;
-      for (int c = lane; c < NCON; c += 32) {
-        float* o = a + AUX_OFF_CONTACTS + QS_CONTACT_STRIDE * c;
-        if (c < w.ncon) {
-          o[0] = float(w.c_dist[c]);
-          o[1] = float(w.c_pos[c][0] + real(w.org[0])); o[2] = float(w.c_pos[c][1] + real(w.org[1])); o[3] = float(w.c_pos[c][2]);
-          for (int i = 0; i < 9; i++) o[4 + i] = float(w.c_frame[c][i]);
-          for (int i = 0; i < 3; i++) o[13 + i] = (i < w.c_dim[c]) ? float(w.c_F[c][i]) : 0.f;
-          o[16] = float(w.c_geom[c]); o[17] = float(w.c_body[c]); o[18] = float(w.c_fri[c][0]); o[19] = float(w.c_dim[c]);
-        } else {
-          for (int i = 0; i < QS_CONTACT_STRIDE; i++) o[i] = 0.f;
+    // ---- write back
+    {
+      bool ok = true;
+      if (lane < NQ) ok = ok && isfinite(double(w.qpos[lane]));
+      if (lane < NV) ok = ok && isfinite(double(w.qvel[lane]));
+      if (qs::ballot(!ok) != 0) status |= 1u;
+    }
+    if (w.overflow) status |= 2u;
+    if (e.solver_maxed) status |= 4u;
+    if (lane < NQ) B.qpos[size_t(env) * NQ + lane] = (lane < 3) ? float(base64[lane]) : float(w.qpos[lane]);
+    if (lane < NV) {
+      B.qvel[size_t(env) * NV + lane] = float(w.qvel[lane]);
+      B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
+      B.qacc_warmstart[size_t(env) * NV + lane] = float(w.qacc[lane]);
+    }
+    float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
+    if (obs)
+      for (int i = lane; i < NOBS_BASE; i += 32) obs[i] = float(w.obs[i]);
+    if (p.use_imu) {
+      // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals
+      unsigned tk = p.tick[env];
+      if (lane < 3) {
+        uint32_t r[4];
+        philox4x32(env_g, tk, unsigned(lane), 0x1A2Bu, p.seed_lo ^ 0x9E3779B9u, p.seed_hi, r);
+        const float u1 = fmaxf(u32_to_unit(r[0]), 5.9604645e-8f), u2 = u32_to_unit(r[1]), u3 = fmaxf(u32_to_unit(r[2]), 5.9604645e-8f), u4 = u32_to_unit(r[3]);
+        const float ra = sqrtf(-2.f * logf(u1)), rb = sqrtf(-2.f * logf(u3));
+        float s1, c1, s2, c2;
+        sincosf(6.28318530717958647692f * u2, &s1, &c1);
+        sincosf(6.28318530717958647692f * u4, &s2, &c2);
+        const float n_acc = ra * c1 * p.imu_an, n_ab = ra * s1 * p.imu_abr, n_gyr = rb * c2 * p.imu_gn, n_gb = rb * s2 * p.imu_gbr;
+        float* bias = B.imu_bias + size_t(env) * 6;
+        const float ab = bias[lane] + n_ab, gb = bias[3 + lane] + n_gb;
+        bias[lane] = ab; bias[3 + lane] = gb;
+        if (obs) {
+          float* io = obs + NOBS_BASE;
+          io[lane] = float(w.sens[lane]) + ab + n_acc; io[3 + lane] = n_acc; io[6 + lane] = ab;
+          io[9 + lane] = float(w.sens[3 + lane]) + gb + n_gyr; io[12 + lane] = n_gyr; io[15 + lane] = gb;
         }
       }
+      syncwarp();
+      if (lane == 0) p.tick[env] = tk + 1;
     }
     if (lane == 0) {
+      B.sim_time[env] = sim_time;
+      B.step_count[env] = step_count;
+      B.status[env] = uint8_t(status);
       B.ncon[env] = w.ncon;
-      B.solver_iter[env] = e.solver_iter;
+      B.solver_iter[env] = e.solver_iter | (e.ls_evals << 8);  // low byte: Newton iterations, upper bits: line-search evaluations
       B.invalid_body_mask[2 * env] = uint8_t(fl.invalid_mask & 0xff); B.invalid_body_mask[2 * env + 1] = uint8_t((fl.invalid_mask >> 8) & 0xff);
-    }
-    return;
-  }
-
-  // ---- integrate, then env-side bookkeeping
-  e.integrate(base64);
-  fl.out_of_bounds = e.flags().out_of_bounds;  // bounds are tested on the post-step base position (:1252-1256)
-
-  float sim_time = (MODE == MODE_RESET) ? 0.f : B.sim_time[env];
-  sim_time += float(m.timestep);
-  if (MODE == MODE_RESET) {
-    // command + friction resampling happen after the step inside reset (:397-404)
-    const QsResetOptions& ro = p.ro;
-    const real* u = w.obs;
-    const real vn = real(ro.lin_vel_range[0] + (ro.lin_vel_range[1] - ro.lin_vel_range[0]) * double(u[26]));
-    real hx = 1, hy = 0, vnorm = vn;
-    if (ro.command_mode & 2) { real ang = real(-3.14159265358979323846 + 2 * 3.14159265358979323846 * double(u[27])); Num<real>::sincos(ang, &hy, &hx); }
-    if (!(ro.command_mode & 3)) vnorm = 0;  // 'human'
-    command[0] = vnorm * hx; command[1] = vnorm * hy; command[2] = 0;
-    command[3] = (ro.command_mode & 4) ? real(ro.ang_vel_range[0] + (ro.ang_vel_range[1] - ro.ang_vel_range[0]) * double(u[28])) : real(0);
-    const float mu = float(ro.friction_range[0] + (ro.friction_range[1] - ro.friction_range[0]) * double(u[29]));
-    if (lane < 4) B.command[4 * env + lane] = float(command[lane]);
-    if (lane < 2) B.friction[2 * env + lane] = mu;
-    if (lane == 0) p.episode[env] = p.episode[env] + 1;
-  }
-  syncwarp();
-  e.pack_obs(command, fl.contact_mask);
-
-  // ---- write back
-  const bool finite_ok = [&] {
-    bool ok = true;
-    if (lane < NQ) ok = ok && isfinite(double(w.qpos[lane]));
-    if (lane < NV) ok = ok && isfinite(double(w.qvel[lane]));
-    return qs::ballot(!ok) == 0;
-  }();
-  if (!finite_ok) status |= 1u;
-  if (w.overflow) status |= 2u;
-  if (e.solver_maxed) status |= 4u;
-  if (lane < NQ) B.qpos[size_t(env) * NQ + lane] = (lane < 3) ? float(base64[lane]) : float(w.qpos[lane]);
-  if (lane < NV) {
-    B.qvel[size_t(env) * NV + lane] = float(w.qvel[lane]);
-    B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
-    B.qacc_warmstart[size_t(env) * NV + lane] = float(w.qacc[lane]);
-  }
-  if (MODE == MODE_RESET && lane < 6) B.qfrc_applied[size_t(env) * 6 + lane] = 0.f;
-  float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
-  if (obs)
-    for (int i = lane; i < NOBS_BASE; i += 32) obs[i] = float(w.obs[i]);
-  if (p.use_imu) {
-    // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals
-    unsigned tk = p.tick[env];
-    if (lane < 3) {
-      uint32_t r[4];
-      philox4x32(env_g, tk, unsigned(lane), 0x1A2Bu, p.seed_lo ^ 0x9E3779B9u, p.seed_hi, r);
-      const float u1 = fmaxf(u32_to_unit(r[0]), 5.9604645e-8f), u2 = u32_to_unit(r[1]), u3 = fmaxf(u32_to_unit(r[2]), 5.9604645e-8f), u4 = u32_to_unit(r[3]);
-      const float ra = sqrtf(-2.f * logf(u1)), rb = sqrtf(-2.f * logf(u3));
-      float s1, c1, s2, c2;
-      sincosf(6.28318530717958647692f * u2, &s1, &c1);
-      sincosf(6.28318530717958647692f * u4, &s2, &c2);
-      const float n_acc = ra * c1 * p.imu_an, n_ab = ra * s1 * p.imu_abr, n_gyr = rb * c2 * p.imu_gn, n_gb = rb * s2 * p.imu_gbr;
-      float* bias = B.imu_bias + size_t(env) * 6;
-      const float ab = bias[lane] + n_ab, gb = bias[3 + lane] + n_gb;
-      bias[lane] = ab; bias[3 + lane] = gb;
-      if (obs) {
-        float* io = obs + NOBS_BASE;
-        io[lane] = float(w.sens[lane]) + ab + n_acc; io[3 + lane] = n_acc; io[6 + lane] = ab;
-        io[9 + lane] = float(w.sens[3 + lane]) + gb + n_gyr; io[12 + lane] = n_gyr; io[15 + lane] = gb;
+      if (MODE == MODE_STEP && !resetting) {
+        if (p.reward) p.reward[env] = 0.f;  // _compute_reward, quadruped_env.py:1141-1144
+        if (p.terminated) p.terminated[env] = uint8_t(terminated);
+        if (p.truncated) p.truncated[env] = 0;
       }
     }
-    if (lane == 0) p.tick[env] = tk + 1;
-  }
-  if (lane == 0) {
-    B.sim_time[env] = sim_time;
-    B.step_count[env] = (MODE == MODE_RESET) ? 0 : B.step_count[env] + 1;
-    B.status[env] = uint8_t(status);
-    B.ncon[env] = w.ncon;
-    B.solver_iter[env] = e.solver_iter;
-    B.invalid_body_mask[2 * env] = uint8_t(fl.invalid_mask & 0xff); B.invalid_body_mask[2 * env + 1] = uint8_t((fl.invalid_mask >> 8) & 0xff);
-    if (MODE == MODE_STEP) {
-      if (p.reward) p.reward[env] = 0.f;  // _compute_reward, quadruped_env.py:1141-1144
-      if (p.terminated) p.terminated[env] = uint8_t(fl.invalid_mask != 0 || fl.out_of_bounds);
-      if (p.truncated) p.truncated[env] = 0;
-    }
+    // in-kernel auto-reset: the warp of an env that just terminated goes round once more as a reset pass
+    if (MODE != MODE_STEP || !p.auto_reset || resetting || !terminated) break;
+    resetting = true;
+    given_state = false;
+    e.ls_evals = 0;
+    syncwarp();
   }
 }
 
@@ -416,8 +447,8 @@ template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const
   int dev = 0, max_smem = 0;
   QS_CUDA(h, cudaGetDevice(&dev));
   QS_CUDA(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int warps = 8;
-  while (warps > 1 && V::dm_bytes() + 128 + warps * V::ws_bytes() > size_t(max_smem)) warps >>= 1;
+  int warps = LaunchCfg<real>::kMaxWarps;
+  while (warps > 1 && V::dm_bytes() + 128 + warps * V::ws_bytes() > size_t(max_smem)) warps--;
   h->warps_per_cta = warps;
   h->smem_bytes = V::dm_bytes() + 128 + warps * V::ws_bytes();
   if (h->smem_bytes > size_t(max_smem)) return fail(h, 3, "workspace does not fit in shared memory");
@@ -502,15 +533,28 @@ static int launch(QsHandle* h, KernelFn fn, const KParams& p, cudaStream_t s) {
   return 0;
 }
 
-int qs_step(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
+                     const QsResetOptions* auto_reset, void* stream) {
   if (!h || !h->bound) return fail(h, 1, "qs_step: handle not bound");
   if (!ctrl) return fail(h, 1, "qs_step: ctrl is null");
   KParams p = base_params(h);
   p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
+  if (auto_reset) { p.auto_reset = 1; p.ro = *auto_reset; }
   return launch(h, h->k_step, p, static_cast<cudaStream_t>(stream));
 }
 
-int qs_step_host(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+int qs_step(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {
+  return step_impl(h, ctrl, obs, reward, terminated, truncated, nullptr, stream);
+}
+
+int qs_step_autoreset(QsHandle* h, const float* ctrl, const QsResetOptions* opt, float* obs, float* reward, uint8_t* terminated,
+                      uint8_t* truncated, void* stream) {
+  if (!opt) return fail(h, 1, "qs_step_autoreset: options are null");
+  return step_impl(h, ctrl, obs, reward, terminated, truncated, opt, stream);
+}
+
+int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_reset, float* obs, float* reward, uint8_t* terminated,
+                 uint8_t* truncated, void* stream) {
   if (!h || !h->bound) return fail(h, 1, "qs_step_host: handle not bound");
   const size_t n = size_t(h->cfg.num_envs);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -522,7 +566,7 @@ int qs_step_host(QsHandle* h, const float* ctrl, float* obs, float* reward, uint
     QS_CUDA(h, cudaMalloc(&h->d_trunc, n));
   }
   QS_CUDA(h, cudaMemcpyAsync(h->d_ctrl, ctrl, n * NU * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = qs_step(h, h->d_ctrl, h->d_obs, h->d_reward, h->d_term, h->d_trunc, stream);
+  int rc = step_impl(h, h->d_ctrl, h->d_obs, h->d_reward, h->d_term, h->d_trunc, auto_reset, stream);
   if (rc) return rc;
   if (obs) QS_CUDA(h, cudaMemcpyAsync(obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (reward) QS_CUDA(h, cudaMemcpyAsync(reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,486 @@
+"""`QuadrupedEnv`: the reference's gym.Env surface on top of the batched B200 step.
+
+Mirror of gym_quadruped/quadruped_env.py:71-1432 for the hot path (constructor kwargs :85-99, `step` :251-307,
+`reset` :309-406, `ALL_OBS` :35-81, the accessors controllers use :488-1044).  `num_envs=1` (default) reproduces the
+reference's return types -- dict of `(dim,)` float64 NumPy arrays, Python float / bool flags, info dict; `num_envs>1`
+returns dict-of-`[N, dim]` torch views into one packed `[N, D]` CUDA tensor and tensor flags.
+
+Everything physical happens in libqstep's fused kernel (see csrc/qs_env.cuh); this file only slices tensors.
+Viewer / rendering (`render`, ghost robots, key callbacks) are out of scope.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+import math
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import backend
+from .backend import BatchSim, command_mode_bits
+from .model import QS_NOBS_BASE, Model
+from .robot_cfgs import RobotConfig, get_robot_config
+from .sensors.base_sensor import Sensor
+from .sensors.imu import IMU
+from .spaces import Box, Env
+from .utils.math_utils import _process_range
+from .utils.quadruped_utils import LegsAttr, configure_observation_space, extract_joint_info
+
+log = logging.getLogger(__name__)
+
+BASE_OBS = ['base_pos', 'base_lin_vel', 'base_lin_vel_err', 'base_lin_acc', 'base_ang_vel', 'base_ang_vel_err',
+            'base_ori_euler_xyz', 'base_ori_quat_wxyz', 'base_ori_SO3', 'gravity_vector:base']
+BASE_OBS_BASE_FRAME = ['base_lin_vel:base', 'base_lin_vel_err:base', 'base_lin_acc:base', 'base_ang_vel:base',
+                       'base_ang_vel_err:base']
+GEN_COORDS_OBS = ['qpos', 'qvel', 'tau_ctrl_setpoint', 'qpos_js', 'qvel_js', 'kinetic_energy', 'work']
+FEET_OBS = ['feet_pos', 'feet_pos:base', 'feet_vel', 'feet_vel_rel', 'feet_vel:base', 'feet_vel_rel:base', 'contact_state',
+            'contact_forces', 'contact_forces:base']
+
+# packed layout of the kernel's observation row: name -> (offset, dim); SURVEY.md section 8(a)
+_OBS_DIMS = [3, 3, 3, 3, 3, 3, 3, 4, 9, 3, 3, 3, 3, 3, 3, 19, 18, 12, 12, 12, 1, 1, 12, 12, 12, 12, 12, 12, 4, 12, 12]
+OBS_LAYOUT: dict[str, tuple[int, int]] = {}
+_off = 0
+for _name, _dim in zip(BASE_OBS + BASE_OBS_BASE_FRAME + GEN_COORDS_OBS + FEET_OBS, _OBS_DIMS):
+    OBS_LAYOUT[_name] = (_off, _dim)
+    _off += _dim
+assert _off == QS_NOBS_BASE
+IMU_LAYOUT = {n: (QS_NOBS_BASE + 3 * i, 3) for i, n in enumerate(IMU.ALL_OBS)}
+_PER_LEG_OBS = {'feet_pos', 'feet_pos:base', 'feet_vel', 'feet_vel_rel', 'feet_vel:base', 'feet_vel_rel:base', 'contact_forces',
+                'contact_forces:base'}
+_MODEL_LEGS = ('FL', 'FR', 'RL', 'RR')
+
+
+class QuadrupedEnv(Env):
+    """Batched quadruped environment with the reference's constructor and step / reset surface."""
+
+    _DEFAULT_OBS = ('qpos', 'qvel', 'tau_ctrl_setpoint', 'feet_pos:base', 'feet_vel:base')
+    ALL_OBS = BASE_OBS + BASE_OBS_BASE_FRAME + GEN_COORDS_OBS + FEET_OBS
+    metadata = {'render.modes': ['human'], 'version': 0}
+
+    def __init__(
+        self,
+        robot: str,
+        state_obs_names: tuple[str, ...] = _DEFAULT_OBS,
+        scene: str = 'flat',
+        sim_dt: float = 0.002,
+        base_vel_command_type: str = 'forward',
+        ref_base_lin_vel=0.5,
+        ref_base_ang_vel=0.0,
+        ground_friction_coeff=1.0,
+        legs_order: tuple[str, str, str, str] = ('FL', 'FR', 'RL', 'RR'),
+        sensors: tuple | None = None,
+        sensors_kwargs: tuple[dict[str, Any]] | None = None,
+        external_disturbances_kwargs: dict[str, Any] | None = None,
+        *,
+        num_envs: int = 1,
+        device: str | int | torch.device = 'cuda:0',
+        seed: int = 0,
+        precision: str = 'fp32',
+        env_id_offset: int = 0,
+    ):
+        self._init_args = dict(robot=robot, state_obs_names=state_obs_names, scene=scene, sim_dt=sim_dt,
+                               base_vel_command_type=base_vel_command_type, ref_base_lin_vel=ref_base_lin_vel,
+                               ref_base_ang_vel=ref_base_ang_vel, ground_friction_coeff=ground_friction_coeff, legs_order=legs_order,
+                               sensors=sensors, sensors_kwargs=sensors_kwargs, external_disturbances_kwargs=external_disturbances_kwargs)
+        self.robot_name = robot
+        self.robot_cfg: RobotConfig = get_robot_config(robot_name=robot)
+        self.base_vel_command_type = base_vel_command_type
+        self._command_mode = command_mode_bits(base_vel_command_type)
+        self.base_lin_vel_range = _process_range(ref_base_lin_vel)
+        self.base_ang_vel_range = _process_range(ref_base_ang_vel)
+        if self.base_lin_vel_range is None or self.base_ang_vel_range is None:
+            raise NotImplementedError('callable velocity references are not supported by the batched env')
+        self.ground_friction_coeff_range = _process_range(ground_friction_coeff)
+        self.legs_order = tuple(legs_order)
+        assert sorted(self.legs_order) == sorted(_MODEL_LEGS), f'legs_order must be a permutation of {_MODEL_LEGS}'
+        self.is_paused = False
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+
+        self.model = Model(self.robot_cfg.tables, scene, sim_dt)
+        self.terrain_limits = self.model.terrain_limits
+        self.joint_info = extract_joint_info(self.model.tables)
+        idx = {leg: [7 + 3 * k + j for j in range(3)] for k, leg in enumerate(_MODEL_LEGS)}
+        self.legs_qpos_idx = LegsAttr(**idx)
+        self.legs_qvel_idx = LegsAttr(**{leg: [i - 1 for i in v] for leg, v in idx.items()})
+        self.legs_tau_idx = LegsAttr(**{leg: [i - 7 for i in v] for leg, v in idx.items()})
+        self._feet_geom_id = LegsAttr(**{leg: self.model.tables['foot_geom'][k] for k, leg in enumerate(_MODEL_LEGS)})
+        self._feet_body_id = LegsAttr(**{leg: 4 + 3 * k for k, leg in enumerate(_MODEL_LEGS)})
+
+        # action space: unbounded, exactly like the reference (its limit logic is always-truthy, quadruped_env.py:219-225)
+        self.action_space = Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
+
+        # sensors: IMU is fused into the kernel; other Sensor subclasses are stepped on the host after the kernel
+        self.sensors: list[Sensor] = []
+        use_imu, imu_noise = False, (0.01, 0.01, 0.01, 0.01)
+        sensors = sensors or ()
+        sensors_kwargs = sensors_kwargs or tuple({} for _ in sensors)
+        for cls, kw in zip(sensors, sensors_kwargs):
+            if cls is IMU or (isinstance(cls, type) and issubclass(cls, IMU)):
+                s = cls(mj_model=self.model, mj_data=self, **kw)
+                use_imu, imu_noise = True, s.noise
+            else:
+                s = cls(mj_model=self.model, mj_data=self, **kw)
+            self.sensors.append(s)
+
+        for name in state_obs_names:
+            if name not in OBS_LAYOUT and not (use_imu and name in IMU_LAYOUT):
+                raise ValueError(f'Invalid observation name: {name}, available obs: {self.ALL_OBS}')
+        self.observation_space = configure_observation_space(self.model.tables, state_obs_names)
+        self.state_obs_names = state_obs_names
+
+        self.sim = BatchSim(self.model, self.num_envs, device=self.device, precision=0 if precision == 'fp32' else 1,
+                            use_imu=use_imu, imu_noise=imu_noise, seed=seed, env_id_offset=env_id_offset)
+        self._layout = dict(OBS_LAYOUT)
+        if use_imu:
+            self._layout.update(IMU_LAYOUT)
+        perm = [_MODEL_LEGS.index(leg) for leg in self.legs_order]
+        self._leg_perm = None if perm == [0, 1, 2, 3] else torch.tensor(
+            [3 * p + i for p in perm for i in range(3)], device=self.device, dtype=torch.long)
+
+        self.external_disturbances_kwargs = external_disturbances_kwargs
+        self._ext_schedule = None
+        if external_disturbances_kwargs is not None:
+            self._sample_external_disturbances(torch.ones(self.num_envs, dtype=torch.bool, device=self.device))
+        self._vel_schedule = None
+        self.viewer = None
+        self.step_num = 0
+        self._last_obs_tensor = self.sim.obs
+
+    # ------------------------------------------------------------------ gym API
+    def step(self, action):
+        """Apply joint torques, advance one sim step, return (obs, reward, terminated, truncated, info); :251-307."""
+        if self.num_envs == 1 and not isinstance(action, torch.Tensor):
+            action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 12), device=self.device)
+        obs_t, rew, term, trunc = self.sim.step(action)
+        for s in self.sensors:
+            s.step()
+        info_invalid = self.sim.invalid_body_mask
+        self.step_num += 1
+        if self._command_mode & backend.CMD_RESET:
+            self._advance_velocity_schedule()
+        if self.external_disturbances_kwargs is not None and self.external_disturbances_kwargs.get('type') == 'reset':
+            self._advance_disturbance_schedule()
+        obs = self._obs_dict(obs_t)
+        if self.num_envs == 1:
+            mask = int(info_invalid[0, 0].item()) | (int(info_invalid[0, 1].item()) << 8)
+            names = self.model.tables['body_names']
+            invalid = {f'world:0_{names[b]}:{b}': None for b in range(1, 14) if mask >> b & 1}
+            info = {'time': float(self.sim.sim_time[0].item()), 'step_num': self.step_num - 1, 'invalid_contacts': invalid}
+            return obs, 0, bool(term[0].item()), False, info
+        info = {'time': self.sim.sim_time, 'step_num': self.step_num - 1, 'invalid_contacts': info_invalid}
+        return obs, rew, term.bool(), trunc.bool(), info
+
+    def reset(self, qpos=None, qvel=None, seed: int | None = None, random: bool = True, options: dict[str, Any] | None = None,
+              env_mask: torch.Tensor | None = None):
+        """Reset (all envs, or those selected by `env_mask`) and return the observation dict; :309-406."""
+        options = {} if options is None else options
+        self.step_num = 0
+        if seed is not None:
+            self._reseed(seed)
+        opt = self.sim.make_reset_options(
+            randomize=random, angle_sweep=options.get('angle_sweep', 20 * math.pi / 180),
+            roll_sweep=options.get('roll_sweep', 10 * math.pi / 180), pitch_sweep=options.get('pitch_sweep', 10 * math.pi / 180),
+            lin_vel_range=self.base_lin_vel_range, ang_vel_range=self.base_ang_vel_range,
+            friction_range=self.ground_friction_coeff_range, command_mode=self._command_mode)
+        self.sim.reset_options = opt
+        mask = None if env_mask is None else env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if qpos is not None or qvel is not None:
+            assert qpos is not None and qvel is not None, 'qpos and qvel must be given together'
+            q = torch.as_tensor(np.asarray(qpos) if not isinstance(qpos, torch.Tensor) else qpos, dtype=torch.float32, device=self.device)
+            v = torch.as_tensor(np.asarray(qvel) if not isinstance(qvel, torch.Tensor) else qvel, dtype=torch.float32, device=self.device)
+            obs_t = self.sim.reset(mask, q.reshape(-1, 19).expand(self.num_envs, 19).contiguous(),
+                                   v.reshape(-1, 18).expand(self.num_envs, 18).contiguous(), opt)
+        else:
+            obs_t = self.sim.reset(mask, None, None, opt)
+        if self.num_envs == 1 and (int(self.sim.status[0].item()) & 8):
+            raise RuntimeError('Unable to initialize the robot without ground contact.')
+        if self._command_mode & backend.CMD_RESET:
+            self._vel_schedule = None
+        return self._obs_dict(obs_t)
+
+    def auto_reset(self):
+        """Batched convenience: reset every env whose last `terminated` flag is set (one masked kernel launch)."""
+        return self._obs_dict(self.sim.reset_done())
+
+    def render(self, *args, **kwargs):
+        raise NotImplementedError('rendering / viewer decorations are out of scope for the batched B200 env')
+
+    def close(self):
+        if getattr(self, 'sim', None) is not None:
+            self.sim.close()
+
+    # ------------------------------------------------------------------ observation plumbing
+    def _obs_dict(self, obs_t: torch.Tensor):
+        self._last_obs_tensor = obs_t
+        out = {}
+        for name in self.state_obs_names:
+            off, dim = self._layout[name]
+            v = obs_t[:, off:off + dim]
+            if self._leg_perm is not None and name in _PER_LEG_OBS:
+                v = v.index_select(1, self._leg_perm)
+            out[name] = v
+        if self.num_envs == 1:
+            flat = obs_t[0].detach().cpu().numpy().astype(np.float64)
+            res = {}
+            for name in self.state_obs_names:
+                off, dim = self._layout[name]
+                a = flat[off:off + dim]
+                if self._leg_perm is not None and name in _PER_LEG_OBS:
+                    a = a[self._leg_perm.cpu().numpy()]
+                res[name] = a.copy()
+            return res
+        return out
+
+    def _sensor_obs(self, name):
+        off, dim = self._layout[name]
+        v = self._last_obs_tensor[:, off:off + dim]
+        return v[0].detach().cpu().numpy().astype(np.float64) if self.num_envs == 1 else v
+
+    def _np(self, t: torch.Tensor):
+        return t[0].detach().cpu().numpy().astype(np.float64) if self.num_envs == 1 else t
+
+    # ------------------------------------------------------------------ state tensors (write-then-step semantics of mjData)
+    @property
+    def qpos(self) -> torch.Tensor:
+        return self.sim.qpos
+
+    @property
+    def qvel(self) -> torch.Tensor:
+        return self.sim.qvel
+
+    def set_state(self, qpos, qvel, env_ids=None):
+        """`env.mjData.qpos[...] = ...` equivalent (examples/aliengo_with_heightmap.py:32-34)."""
+        self.sim.set_state(torch.as_tensor(qpos), torch.as_tensor(qvel), env_ids)
+
+    # ------------------------------------------------------------------ accessors (quadruped_env.py:488-1044)
+    def _slice(self, name):
+        off, dim = OBS_LAYOUT[name]
+        return self._np(self.sim.obs[:, off:off + dim])
+
+    def _frame_name(self, base, frame):
+        if frame == 'world':
+            return base
+        if frame == 'base':
+            return base + ':base'
+        raise ValueError(f"Invalid frame: {frame} != 'world' or 'base'")
+
+    def _legs(self, arr, width=3):
+        a = arr.reshape(*arr.shape[:-1], 4, width) if self.num_envs > 1 else arr.reshape(4, width)
+        pick = (lambda k: a[..., k, :]) if self.num_envs > 1 else (lambda k: a[k])
+        return LegsAttr(**{leg: pick(k) for k, leg in enumerate(_MODEL_LEGS)})
+
+    def target_base_vel(self, frame='world'):
+        cmd = self.sim.command
+        yaw = self.sim.obs[:, 20]
+        c, s = torch.cos(yaw), torch.sin(yaw)
+        lin = torch.stack([c * cmd[:, 0] - s * cmd[:, 1], s * cmd[:, 0] + c * cmd[:, 1], cmd[:, 2]], dim=1)
+        ang = torch.stack([torch.zeros_like(yaw), torch.zeros_like(yaw), cmd[:, 3]], dim=1)
+        if frame == 'base':
+            R = self.sim.obs[:, 25:34].reshape(-1, 3, 3)
+            lin, ang = torch.einsum('nji,nj->ni', R, lin), torch.einsum('nji,nj->ni', R, ang)
+        elif frame != 'world':
+            raise ValueError(f"Invalid frame: {frame} != 'world' or 'base'")
+        return self._np(lin), self._np(ang)
+
+    def base_lin_vel(self, frame='world'):
+        return self._slice(self._frame_name('base_lin_vel', frame))
+
+    def base_lin_vel_err(self, frame='world'):
+        return self._slice(self._frame_name('base_lin_vel_err', frame))
+
+    def base_ang_vel(self, frame='world'):
+        return self._slice(self._frame_name('base_ang_vel', frame))
+
+    def base_ang_vel_err(self, frame='world'):
+        return self._slice(self._frame_name('base_ang_vel_err', frame))
+
+    def base_lin_acc(self, frame='world'):
+        return self._slice(self._frame_name('base_lin_acc', frame))
+
+    def feet_pos(self, frame='world') -> LegsAttr:
+        return self._legs(self._slice(self._frame_name('feet_pos', frame)))
+
+    def feet_vel(self, frame='world', relative=False) -> LegsAttr:
+        return self._legs(self._slice(self._frame_name('feet_vel_rel' if relative else 'feet_vel', frame)))
+
+    def feet_contact_state(self, frame='world', ground_reaction_forces=False):
+        cs = self._slice('contact_state')
+        state = LegsAttr(**{leg: (bool(cs[k]) if self.num_envs == 1 else cs[:, k] > 0.5) for k, leg in enumerate(_MODEL_LEGS)})
+        if not ground_reaction_forces:
+            return state, None
+        return state, None, self._legs(self._slice(self._frame_name('contact_forces', frame)))
+
+    def _tables(self, field):
+        self.sim.forward()
+        return self.sim.get(field)
+
+    def feet_jacobians(self, frame='world', return_rot_jac=False):
+        """Translational foot Jacobians (4 x 3 x nv) at the current state (mj_jac, :681-740)."""
+        if return_rot_jac:
+            raise NotImplementedError('rotational foot Jacobians are not exported yet')
+        J = self._tables(backend.FIELD_FEET_JACP)
+        if frame == 'base':
+            R = self.sim.obs[:, 25:34].reshape(-1, 3, 3)
+            J = torch.einsum('nji,nljd->nlid', R, J)
+        elif frame != 'world':
+            raise ValueError(f"Invalid frame: {frame} != 'world' or 'base'")
+        return LegsAttr(**{leg: self._np(J[:, k]) for k, leg in enumerate(_MODEL_LEGS)})
+
+    @property
+    def mass_matrix(self):
+        return self._np(self._tables(backend.FIELD_MASS_MATRIX))
+
+    @property
+    def legs_mass_matrix(self):
+        M = self._tables(backend.FIELD_MASS_MATRIX)
+        out = {}
+        for k, leg in enumerate(_MODEL_LEGS):
+            i = 6 + 3 * k
+            out[leg] = self._np(M[:, i:i + 3, i:i + 3])
+        return LegsAttr(**out)
+
+    def get_base_inertia(self):
+        return self._np(self._tables(backend.FIELD_MASS_MATRIX)[:, 3:6, 3:6])
+
+    @property
+    def legs_qfrc_bias(self):
+        b = self._tables(backend.FIELD_QFRC_BIAS)
+        return LegsAttr(**{leg: self._np(b[:, 6 + 3 * k:9 + 3 * k]) for k, leg in enumerate(_MODEL_LEGS)})
+
+    @property
+    def legs_qfrc_passive(self):
+        b = self._tables(backend.FIELD_QFRC_PASSIVE)
+        return LegsAttr(**{leg: self._np(b[:, 6 + 3 * k:9 + 3 * k]) for k, leg in enumerate(_MODEL_LEGS)})
+
+    @property
+    def com(self):
+        return self._np(self._tables(backend.FIELD_COM))
+
+    def hip_positions(self, frame='world') -> LegsAttr:
+        x = self._tables(backend.FIELD_XPOS)  # bodies 1..13
+        if frame == 'base':  # the reference applies R^T without subtracting the base position (:581-595)
+            R = self.sim.obs[:, 25:34].reshape(-1, 3, 3)
+            x = torch.einsum('nji,nbj->nbi', R, x)
+        elif frame != 'world':
+            raise ValueError(f"Invalid frame: {frame} != 'world' or 'base'")
+        return LegsAttr(**{leg: self._np(x[:, 1 + 3 * k]) for k, leg in enumerate(_MODEL_LEGS)})
+
+    @property
+    def base_configuration(self):
+        R = self.sim.obs[:, 25:34].reshape(-1, 3, 3)
+        X = torch.eye(4, device=self.device).repeat(self.num_envs, 1, 1)
+        X[:, :3, :3] = R
+        X[:, :3, 3] = self.sim.base_pos64.to(torch.float32)
+        return self._np(X)
+
+    @property
+    def joint_space_state(self):
+        return self._np(self.sim.qpos[:, 7:]), self._np(self.sim.qvel[:, 6:])
+
+    @property
+    def base_pos(self):
+        return self._np(self.sim.base_pos64)
+
+    @property
+    def base_ori_euler_xyz(self):
+        return self._slice('base_ori_euler_xyz')
+
+    @property
+    def heading_orientation_SO3(self):
+        yaw = self.sim.obs[:, 20]
+        c, s, z, o = torch.cos(yaw), torch.sin(yaw), torch.zeros_like(yaw), torch.ones_like(yaw)
+        return self._np(torch.stack([c, -s, z, s, c, z, z, z, o], dim=1).reshape(-1, 3, 3))
+
+    @property
+    def torque_ctrl_setpoint(self):
+        return self._slice('tau_ctrl_setpoint')
+
+    @property
+    def gravity_vector(self):
+        return self._slice('gravity_vector:base')
+
+    @property
+    def kinetic_energy(self):
+        return self._slice('kinetic_energy')
+
+    @property
+    def work(self):
+        return self._slice('work')
+
+    @property
+    def simulation_dt(self):
+        return self.model.c.timestep
+
+    @property
+    def simulation_time(self):
+        return float(self.sim.sim_time[0].item()) if self.num_envs == 1 else self.sim.sim_time
+
+    def get_hyperparameters(self):
+        return copy.copy(self._init_args)
+
+    # ------------------------------------------------------------------ schedules (:293-305, :1046-1139)
+    def _reseed(self, seed: int):
+        """`np.random.seed(seed)` equivalent for the counter-based generator: restart the reset stream under a new key."""
+        old = self.sim
+        state = (old.qpos.clone(), old.qvel.clone(), old.base_pos64.clone())
+        use_imu, noise = bool(old.cfg.use_imu), (old.cfg.imu_accel_noise, old.cfg.imu_gyro_noise, old.cfg.imu_accel_bias_rate, old.cfg.imu_gyro_bias_rate)
+        old.close()
+        self.sim = BatchSim(self.model, self.num_envs, device=self.device, precision=old.cfg.precision, use_imu=use_imu,
+                            imu_noise=noise, seed=seed, env_id_offset=old.cfg.env_id_offset)
+        self.sim.qpos.copy_(state[0]); self.sim.qvel.copy_(state[1]); self.sim.base_pos64.copy_(state[2])
+
+    def _advance_velocity_schedule(self):
+        n, dev = self.num_envs, self.device
+        if self._vel_schedule is None:
+            self._vel_schedule = [torch.zeros(n, dtype=torch.int32, device=dev), torch.randint(1000, 3000, (n,), dtype=torch.int32, device=dev)]
+        cnt, lim = self._vel_schedule
+        cnt += 1
+        due = cnt >= lim
+        if bool(due.any()):
+            lo, hi = self.base_lin_vel_range
+            norm = lo + (hi - lo) * torch.rand(n, device=dev)
+            if self._command_mode & backend.CMD_RANDOM:
+                ang = (torch.rand(n, device=dev) * 2 - 1) * math.pi
+                hx, hy = torch.cos(ang), torch.sin(ang)
+            else:
+                hx, hy = torch.ones(n, device=dev), torch.zeros(n, device=dev)
+            alo, ahi = self.base_ang_vel_range
+            yawrate = (alo + (ahi - alo) * torch.rand(n, device=dev)) if self._command_mode & backend.CMD_ROTATE else torch.zeros(n, device=dev)
+            new = torch.stack([norm * hx, norm * hy, torch.zeros(n, device=dev), yawrate], dim=1)
+            self.sim.command[due] = new[due]
+            cnt[due] = 0
+            lim[due] = torch.randint(1000, 3000, (int(due.sum().item()),), dtype=torch.int32, device=dev)
+
+    def _sample_external_disturbances(self, which: torch.Tensor):
+        kw, n, dev = self.external_disturbances_kwargs, self.num_envs, self.device
+        if self._ext_schedule is None:
+            self._ext_schedule = [torch.zeros(n, dtype=torch.int32, device=dev), torch.randint(1000, 3000, (n,), dtype=torch.int32, device=dev),
+                                  torch.zeros(n, 6, device=dev)]
+        cnt, lim, val = self._ext_schedule
+        cnt[which] = 0
+        lim[which] = torch.randint(1000, 3000, (int(which.sum().item()),), dtype=torch.int32, device=dev)
+        for k, key in enumerate(('x', 'y', 'z', 'roll', 'pitch', 'yaw')):
+            col = torch.zeros(n, device=dev)
+            if key in kw:
+                r = kw[key]
+                col = torch.full((n,), float(r[0]), device=dev) if len(r) == 1 else float(r[0]) + (float(r[1]) - float(r[0])) * torch.rand(n, device=dev)
+            val[which, k] = col[which]
+
+    def _advance_disturbance_schedule(self):
+        cnt, lim, val = self._ext_schedule
+        cnt += 1
+        due = cnt >= lim
+        if bool(due.any()):
+            self._sample_external_disturbances(due)
+        self.sim.qfrc_applied.copy_(val)  # acts on the next step, as in the reference (:305)
+
+    def __str__(self):
+        msg = f'robot={self._init_args["robot"]} terrain={self._init_args["scene"]} task={self.base_vel_command_type} num_envs={self.num_envs}'
+        if self.base_vel_command_type != 'human':
+            msg += (f' lin_vel_range=({self.base_lin_vel_range[0]:.3f}, {self.base_lin_vel_range[1]:.3f})'
+                    f' ang_vel_range=({self.base_ang_vel_range[0]:.3f}, {self.base_ang_vel_range[1]:.3f})'
+                    f' lat_friction_range=({self.ground_friction_coeff_range[0]:.1e}, {self.ground_friction_coeff_range[1]:.1e})')
+        return msg

@@ -228,8 +228,15 @@ int qs_bind(QsHandle* h, const QsBuffers* dev_buffers);
 int qs_step(QsHandle* h, const float* dev_ctrl, float* dev_obs, float* dev_reward,
             uint8_t* dev_terminated, uint8_t* dev_truncated, void* cuda_stream);
 
-/* same call with HOST buffers: H2D(ctrl) -> step -> D2H(obs, reward, flags), stream-synchronised. */
-int qs_step_host(QsHandle* h, const float* host_ctrl, float* host_obs, float* host_reward,
+/* qs_step followed, inside the same kernel launch, by a random reset (as qs_reset with the given options) of every env
+ * that just terminated.  For those envs `terminated` stays 1 and obs / state hold the post-reset values (the usual
+ * vectorised-rollout convention); the reference leaves this loop to the caller (quadruped_env.py:1419-1421). */
+int qs_step_autoreset(QsHandle* h, const float* dev_ctrl, const QsResetOptions* opt, float* dev_obs, float* dev_reward,
+                      uint8_t* dev_terminated, uint8_t* dev_truncated, void* cuda_stream);
+
+/* same call with HOST buffers: H2D(ctrl) -> step -> D2H(obs, reward, flags), stream-synchronised.
+ * auto_reset: NULL = plain qs_step, else qs_step_autoreset with these options. */
+int qs_step_host(QsHandle* h, const float* host_ctrl, const QsResetOptions* auto_reset, float* host_obs, float* host_reward,
                  uint8_t* host_terminated, uint8_t* host_truncated, void* cuda_stream);
 
 /* reset, quadruped_env.py:309-406. env_mask [N] (NULL = all). If dev_qpos/dev_qvel are non-NULL

@@ -33,6 +33,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
   double base64[3] = {qpos[0], qpos[1], qpos[2]};
   WarpCtx ctx;
   int iters = 0, maxed = 0;
+  std::vector<float> bias_buf(18, 0.f);
   unsigned cmask = 0, imask = 0;
   bool oob = false;
   std::vector<std::thread> th;
@@ -41,6 +42,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       g_ctx = &ctx;
       g_lane = lane;
       Env<real, NCON, MAXDIM> e(*dm, *ws, verts.data(), lane);
+      e.bias_out = bias_buf.data();
       e.forward(max_iter, real(tol));
       auto f = e.flags();
       if (mode == 1) {
@@ -62,7 +64,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
     misc[k++] = iters; misc[k++] = maxed; misc[k++] = cmask; misc[k++] = imask; misc[k++] = oob; misc[k++] = ws->ncon; misc[k++] = ws->overflow;
     k = 8;
     for (int i = 0; i < 18; i++) misc[k++] = double(ws->qacc[i]);      // 8
-    for (int i = 0; i < 18; i++) misc[k++] = double(ws->bias[i]);      // 26
+    for (int i = 0; i < 18; i++) misc[k++] = double(bias_buf[i]);      // 26
     for (int i = 0; i < 18; i++) misc[k++] = double(ws->fsm[i]);       // 44
     for (int i = 0; i < 18; i++) misc[k++] = double(ws->asmooth[i]);   // 62
     for (int i = 0; i < 18; i++) misc[k++] = double(ws->fcon[i]);      // 80
@@ -78,11 +80,14 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       }
     // contacts, 422: per contact dist,pos3,frame9,F3,geom,body,mu,dim
     for (int c = 0; c < ws->ncon; c++) {
+      const int info = ws->c_info[c], dim = info >> 16;
       misc[k++] = ws->c_dist[c];
       misc[k++] = ws->c_pos[c][0] + ws->org[0]; misc[k++] = ws->c_pos[c][1] + ws->org[1]; misc[k++] = ws->c_pos[c][2];
-      for (int i = 0; i < 9; i++) misc[k++] = ws->c_frame[c][i];
-      for (int i = 0; i < 3; i++) misc[k++] = (i < ws->c_dim[c]) ? double(ws->c_F[c][i]) : 0.0;
-      misc[k++] = ws->c_geom[c]; misc[k++] = ws->c_body[c]; misc[k++] = ws->c_fri[c][0]; misc[k++] = ws->c_dim[c];
+      const real* f = ws->c_frame[c];
+      for (int i = 0; i < 6; i++) misc[k++] = f[i];
+      misc[k++] = f[1] * f[5] - f[2] * f[4]; misc[k++] = f[2] * f[3] - f[0] * f[5]; misc[k++] = f[0] * f[4] - f[1] * f[3];
+      for (int i = 0; i < 3; i++) misc[k++] = (i < dim) ? double(ws->c_F[c][i]) : 0.0;
+      misc[k++] = info & 0xff; misc[k++] = (info >> 8) & 0xff; misc[k++] = ws->c_fri[c][0]; misc[k++] = dim;
     }
     // sensors at 422 + 20*16 = 742
     k = 742;

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #define QS_DEV inline
+#define QS_NOINLINE
 namespace qs {
 struct WarpCtx {
   std::barrier<> bar{32};
@@ -37,5 +38,6 @@ inline unsigned ballot(bool p) {
   return m;
 }
 inline int popc(unsigned x) { return __builtin_popcount(x); }
+inline int ctz(unsigned x) { return __builtin_ctz(x); }
 inline uint32_t umulhi(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * uint64_t(b)) >> 32); }
 }  // namespace qs
