@@ -1,0 +1,68 @@
+"""Compiled model tables and procedural terrain against the reference's own numbers."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from gym_quadruped_b200.model import Model, load_robot_tables
+from gym_quadruped_b200.terrain import FLAT_LIMITS, generate_terrain, perlin_image, world_of_boxes
+
+GOLDEN = Path(__file__).resolve().parent / 'golden'
+
+
+@pytest.mark.parametrize('robot', ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1'])
+def test_random_boxes_bit_exact_against_reference_generator(robot):
+    g = json.loads((GOLDEN / f'terrain_boxes_{robot}.json').read_text())  # dumped from the reference's terrain.py
+    t = world_of_boxes(g['hip_height'])
+    assert len(t['box_pos']) == 100 and g['n_world_geoms'] == 101
+    assert np.array_equal(t['box_pos'], np.array(g['pos']))
+    assert np.array_equal(t['box_half'], np.array(g['half']))
+    np.testing.assert_allclose(t['box_quat'], np.array(g['quat']), atol=1e-15)
+    assert tuple(t['terrain_limits']) == tuple(g['terrain_limits'])
+
+
+def test_flat_and_perlin_scene_tables():
+    assert generate_terrain('flat', 0.3)['terrain_limits'] == FLAT_LIMITS == (10000, -10000, 10000, -10000)
+    t = generate_terrain('perlin', 0.35)
+    assert t['data'].shape == (128, 128) and t['data'].min() == 0.0 and t['data'].max() == 1.0
+    np.testing.assert_allclose(t['size'], (17.5, 17.5, 0.70, 0.005))
+    np.testing.assert_allclose(t['terrain_limits'], (14.0, -14.0, 14.0, -14.0))
+    img = perlin_image()  # regression values of SURVEY.md App. D.5 (best-effort restatement of the absent `noise` package)
+    assert (img.min(), img.max()) == (64, 195) and list(img[0, :6]) == [127, 136, 129, 135, 143, 143]
+    assert list(img[64, 60:66]) == [158, 152, 152, 159, 164, 177]
+    with pytest.raises(ValueError):
+        generate_terrain('stairs', 0.3)
+
+
+def test_model_constants_from_the_mjcf():
+    """SURVEY.md App. C, values read from the XML files."""
+    mc = load_robot_tables('mini_cheetah')
+    assert abs(mc['total_mass'] - 12.473) < 1e-3 and mc['cone'] == 'pyramidal' and mc['hip_height'] == 0.225
+    assert sum(mc['jnt_limited']) == 0                                   # ranges live in unused default classes (App. B.14)
+    assert len(mc['geoms']) == 15 and sum(g['type'] == 7 for g in mc['geoms']) == 11
+    assert all(g['condim'] == 1 and g['margin'] == 0.001 and g['friction'][0] == 0.6 for g in mc['geoms'])
+    np.testing.assert_allclose(mc['act_ctrlrange'][:3], [[-23.7, 23.7], [-23.7, 23.7], [-45.43, 45.43]])
+    np.testing.assert_allclose(mc['qpos0'][7:13], [0, -np.pi / 2, 0, 0, -np.pi / 2, 0])
+    np.testing.assert_allclose(mc['dof_damping'][6:], 0.2); np.testing.assert_allclose(mc['dof_frictionloss'][6:], 0.2)
+    al = load_robot_tables('aliengo')
+    assert abs(al['total_mass'] - 24.638) < 1e-3 and al['jnt_limited'] == [1, 0, 1] * 4
+    assert sorted(g['type'] for g in al['geoms']).count(6) == 9 and sum(g['type'] == 3 for g in al['geoms']) == 4
+    go2 = load_robot_tables('go2')
+    assert go2['cone'] == 'elliptic' and go2['impratio'] == 100 and len(go2['geoms']) == 31
+    foot = go2['geoms'][go2['foot_geom'][0]]
+    assert foot['condim'] == 6 and foot['priority'] == 1 and foot['friction'] == [0.8, 0.02, 0.01]
+    hy = load_robot_tables('hyqreal1')
+    assert abs(hy['total_mass'] - 107.573) < 1e-2 and hy['sensor_adr']['Body_Acc'] == 24  # 24 joint sensors come first
+    radii = [hy['geoms'][i]['size'][0] for i in hy['foot_geom']]
+    assert radii == [0.036, 0.032, 0.032, 0.032]                          # App. B.15
+    assert hy['imu'] is not None and hy['imu']['accel_name'] == 'Body_Acc'
+
+
+def test_qsmodel_struct_roundtrip():
+    m = Model('go2', 'random_boxes')
+    assert m.c.nbox == 100 and m.c.terrain_type == 2 and m.c.cone == 1 and m.c.ngeom == 31
+    np.testing.assert_allclose(m.terrain_limits[0], 8.051757569573601)
+    assert list(m.c.body_parent) == [0, 0, 1, 2, 3, 1, 5, 6, 1, 8, 9, 1, 11, 12]
+    with pytest.raises(ValueError):
+        Model('hyqreal', 'flat')  # the reference rejects this name too (robot_cfgs.py:49-58)
