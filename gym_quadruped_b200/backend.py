@@ -91,7 +91,7 @@ class BatchSim:
 
     def __init__(self, model: Model, num_envs: int, device: int | str | torch.device = 0, precision: int = 0,
                  use_imu: bool = False, imu_noise=(0.01, 0.01, 0.01, 0.01), seed: int = 0, env_id_offset: int = 0,
-                 solver_max_iter: int = 0):
+                 solver_max_iter: int = 0, heightmap: tuple | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError('gym_quadruped_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
         self.L = load_library()
@@ -107,6 +107,8 @@ class BatchSim:
             raise ValueError(f'robot {model.robot} has no accelerometer/gyro pair in its model')
         cfg.imu_accel_noise, cfg.imu_gyro_noise, cfg.imu_accel_bias_rate, cfg.imu_gyro_bias_rate = [float(x) for x in imu_noise]
         cfg.seed, cfg.env_id_offset, cfg.solver_max_iter = int(seed), int(env_id_offset), int(solver_max_iter)
+        if heightmap is not None:  # (rows, cols, dx, dy): appended to every observation row
+            cfg.hm_rows, cfg.hm_cols, cfg.hm_dx, cfg.hm_dy = int(heightmap[0]), int(heightmap[1]), float(heightmap[2]), float(heightmap[3])
         self.cfg = cfg
         self.obs_dim = self.L.qs_obs_dim(C.byref(cfg))
         self.h = C.c_void_p()

@@ -24,6 +24,8 @@ constexpr int NLIM = 12;  // joint-limit units (one slot per hinge; lower and up
 enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_BOX = 6, GEOM_MESH = 7 };
 
 template <typename real> struct alignas(16) Vert4 { real x, y, z, w; };
+// static terrain box (random_boxes scene): centre, rotation (row-major), half sizes, bounding radius
+template <typename real> struct alignas(16) DBox { real pos[3], mat[9], half[3], rad; };
 
 // Robot + scene constants in the kernel's precision; built on the host from QsModel (qstep.cu: build_dmodel),
 // staged into shared memory once per CTA with one TMA bulk copy.
@@ -34,7 +36,9 @@ template <typename real> struct alignas(16) DModel {
   real floor_fri[4];
   real imu_pos[4];
   real imu_mat[12];
-  real mass_total, pad_r[3];
+  real mass_total, robot_radius, pad_r[2];
+  real hf_size[4], hf_pos[4];          // height field: half-x, half-y, z-scale, base; position
+  real terr_fri[4], terr_margin, terr_pad[3];  // hfield / box geoms carry default parameters
   real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_imat[NB][9], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
   real jnt_pos[NJ][3], jnt_axis[NJ][3], jnt_range[NJ][2], jnt_K[NJ], jnt_B[NJ], jnt_solimp[NJ][5], jnt_margin[NJ];
   real qpos0[20], key_qpos[20];
@@ -43,6 +47,7 @@ template <typename real> struct alignas(16) DModel {
   real geom_pos[MAXGEOM][3], geom_mat[MAXGEOM][9], geom_size[MAXGEOM][3], geom_bcenter[MAXGEOM][3], geom_bhalf[MAXGEOM][3], geom_rbound[MAXGEOM],
       geom_fri[MAXGEOM][3], geom_margin[MAXGEOM], geom_incmargin[MAXGEOM], geom_K[MAXGEOM], geom_B[MAXGEOM], geom_solimp[MAXGEOM][5];
   int cone, iterations, ls_iterations, ngeom, nvert, terrain_type, nbox, has_imu;
+  int hf_nrow, hf_ncol, terr_pad_i[2];
   int jnt_limited[NJ];
   int geom_type[MAXGEOM], geom_body[MAXGEOM], geom_leg[MAXGEOM], geom_vertadr[MAXGEOM], geom_vertnum[MAXGEOM], geom_dim[MAXGEOM],
       geom_prio[MAXGEOM];
@@ -95,13 +100,15 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   const DModel<real>& m;
   W& w;
   const Vert4<real>* vert;
+  const real* hf;             // height-field samples [nrow][ncol] in [0,1] (global memory), or nullptr
+  const DBox<real>* boxes;    // static terrain boxes (global memory), or nullptr
   const int lane;
   int solver_iter, ls_evals;
   bool solver_maxed;
   float* bias_out;  // optional destination for qfrc_bias (accessor dump), else nullptr
 
   QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_)
-      : m(m_), w(w_), vert(v_), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {}
+      : m(m_), w(w_), vert(v_), hf(nullptr), boxes(nullptr), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {}
 
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
@@ -464,7 +471,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV void contact_friction(int g, bool world_is_floor, real* fri) const {
     real gf[3] = {m.geom_fri[g][0], m.geom_fri[g][1], m.geom_fri[g][2]};
     if (m.geom_leg[g] >= 0 && w.mu_feet >= 0) { gf[0] = w.mu_feet; gf[1] = real(0.005); gf[2] = 0; }   // quadruped_env.py:1290-1296
-    real wf[3] = {m.floor_fri[0], m.floor_fri[1], m.floor_fri[2]};
+    real wf[3] = {world_is_floor ? m.floor_fri[0] : m.terr_fri[0], world_is_floor ? m.floor_fri[1] : m.terr_fri[1], world_is_floor ? m.floor_fri[2] : m.terr_fri[2]};
     if (world_is_floor && w.mu_floor >= 0) { wf[0] = w.mu_floor; wf[1] = real(0.005); wf[2] = 0; }
     const int prio = m.geom_prio[g];
     for (int i = 0; i < 3; i++) {
@@ -496,6 +503,195 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (k == 0) { out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; }
     else if (k == 1) { out[0] = f[3]; out[1] = f[4]; out[2] = f[5]; }
     else cross3(out, f, f + 3);
+  }
+
+  // ------------------------------------------------------------------ terrain beyond the floor plane
+  // height of the perlin field under (x, y) and the unit normal of the triangle there; cells split along (0,0)-(1,1) [MJ]
+  QS_DEV bool hfield_height(real x, real y, real& z, real* n) const {
+    const real sx = m.hf_size[0], sy = m.hf_size[1], sz = m.hf_size[2];
+    const real lx = x - m.hf_pos[0], ly = y - m.hf_pos[1];
+    if (lx < -sx || lx > sx || ly < -sy || ly > sy) return false;
+    const int nc = m.hf_ncol, nr = m.hf_nrow;
+    const real dx = 2 * sx / real(nc - 1), dy = 2 * sy / real(nr - 1);
+    int c = int(N::floor((lx + sx) / dx)), r = int(N::floor((ly + sy) / dy));
+    c = c > nc - 2 ? nc - 2 : (c < 0 ? 0 : c);
+    r = r > nr - 2 ? nr - 2 : (r < 0 ? 0 : r);
+    const real u = (lx + sx - c * dx) / dx, v = (ly + sy - r * dy) / dy;
+    const real z00 = sz * hf[r * nc + c], z10 = sz * hf[r * nc + c + 1], z01 = sz * hf[(r + 1) * nc + c], z11 = sz * hf[(r + 1) * nc + c + 1];
+    real gx, gy;
+    if (u >= v) { z = z00 + u * (z10 - z00) + v * (z11 - z10); gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; }
+    else { z = z00 + u * (z11 - z01) + v * (z01 - z00); gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; }
+    z += m.hf_pos[2];
+    const real inv = N::rsqrt(gx * gx + gy * gy + 1);
+    n[0] = -gx * inv; n[1] = -gy * inv; n[2] = inv;
+    return true;
+  }
+
+  // candidate terrain contact kept in registers by the geom's lane (the 4 deepest per geom survive)
+  struct Cand { real dist, pos[3], nrm[3], sign; };
+  QS_DEV static void cand_insert(Cand* list, int& n, const Cand& c) {
+    int k = n < 4 ? n : 4;
+    if (n >= 4 && !(c.dist < list[3].dist)) return;
+    if (k == 4) k = 3;
+    while (k > 0 && c.dist < list[k - 1].dist) { list[k] = list[k - 1]; k--; }
+    list[k] = c;
+    if (n < 4) n++;
+  }
+  // point feature (centre p, radius r) against the height field or the candidate boxes; robot_first: sphere / capsule sort
+  // before box in the engine's geom ordering, so the robot geom is geom1 and the normal points from it into the box
+  QS_DEV void point_vs_terrain(const real* p, real r, real margin, bool robot_first, const unsigned* boxmask, Cand* list, int& n) const {
+    if (m.terrain_type == 1) {
+      real z, nn[3];
+      if (!hfield_height(p[0], p[1], z, nn)) return;
+      const real dist = (p[2] - z) * nn[2] - r;
+      if (dist > margin) return;
+      Cand c;
+      c.dist = dist; c.sign = 1;
+      for (int i = 0; i < 3; i++) { c.nrm[i] = nn[i]; c.pos[i] = p[i] - nn[i] * (r + real(0.5) * dist); }
+      cand_insert(list, n, c);
+    } else if (m.terrain_type == 2) {
+      for (int wd = 0; wd < 4; wd++) {
+        unsigned mask = boxmask[wd];
+        while (mask) {
+          const int b = 32 * wd + ctz(mask);
+          mask &= mask - 1;
+          const DBox<real>& bx = boxes[b];
+          const real rel[3] = {p[0] - bx.pos[0], p[1] - bx.pos[1], p[2] - bx.pos[2]};
+          const real reach = bx.rad + r + real(0.01);
+          if (dot3(rel, rel) > reach * reach) continue;
+          real q[3], cl, dl[3], nl[3] = {0, 0, 0}, dist;
+          mul_mtv(q, bx.mat, rel);
+          bool inside = true;
+          for (int i = 0; i < 3; i++) { cl = q[i] < -bx.half[i] ? -bx.half[i] : (q[i] > bx.half[i] ? bx.half[i] : q[i]); dl[i] = q[i] - cl; if (dl[i] != 0) inside = false; }
+          if (!inside) {
+            const real len = N::sqrt(dot3(dl, dl));
+            dist = len - r;
+            for (int i = 0; i < 3; i++) nl[i] = dl[i] / len;
+          } else {
+            int best = 0;
+            real depth = N::big;
+            for (int i = 0; i < 3; i++) { const real e = bx.half[i] - N::abs(q[i]); if (e < depth) { depth = e; best = i; } }
+            dist = -depth - r;
+            nl[best] = q[best] >= 0 ? real(1) : real(-1);
+          }
+          if (dist > margin) continue;
+          real nw[3];
+          mul_mv(nw, bx.mat, nl);
+          Cand c;
+          c.dist = dist; c.sign = robot_first ? real(-1) : real(1);
+          for (int i = 0; i < 3; i++) { c.pos[i] = p[i] - nw[i] * (r + real(0.5) * dist); c.nrm[i] = robot_first ? -nw[i] : nw[i]; }
+          cand_insert(list, n, c);
+        }
+      }
+    }
+  }
+
+  // Primitive robot geoms against the perlin height field / the static boxes, as feature points (sphere centre + radius, capsule
+  // end spheres, box corners) -- exact for sphere-box and plane-like cases, an approximation of the engine's capsule-box,
+  // box-box and prism-based hfield routines otherwise (documented in DESIGN.md).  Appends after the floor contacts.
+  QS_DEV void collide_terrain(int& ncon) {
+    unsigned boxmask[4] = {0, 0, 0, 0};
+    if (m.terrain_type == 2) {
+      for (int wd = 0; wd < 4; wd++) {
+        const int b = 32 * wd + lane;
+        bool near = false;
+        if (b < m.nbox) {
+          const real rel[3] = {boxes[b].pos[0] - w.kin.xpos[1][0], boxes[b].pos[1] - w.kin.xpos[1][1], boxes[b].pos[2] - w.kin.xpos[1][2]};
+          const real reach = boxes[b].rad + m.robot_radius;
+          near = dot3(rel, rel) < reach * reach;
+        }
+        boxmask[wd] = ballot(near);
+      }
+    }
+    Cand list[4];
+    int n = 0;
+    const int g = lane;
+    real yh[3] = {0, 0, 0};
+    bool is_caps = false;
+    if (g < m.ngeom && m.geom_type[g] != GEOM_MESH) {
+      const int b = m.geom_body[g], type = m.geom_type[g];
+      real gx[3], tmp[3];
+      mul_mv(tmp, w.kin.xmat[b], m.geom_pos[g]);
+      for (int i = 0; i < 3; i++) gx[i] = w.kin.xpos[b][i] + tmp[i];
+      const real margin = N::max(m.geom_margin[g], m.terr_margin);
+      const real* sz = m.geom_size[g];
+      if (type == GEOM_SPHERE) {
+        point_vs_terrain(gx, sz[0], margin, true, boxmask, list, n);
+      } else if (type == GEOM_CAPSULE) {
+        real gz[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]}, axis[3];
+        mul_mv(axis, w.kin.xmat[b], gz);
+        for (int i = 0; i < 3; i++) yh[i] = axis[i];
+        is_caps = true;
+        for (int s = 1; s >= -1; s -= 2) {
+          const real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
+          point_vs_terrain(p, sz[0], margin, true, boxmask, list, n);
+        }
+      } else if (type == GEOM_BOX) {
+        real gm[9];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.kin.xmat[b][3 * r] * m.geom_mat[g][c] + w.kin.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.kin.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
+        for (int i = 0; i < 8; i++) {
+          const real v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]};
+          real corner[3];
+          mul_mv(corner, gm, v);
+          const real p[3] = {corner[0] + gx[0], corner[1] + gx[1], corner[2] + gx[2]};
+          point_vs_terrain(p, real(0), margin, false, boxmask, list, n);
+        }
+      }
+    }
+    for (int r = 0; r < 4; r++) {
+      const bool has = n > r;
+      const unsigned mask = ballot(has);
+      if (mask == 0) break;
+      const int slot = ncon + popc(mask & ((1u << lane) - 1u));
+      if (has && slot < NCON) store_contact(slot, g, list[r].sign, list[r].dist, list[r].pos, list[r].nrm, is_caps ? yh : nullptr, false);
+      ncon += popc(mask);
+    }
+  }
+
+  // downward ray from `org` against the static terrain: distance to the nearest hit or -1 ([MJ] mj_ray, heightmap.py:77-99)
+  QS_DEV real ray_down(const real* org) const {
+    real best = org[2] >= 0 ? org[2] : real(-1);  // floor plane z = 0
+    if (m.terrain_type == 1) {
+      real z, nn[3];
+      if (hfield_height(org[0], org[1], z, nn) && org[2] >= z) { const real t = org[2] - z; if (best < 0 || t < best) best = t; }
+    } else if (m.terrain_type == 2) {
+      for (int b = 0; b < m.nbox; b++) {
+        const DBox<real>& bx = boxes[b];
+        const real rel[3] = {org[0] - bx.pos[0], org[1] - bx.pos[1], org[2] - bx.pos[2]};
+        if (rel[0] * rel[0] + rel[1] * rel[1] > bx.rad * bx.rad) continue;
+        real o[3];
+        mul_mtv(o, bx.mat, rel);
+        const real dl[3] = {-bx.mat[6], -bx.mat[7], -bx.mat[8]};  // R^T (0,0,-1)
+        real tmin = -N::big, tmax = N::big;
+        bool miss = false;
+        for (int i = 0; i < 3; i++) {
+          if (N::abs(dl[i]) < real(1e-12)) { if (o[i] < -bx.half[i] || o[i] > bx.half[i]) miss = true; continue; }
+          real t1 = (-bx.half[i] - o[i]) / dl[i], t2 = (bx.half[i] - o[i]) / dl[i];
+          if (t1 > t2) { const real t = t1; t1 = t2; t2 = t; }
+          tmin = N::max(tmin, t1); tmax = N::min(tmax, t2);
+        }
+        if (miss || tmin > tmax || tmax < 0) continue;
+        const real t = tmin >= 0 ? tmin : tmax;
+        if (best < 0 || t < best) best = t;
+      }
+    }
+    return best;
+  }
+
+  // HeightMap.create_sensor_matrix (sensors/heightmap.py:106-169): rows x cols hit points around `center` with heading `yaw`,
+  // written as [rows][cols][3] floats to `out` (global memory); lanes stride over the grid cells
+  QS_DEV void heightmap(const real* center, real yaw, int rows, int cols, real dx, real dy, real ox, real oy, float* out) const {
+    const real c_rows = rows % 2 == 0 ? real(rows) / 2 : real(rows - 1) / 2, add_r = rows % 2 == 0 ? -dx / 2 : real(0);
+    const real c_cols = cols % 2 == 0 ? real(cols) / 2 : real(cols - 1) / 2, add_c = cols % 2 == 0 ? -dy / 2 : real(0);
+    real sy, cy;
+    N::sincos(yaw, &sy, &cy);
+    for (int it = lane; it < rows * cols; it += 32) {
+      const int i = it / cols, j = it % cols;
+      const real offx = dx * (c_rows - i) + add_r, offy = dy * (c_cols - j) + add_c;
+      const real org[3] = {center[0] + cy * offx - sy * offy, center[1] + sy * offx + cy * offy, center[2] + real(0.6) - real(0.07)};
+      const real t = ray_down(org);
+      out[3 * it] = float(org[0] + ox); out[3 * it + 1] = float(org[1] + oy); out[3 * it + 2] = float(org[2] - t);
+    }
   }
 
   // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
@@ -553,6 +749,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       ncon += popc(mask);
     }
+    if (m.terrain_type != 0) collide_terrain(ncon);
     // convex meshes. Broad phase: lanes test the body-frame bounding box of every mesh against the plane (a lower bound of the
     // hull's lowest point, tight for long thin links); only the survivors are scanned, by the whole warp, for their support vertex.
     unsigned cand;

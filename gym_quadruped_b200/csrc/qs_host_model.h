@@ -54,6 +54,23 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
     if (s.body_parent[b] != expect) return "body tree is not base + 4 x (hip, thigh, calf)";
   }
   d.mass_total = real(mass);
+  {  // conservative reach of any robot geom from the base origin (terrain broad phase)
+    double reach = 0;
+    for (int l = 0; l < 4; l++) {
+      double chain = 0;
+      for (int k = 0; k < 3; k++) { const double* bp = s.body_pos[2 + 3 * l + k]; chain += std::sqrt(bp[0] * bp[0] + bp[1] * bp[1] + bp[2] * bp[2]); }
+      reach = std::max(reach, chain);
+    }
+    double gext = 0;
+    for (int g = 0; g < s.ngeom; g++) { const double* gp = s.geom_pos[g]; gext = std::max(gext, std::sqrt(gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2]) + s.geom_rbound[g]); }
+    d.robot_radius = real(reach + gext + 0.05);
+  }
+  for (int i = 0; i < 4; i++) d.hf_size[i] = real(s.hf_size[i]);
+  for (int i = 0; i < 3; i++) { d.hf_pos[i] = real(s.hf_pos[i]); d.terr_fri[i] = real(s.box_par.friction[i]); }
+  d.terr_margin = real(s.box_par.margin);
+  d.hf_nrow = s.hf_nrow; d.hf_ncol = s.hf_ncol;
+  if (s.terrain_type == QS_TERRAIN_HFIELD && (s.hf_nrow < 2 || s.hf_ncol < 2 || !s.hf_data)) return "height field data missing";
+  if (s.terrain_type == QS_TERRAIN_BOXES && (s.nbox < 0 || s.nbox > QS_MAXBOX)) return "nbox out of range";
   for (int j = 0; j < QS_NJNT; j++) {
     for (int i = 0; i < 3; i++) {
       if (s.jnt_pos[j][i] != 0.0) return "joint anchors offset from the body origin (jnt_pos != 0) are not supported";
@@ -144,6 +161,25 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   verts.resize(std::max(1, s.nvert));
   for (int i = 0; i < s.nvert; i++) { verts[i].x = real(s.vert[3 * i]); verts[i].y = real(s.vert[3 * i + 1]); verts[i].z = real(s.vert[3 * i + 2]); verts[i].w = 0; }
   return "";
+}
+
+template <typename real> std::vector<DBox<real>> build_boxes(const QsModel& s) {
+  std::vector<DBox<real>> out(std::max(1, s.nbox));
+  for (int b = 0; b < s.nbox; b++) {
+    double m9[9];
+    quat2mat(s.box_quat[b], m9);
+    double r2 = 0;
+    for (int i = 0; i < 3; i++) { out[b].pos[i] = real(s.box_pos[b][i]); out[b].half[i] = real(s.box_half[b][i]); r2 += s.box_half[b][i] * s.box_half[b][i]; }
+    for (int i = 0; i < 9; i++) out[b].mat[i] = real(m9[i]);
+    out[b].rad = real(std::sqrt(r2));
+  }
+  return out;
+}
+template <typename real> std::vector<real> build_hfield(const QsModel& s) {
+  const size_t n = s.terrain_type == QS_TERRAIN_HFIELD ? size_t(s.hf_nrow) * s.hf_ncol : 1;
+  std::vector<real> out(n, real(0));
+  if (s.terrain_type == QS_TERRAIN_HFIELD) for (size_t i = 0; i < n; i++) out[i] = real(s.hf_data[i]);
+  return out;
 }
 
 inline int model_max_dim(const QsModel& s) {

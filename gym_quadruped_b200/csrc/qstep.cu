@@ -32,6 +32,11 @@ constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_
 struct KParams {
   const void* dm;      // DModel<real>
   const void* vert;    // Vert4<real>[nvert]
+  const void* hf;      // real[nrow*ncol] height-field samples
+  const void* boxes;   // DBox<real>[nbox]
+  int hm_rows, hm_cols;
+  float hm_dx, hm_dy;
+  float* hm_out;       // stand-alone ray cast destination [N, rows, cols, 3]
   int num_envs, obs_dim, use_imu, max_iter, env_id_offset, auto_reset;
   float tol;
   unsigned seed_lo, seed_hi;
@@ -101,7 +106,9 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   DM* dm = reinterpret_cast<DM*>(smem);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + DM_BYTES);
   W* wsbase = reinterpret_cast<W*>(smem + DM_BYTES + 128);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  // canonical warp index broadcast from lane 0: lets the compiler prove it warp-uniform, so the per-warp workspace base lives
+  // in a uniform register instead of being re-derived from threadIdx before every shared-memory access
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int env = blockIdx.x * nwarp + warp;
 
   if (threadIdx.x == 0) mbar_init(mbar, 1);
@@ -143,6 +150,8 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   syncwarp();
 
   Env<real, NCON, MAXDIM> e(m, w, reinterpret_cast<const Vert4<real>*>(p.vert), lane);
+  e.hf = reinterpret_cast<const real*>(p.hf);
+  e.boxes = reinterpret_cast<const DBox<real>*>(p.boxes);
   const unsigned env_g = unsigned(env + p.env_id_offset);
   real command[4] = {real(B.command[4 * env]), real(B.command[4 * env + 1]), real(B.command[4 * env + 2]), real(B.command[4 * env + 3])};
   float sim_time = B.sim_time[env];
@@ -338,6 +347,15 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
     if (obs)
       for (int i = lane; i < NOBS_BASE; i += 32) obs[i] = float(w.obs[i]);
+    if (obs && p.hm_rows > 0) {
+      // sensors/heightmap columns: grid around the post-step base position / heading (heightmap.py:106-169)
+      real qq[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]}, Rn[9];
+      quat_normalize(qq);
+      quat_to_mat(Rn, qq);
+      const real ctr[3] = {w.qpos[0], w.qpos[1], w.qpos[2]};
+      e.heightmap(ctr, Num<real>::atan2(Rn[3], Rn[0]), p.hm_rows, p.hm_cols, real(p.hm_dx), real(p.hm_dy), real(w.org[0]), real(w.org[1]),
+                  obs + NOBS_BASE + (p.use_imu ? QS_NOBS_IMU : 0));
+    }
     if (p.use_imu) {
       // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals
       unsigned tk = p.tick[env];
@@ -384,6 +402,29 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   }
 }
 
+// HeightMap.update_height_map for every env (sensors/heightmap.py:106-169): one warp per env, rays spread over the lanes
+template <typename real>
+__global__ void __launch_bounds__(256) raycast_kernel(const KParams p) {
+  const int lane = threadIdx.x & 31, env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= p.num_envs) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const DModel<real>& m = *reinterpret_cast<const DModel<real>*>(p.dm);
+  using W = WS<real, NCON_MAX, 3>;
+  Env<real, NCON_MAX, 3> e(m, *reinterpret_cast<W*>(smem), reinterpret_cast<const Vert4<real>*>(p.vert), lane);  // workspace is never touched
+  e.hf = reinterpret_cast<const real*>(p.hf);
+  e.boxes = reinterpret_cast<const DBox<real>*>(p.boxes);
+  const double* b64 = p.b.base_pos64 + size_t(env) * 3;
+  const float* qp = p.b.qpos + size_t(env) * NQ;
+  const bool flat = m.terrain_type == 0;
+  const double ox = flat ? rint(b64[0]) : 0.0, oy = flat ? rint(b64[1]) : 0.0;
+  real qq[4] = {real(qp[3]), real(qp[4]), real(qp[5]), real(qp[6])}, R[9];
+  quat_normalize(qq);
+  quat_to_mat(R, qq);
+  const real ctr[3] = {real(b64[0] - ox), real(b64[1] - oy), real(b64[2])};
+  e.heightmap(ctr, Num<real>::atan2(R[3], R[0]), p.hm_rows, p.hm_cols, real(p.hm_dx), real(p.hm_dy), real(ox), real(oy),
+              p.hm_out + size_t(env) * p.hm_rows * p.hm_cols * 3);
+}
+
 using KernelFn = void (*)(const KParams);
 
 template <typename real, int MAXDIM> struct Variant {
@@ -406,6 +447,9 @@ struct QsHandle_ {
   int obs_dim = 0;
   void* d_dm = nullptr;
   void* d_vert = nullptr;
+  void* d_hf = nullptr;
+  void* d_boxes = nullptr;
+  KernelFn k_raycast = nullptr;
   unsigned* d_episode = nullptr;
   unsigned* d_tick = nullptr;
   float* d_aux = nullptr;
@@ -442,6 +486,15 @@ template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const
   QS_CUDA(h, cudaMemcpy(h->d_dm, dm.get(), sizeof(DModel<real>), cudaMemcpyHostToDevice));
   QS_CUDA(h, cudaMalloc(&h->d_vert, sizeof(Vert4<real>) * verts.size()));
   QS_CUDA(h, cudaMemcpy(h->d_vert, verts.data(), sizeof(Vert4<real>) * verts.size(), cudaMemcpyHostToDevice));
+  {
+    std::vector<DBox<real>> boxes = build_boxes<real>(*model);
+    std::vector<real> hf = build_hfield<real>(*model);
+    QS_CUDA(h, cudaMalloc(&h->d_boxes, sizeof(DBox<real>) * boxes.size()));
+    QS_CUDA(h, cudaMemcpy(h->d_boxes, boxes.data(), sizeof(DBox<real>) * boxes.size(), cudaMemcpyHostToDevice));
+    QS_CUDA(h, cudaMalloc(&h->d_hf, sizeof(real) * hf.size()));
+    QS_CUDA(h, cudaMemcpy(h->d_hf, hf.data(), sizeof(real) * hf.size(), cudaMemcpyHostToDevice));
+  }
+  h->k_raycast = raycast_kernel<real>;
   using V = Variant<real, MAXDIM>;
   h->k_step = V::fn(MODE_STEP); h->k_reset = V::fn(MODE_RESET); h->k_forward = V::fn(MODE_FORWARD);
   int dev = 0, max_smem = 0;
@@ -471,8 +524,7 @@ int64_t qs_launch_count(QsHandle* h) { return h ? h->launches : 0; }
 int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
   if (!model || !cfg || !out) return fail(nullptr, 1, "null argument");
   if (cfg->num_envs <= 0) return fail(nullptr, 1, "num_envs must be positive");
-  if (model->terrain_type != QS_TERRAIN_FLAT) return fail(nullptr, 4, "only the flat scene is built in this version of libqstep");
-  if (cfg->hm_rows * cfg->hm_cols != 0) return fail(nullptr, 4, "height-map columns are not built in this version of libqstep");
+  if (cfg->hm_rows < 0 || cfg->hm_cols < 0 || cfg->hm_rows * cfg->hm_cols > 1024) return fail(nullptr, 1, "height-map grid out of range");
   QsHandle* h = new (std::nothrow) QsHandle_();
   if (!h) return fail(nullptr, 1, "out of host memory");
   h->cfg = *cfg;
@@ -482,8 +534,12 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
   if (ce != cudaSuccess) { int rc = fail(nullptr, 100 + int(ce), std::string("cudaSetDevice: ") + cudaGetErrorString(ce)); delete h; return rc; }
   h->maxdim = model_max_dim(*model) > 3 ? 6 : 3;
   int rc;
+#ifdef QS_ONLY_F3  // tuning builds: only the fp32 / condim<=3 kernels are compiled
+  rc = (cfg->precision == 0 && h->maxdim == 3) ? setup_variant<float, 3>(h, model) : fail(h, 4, "variant not compiled (QS_ONLY_F3)");
+#else
   if (cfg->precision == 0) rc = h->maxdim == 3 ? setup_variant<float, 3>(h, model) : setup_variant<float, 6>(h, model);
   else rc = h->maxdim == 3 ? setup_variant<double, 3>(h, model) : setup_variant<double, 6>(h, model);
+#endif
   if (rc == 0) {
     cudaError_t e1 = cudaMalloc(&h->d_episode, sizeof(unsigned) * cfg->num_envs), e2 = cudaMalloc(&h->d_tick, sizeof(unsigned) * cfg->num_envs);
     if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(h, 5, "cudaMalloc failed");
@@ -496,7 +552,7 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
 
 void qs_destroy(QsHandle* h) {
   if (!h) return;
-  cudaFree(h->d_dm); cudaFree(h->d_vert); cudaFree(h->d_episode); cudaFree(h->d_tick); cudaFree(h->d_aux);
+  cudaFree(h->d_dm); cudaFree(h->d_vert); cudaFree(h->d_hf); cudaFree(h->d_boxes); cudaFree(h->d_episode); cudaFree(h->d_tick); cudaFree(h->d_aux);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
   delete h;
 }
@@ -513,7 +569,8 @@ int qs_bind(QsHandle* h, const QsBuffers* b) {
 
 static KParams base_params(QsHandle* h) {
   KParams p{};
-  p.dm = h->d_dm; p.vert = h->d_vert;
+  p.dm = h->d_dm; p.vert = h->d_vert; p.hf = h->d_hf; p.boxes = h->d_boxes;
+  p.hm_rows = h->cfg.hm_rows; p.hm_cols = h->cfg.hm_cols; p.hm_dx = float(h->cfg.hm_dx); p.hm_dy = float(h->cfg.hm_dy);
   p.num_envs = h->cfg.num_envs; p.obs_dim = h->obs_dim; p.use_imu = h->cfg.use_imu;
   p.max_iter = h->cfg.solver_max_iter > 0 ? h->cfg.solver_max_iter : (h->cfg.precision == 0 ? 12 : 100);
   p.tol = h->cfg.precision == 0 ? 1e-6f : 1e-8f;
@@ -624,8 +681,16 @@ int qs_get(QsHandle* h, int field, float* dst, void* stream) {
   return 0;
 }
 
-int qs_raycast_heightmap(QsHandle* h, int, int, double, double, float*, void*) {
-  return fail(h, 4, "qs_raycast_heightmap: not built in this version of libqstep");
+int qs_raycast_heightmap(QsHandle* h, int rows, int cols, double dx, double dy, float* out, void* stream) {
+  if (!h || !h->bound) return fail(h, 1, "qs_raycast_heightmap: handle not bound");
+  if (rows <= 0 || cols <= 0 || !out) return fail(h, 1, "qs_raycast_heightmap: bad arguments");
+  KParams p = base_params(h);
+  p.hm_rows = rows; p.hm_cols = cols; p.hm_dx = float(dx); p.hm_dy = float(dy); p.hm_out = out;
+  const int warps = 8, grid = (h->cfg.num_envs + warps - 1) / warps;
+  h->k_raycast<<<grid, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  h->launches++;
+  QS_CUDA(h, cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -23,6 +23,7 @@ from .backend import BatchSim, command_mode_bits
 from .model import QS_NOBS_BASE, Model
 from .robot_cfgs import RobotConfig, get_robot_config
 from .sensors.base_sensor import Sensor
+from .sensors.heightmap import HeightMap
 from .sensors.imu import IMU
 from .spaces import Box, Env
 from .utils.math_utils import _process_range
@@ -114,28 +115,39 @@ class QuadrupedEnv(Env):
 
         # sensors: IMU is fused into the kernel; other Sensor subclasses are stepped on the host after the kernel
         self.sensors: list[Sensor] = []
-        use_imu, imu_noise = False, (0.01, 0.01, 0.01, 0.01)
+        use_imu, imu_noise, hm_cfg = False, (0.01, 0.01, 0.01, 0.01), None
         sensors = sensors or ()
         sensors_kwargs = sensors_kwargs or tuple({} for _ in sensors)
+        deferred = []
         for cls, kw in zip(sensors, sensors_kwargs):
-            if cls is IMU or (isinstance(cls, type) and issubclass(cls, IMU)):
+            if isinstance(cls, type) and issubclass(cls, IMU):
                 s = cls(mj_model=self.model, mj_data=self, **kw)
                 use_imu, imu_noise = True, s.noise
+                self.sensors.append(s)
+            elif isinstance(cls, type) and issubclass(cls, HeightMap):
+                # fused into the step kernel: rows*cols*3 extra observation columns named 'heightmap'
+                hm_cfg = (int(kw['num_rows']), int(kw['num_cols']), float(kw['dist_x']), float(kw['dist_y']))
             else:
-                s = cls(mj_model=self.model, mj_data=self, **kw)
-            self.sensors.append(s)
+                deferred.append((cls, kw))
 
+        hm_dim = 0 if hm_cfg is None else hm_cfg[0] * hm_cfg[1] * 3
         for name in state_obs_names:
-            if name not in OBS_LAYOUT and not (use_imu and name in IMU_LAYOUT):
+            if name not in OBS_LAYOUT and not (use_imu and name in IMU_LAYOUT) and not (hm_cfg is not None and name == 'heightmap'):
                 raise ValueError(f'Invalid observation name: {name}, available obs: {self.ALL_OBS}')
-        self.observation_space = configure_observation_space(self.model.tables, state_obs_names)
+        self.observation_space = configure_observation_space(self.model.tables, [n for n in state_obs_names if n != 'heightmap'])
+        if 'heightmap' in state_obs_names:
+            self.observation_space.spaces['heightmap'] = Box(low=-np.inf, high=np.inf, shape=(hm_dim,), dtype=np.float32)
         self.state_obs_names = state_obs_names
 
         self.sim = BatchSim(self.model, self.num_envs, device=self.device, precision=0 if precision == 'fp32' else 1,
-                            use_imu=use_imu, imu_noise=imu_noise, seed=seed, env_id_offset=env_id_offset)
+                            use_imu=use_imu, imu_noise=imu_noise, seed=seed, env_id_offset=env_id_offset, heightmap=hm_cfg)
+        for cls, kw in deferred:  # host-side plug-ins following the Sensor protocol (base_sensor.py:4-41)
+            self.sensors.append(cls(mj_model=self.model, mj_data=self, **kw))
         self._layout = dict(OBS_LAYOUT)
         if use_imu:
             self._layout.update(IMU_LAYOUT)
+        if hm_cfg is not None:
+            self._layout['heightmap'] = (QS_NOBS_BASE + (18 if use_imu else 0), hm_dim)
         perm = [_MODEL_LEGS.index(leg) for leg in self.legs_order]
         self._leg_perm = None if perm == [0, 1, 2, 3] else torch.tensor(
             [3 * p + i for p in perm for i in range(3)], device=self.device, dtype=torch.long)

