@@ -371,7 +371,7 @@ def test_terrain_scenes_match_oracle(robot, scene, xy, tol, cuda_device):
     orc = []
     for i in range(n):
         qpos[i, 0:2] = np.array(xy) + rng.uniform(-0.6, 0.6, 2)
-        qpos[i, 2] = 0.42 if scene == 'random_boxes' else 0.95
+        qpos[i, 2] = 0.62 if scene == 'random_boxes' else 0.95
         qpos[i, 7:] += rng.uniform(-0.15, 0.15, 12)
         o = Oracle(m)
         o.set_state(qpos[i], np.zeros(18), np.zeros(18)); assert o.lift() >= 0
