@@ -1047,7 +1047,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     real zero[MAXDIM];
     for (int k = 0; k < MAXDIM; k++) zero[k] = 0;
     for (int c = lane; c < w.ncon; c += 32) contact_unit_eval(c, w.c_r[c], zero, cost, d1, d2);
-    return warp_sum(cost);
+    cost = warp_sum(cost);
+    syncwarp();  // residuals are overwritten by the next units_Jx
+    return cost;
   }
 
   // states / forces / weights at the current residuals (w.u_r, w.c_r); returns the constraint cost (warp-uniform)
@@ -1168,25 +1170,24 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // single evaluation site to keep the code footprint (and I-cache pressure) small.
   //   state 0: value at 0; 1: first Newton point; 2: one-sided Newton until the derivative changes sign; 3: bracketed
   //   refinement with Newton steps from both ends plus the midpoint.
-  QS_DEV real line_search(real gtol, real qg0, real qg1, real qg2) {
+  QS_DEV real line_search(real gtol, real qg0, real qg1, real qg2, real cost0, real slope0) {
     constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);
-    int state = 0, it = 0, dir = 1, ci = 3;
-    real a = 0;
+    int state = 1, it = 0, dir = 1, ci = 3;
     LsPoint p0{}, p1{}, p2{}, lo{}, hi{};
+    // The point alpha = 0 needs no evaluation: its cost is the current cost, its slope is grad . search and, because the search
+    // direction solves H s = -grad with the exact Hessian of the piecewise-quadratic cost, its curvature is s^T H s = -slope,
+    // so the first Newton point is alpha = 1.
+    p0.alpha = 0; p0.cost = cost0; p0.d1 = slope0; p0.d2 = -slope0;
+    if (!(p0.d2 > 0)) return 0;
+    // the slope cannot be resolved below a few ulps of its initial magnitude in this precision
+    gtol = N::max(gtol, kNoise * N::abs(slope0));
+    real a = 1;
     real cand[3] = {0, 0, 0};
     bool moved = true;
     const int ls_iter = m.ls_iterations;
     for (;;) {
       const LsPoint p = ls_eval(a, qg0, qg1, qg2);
       ls_evals++;
-      if (state == 0) {
-        p0 = p;
-        // the slope cannot be resolved below a few ulps of its initial magnitude in this precision
-        gtol = N::max(gtol, kNoise * N::abs(p.d1));
-        a = -N::div(p.d1, p.d2);
-        state = 1;
-        continue;
-      }
       if (state == 1) {
         p1 = (p0.cost < p.cost) ? p0 : p;
         if (N::abs(p1.d1) < gtol) return p1.alpha;
@@ -1282,7 +1283,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       units_Jx(w.search, w.u_v, w.c_v, false);
       const real qg1 = warp_sum((lane < NV) ? w.search[lane] * (w.Ma[lane] - w.fsm[lane]) : real(0));
       const real qg2 = warp_sum((lane < NV) ? real(0.5) * w.search[lane] * mv : real(0));
-      const real alpha = line_search(gtol, gauss, qg1, qg2);
+      const real slope0 = warp_sum((lane < NV) ? w.grad[lane] * w.search[lane] : real(0));
+      const real alpha = line_search(gtol, gauss, qg1, qg2, cost, slope0);
+      syncwarp();  // the last evaluation read the residuals that the move below updates
       if (alpha == 0) break;
       // move
       if (lane < NV) { w.qacc[lane] += alpha * w.search[lane]; w.Ma[lane] += alpha * w.Mv[lane]; }

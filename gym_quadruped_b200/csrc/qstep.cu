@@ -44,6 +44,9 @@ struct KParams {
   QsBuffers b;
   unsigned* episode;  // per-env reset counter (keys the reset RNG)
   unsigned* tick;     // per-env step counter  (keys the IMU noise RNG)
+  // straggler-aware placement (MODE_STEP): envs that were contact-rich / slow to solve in the previous step are listed first
+  const int* sched_in; const int* sched_in_cnt;  // [2N] heavy | light lists and their two counters (nullptr: identity placement)
+  int* sched_out; int* sched_out_cnt; int* sched_zero_cnt;
   const float* ctrl;
   float* obs;
   float* reward;
@@ -109,7 +112,15 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   // canonical warp index broadcast from lane 0: lets the compiler prove it warp-uniform, so the per-warp workspace base lives
   // in a uniform register instead of being re-derived from threadIdx before every shared-memory access
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int env = blockIdx.x * nwarp + warp;
+  if (MODE == MODE_STEP && p.sched_zero_cnt && blockIdx.x == 0 && threadIdx.x < 2) p.sched_zero_cnt[threadIdx.x] = 0;
+  int env = blockIdx.x * nwarp + warp;
+  if (MODE == MODE_STEP && p.sched_in) {
+    // Heavy envs first, dealt round-robin over the CTAs and onto the highest warp ids (the issue arbiter favours those): every SM
+    // gets the same share of likely stragglers and starts them early.  Results do not depend on the placement.
+    const int k = (nwarp - 1 - warp) * gridDim.x + blockIdx.x;
+    const int n_heavy = p.sched_in_cnt[0];
+    env = k < p.num_envs ? (k < n_heavy ? p.sched_in[k] : p.sched_in[p.num_envs + (k - n_heavy)]) : p.num_envs;
+  }
 
   if (threadIdx.x == 0) mbar_init(mbar, 1);
   __syncthreads();
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     }
     float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
     if (obs)
-      for (int i = lane; i < NOBS_BASE; i += 32) obs[i] = float(w.obs[i]);
+      for (int i = lane; i < NOBS_BASE; i += 32) __stwt(obs + i, float(w.obs[i]));  // write-through: rows bound for mapped host memory leave right away
     if (obs && p.hm_rows > 0) {
       // sensors/heightmap columns: grid around the post-step base position / heading (heightmap.py:106-169)
       real qq[4] = {w.qpos[3], w.qpos[4], w.qpos[5], w.qpos[6]}, Rn[9];
@@ -392,6 +403,11 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         if (p.terminated) p.terminated[env] = uint8_t(terminated);
         if (p.truncated) p.truncated[env] = 0;
       }
+    }
+    if (MODE == MODE_STEP && p.sched_out && pass == 0 && lane == 0) {
+      const bool heavy = w.ncon > 0 || e.solver_iter > 2;
+      const int idx = atomicAdd(p.sched_out_cnt + (heavy ? 0 : 1), 1);
+      p.sched_out[(heavy ? 0 : p.num_envs) + idx] = env;
     }
     // in-kernel auto-reset: the warp of an env that just terminated goes round once more as a reset pass
     if (MODE != MODE_STEP || !p.auto_reset || resetting || !terminated) break;
@@ -450,6 +466,10 @@ struct QsHandle_ {
   void* d_hf = nullptr;
   void* d_boxes = nullptr;
   KernelFn k_raycast = nullptr;
+  int* d_sched = nullptr;      // 3 rotating buffers of [2N] env ids
+  int* d_sched_cnt = nullptr;  // 3 x 2 counters
+  int sched_phase = -1;        // -1: no valid list yet
+  bool sched_enabled = true;
   unsigned* d_episode = nullptr;
   unsigned* d_tick = nullptr;
   float* d_aux = nullptr;
@@ -510,6 +530,14 @@ template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const
   return 0;
 }
 
+// device-visible alias of a pinned (page-locked, mapped) host pointer, or nullptr for pageable memory
+template <typename T> static T* mapped_alias(T* host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? static_cast<T*>(a.devicePointer) : nullptr;
+}
+
 extern "C" {
 
 int qs_abi_version(void) { return QS_ABI_VERSION; }
@@ -552,6 +580,7 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
 
 void qs_destroy(QsHandle* h) {
   if (!h) return;
+  cudaFree(h->d_sched); cudaFree(h->d_sched_cnt);
   cudaFree(h->d_dm); cudaFree(h->d_vert); cudaFree(h->d_hf); cudaFree(h->d_boxes); cudaFree(h->d_episode); cudaFree(h->d_tick); cudaFree(h->d_aux);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
   delete h;
@@ -597,6 +626,18 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
   KParams p = base_params(h);
   p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
   if (auto_reset) { p.auto_reset = 1; p.ro = *auto_reset; }
+  if (h->sched_enabled) {
+    const size_t n = size_t(h->cfg.num_envs);
+    if (!h->d_sched) {
+      QS_CUDA(h, cudaMalloc(&h->d_sched, 3 * 2 * n * sizeof(int)));
+      QS_CUDA(h, cudaMalloc(&h->d_sched_cnt, 3 * 2 * sizeof(int)));
+      QS_CUDA(h, cudaMemsetAsync(h->d_sched_cnt, 0, 3 * 2 * sizeof(int), static_cast<cudaStream_t>(stream)));
+    }
+    const int cur = h->sched_phase < 0 ? 0 : h->sched_phase, nxt = (cur + 1) % 3, clr = (cur + 2) % 3;
+    if (h->sched_phase >= 0) { p.sched_in = h->d_sched + size_t(cur) * 2 * n; p.sched_in_cnt = h->d_sched_cnt + 2 * cur; }
+    p.sched_out = h->d_sched + size_t(nxt) * 2 * n; p.sched_out_cnt = h->d_sched_cnt + 2 * nxt; p.sched_zero_cnt = h->d_sched_cnt + 2 * clr;
+    h->sched_phase = nxt;
+  }
   return launch(h, h->k_step, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -613,6 +654,7 @@ int qs_step_autoreset(QsHandle* h, const float* ctrl, const QsResetOptions* opt,
 int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_reset, float* obs, float* reward, uint8_t* terminated,
                  uint8_t* truncated, void* stream) {
   if (!h || !h->bound) return fail(h, 1, "qs_step_host: handle not bound");
+  if (!ctrl) return fail(h, 1, "qs_step_host: ctrl is null");
   const size_t n = size_t(h->cfg.num_envs);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!h->d_ctrl) {
@@ -623,12 +665,19 @@ int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_rese
     QS_CUDA(h, cudaMalloc(&h->d_trunc, n));
   }
   QS_CUDA(h, cudaMemcpyAsync(h->d_ctrl, ctrl, n * NU * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = step_impl(h, h->d_ctrl, h->d_obs, h->d_reward, h->d_term, h->d_trunc, auto_reset, stream);
+  // Pinned host buffers are written by the kernel itself through their mapped device alias (zero-copy): every warp streams its
+  // 908-B observation row over PCIe as soon as its env is done, so the transfer overlaps with the envs still being solved instead
+  // of following the kernel.  Pageable buffers fall back to staging + cudaMemcpyAsync.
+  float* k_obs = mapped_alias(obs); float* k_rew = mapped_alias(reward);
+  uint8_t* k_term = mapped_alias(terminated); uint8_t* k_trunc = mapped_alias(truncated);
+  int rc = step_impl(h, h->d_ctrl, obs ? (k_obs ? k_obs : h->d_obs) : nullptr, reward ? (k_rew ? k_rew : h->d_reward) : nullptr,
+                     terminated ? (k_term ? k_term : h->d_term) : h->d_term, truncated ? (k_trunc ? k_trunc : h->d_trunc) : nullptr,
+                     auto_reset, stream);
   if (rc) return rc;
-  if (obs) QS_CUDA(h, cudaMemcpyAsync(obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (reward) QS_CUDA(h, cudaMemcpyAsync(reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (terminated) QS_CUDA(h, cudaMemcpyAsync(terminated, h->d_term, n, cudaMemcpyDeviceToHost, s));
-  if (truncated) QS_CUDA(h, cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
+  if (obs && !k_obs) QS_CUDA(h, cudaMemcpyAsync(obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward && !k_rew) QS_CUDA(h, cudaMemcpyAsync(reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (terminated && !k_term) QS_CUDA(h, cudaMemcpyAsync(terminated, h->d_term, n, cudaMemcpyDeviceToHost, s));
+  if (truncated && !k_trunc) QS_CUDA(h, cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
   QS_CUDA(h, cudaStreamSynchronize(s));
   return 0;
 }
