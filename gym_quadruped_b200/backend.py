@@ -14,8 +14,11 @@ import torch
 
 from .model import (QS_CONTACT_STRIDE, QS_NOBS_BASE, QS_NOBS_IMU, Model, QsBuffers, QsConfig, QsModel, QsResetOptions)
 
+import os
+
 CSRC = Path(__file__).resolve().parent / 'csrc'
-LIB_PATH = CSRC / 'libqstep.so'
+# QSTEP_LIB selects an alternative build of the same library (diagnostic builds such as -DQS_PROF); never a CPU path
+LIB_PATH = Path(os.environ['QSTEP_LIB']).resolve() if os.environ.get('QSTEP_LIB') else CSRC / 'libqstep.so'
 
 FIELD_MASS_MATRIX, FIELD_QFRC_BIAS, FIELD_QFRC_PASSIVE, FIELD_FEET_JACP, FIELD_FEET_POS, FIELD_COM, FIELD_CONTACTS, \
     FIELD_QFRC_SMOOTH, FIELD_QFRC_CONSTRAINT, FIELD_XPOS, FIELD_SENSOR_IMU = range(11)

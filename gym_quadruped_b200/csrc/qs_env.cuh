@@ -106,9 +106,25 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   int solver_iter, ls_evals;
   bool solver_maxed;
   float* bias_out;  // optional destination for qfrc_bias (accessor dump), else nullptr
+#ifdef QS_PROF
+  unsigned tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // diagnostic builds: cycles per solver sub-phase
+  long long tlast = 0;
+#define QS_T0() tlast = clock64()
+#define QS_TACC(k) do { const long long t_ = clock64(); tacc[k] += unsigned(t_ - tlast); tlast = t_; } while (0)
+#else
+#define QS_T0() do { } while (0)
+#define QS_TACC(k) do { } while (0)
+#endif
+
+  int tri;  // (i0, j0, i1, j1), 4 bits each: rows / columns of entries e = lane and e = lane + 32 of a row-major lower triangle
 
   QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_)
-      : m(m_), w(w_), vert(v_), hf(nullptr), boxes(nullptr), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {}
+      : m(m_), w(w_), vert(v_), hf(nullptr), boxes(nullptr), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {
+    int i0 = 0, j0 = lane_, i1 = 0, j1 = lane_ + 32;
+    while (j0 > i0) { j0 -= i0 + 1; i0++; }
+    while (j1 > i1) { j1 -= i1 + 1; i1++; }
+    tri = i0 | (j0 << 4) | (i1 << 8) | (j1 << 12);
+  }
 
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
@@ -352,7 +368,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   // Factor the block matrix in w.hes (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
   // Schur complement S = A - sum B_l^T Y_l -> Cholesky SL (lower) with reciprocal diagonal.
-  QS_NOINLINE static void factor_H(W& w, const int lane) {
+  QS_NOINLINE static void factor_H(W& w, const int lane, const int tri) {
     auto& h = w.hes;
     if (lane < 24) {
       const int l = lane / 6, c = lane % 6;
@@ -376,8 +392,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
     // Schur complement entries (lower triangle) spread over 21 lanes, parked in SL
     if (lane < 21) {
-      int i = 0, j = lane;
-      while (j > i) { j -= i + 1; i++; }
+      const int i = tri & 15, j = (tri >> 4) & 15;
       real s = h.Hbb[i][j];
       for (int l = 0; l < 4; l++)
         for (int k = 0; k < 3; k++) s -= h.Hlb[l][k][i] * h.Y[l][k][j];
@@ -458,11 +473,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
   }
 
+  // H = M + h_damp * diag(damping).  The hes blocks (Hbb, Hlb, Hll) and the mass blocks (Mbb, Mlb, Mll) are laid out identically
+  // (144 contiguous words each), so this is a flat copy followed by 18 diagonal updates.
   QS_DEV void copy_M_to_H(real h_damp) {
-    for (int e = lane; e < 144; e += 32) {
-      if (e < 36) { const int i = e / 6, j = e % 6; w.hes.Hbb[i][j] = w.Mbb[i][j] + ((i == j) ? h_damp * m.dof_damping[i] : real(0)); }
-      else if (e < 108) { const int q = e - 36; (&w.hes.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
-      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.hes.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? h_damp * m.dof_damping[6 + 3 * l + k] : real(0)); }
+    real* H = &w.hes.Hbb[0][0];
+    const real* M = &w.Mbb[0][0];
+#pragma unroll
+    for (int r = 0; r < 5; r++) { const int e = lane + 32 * r; if (r < 4 || lane < 16) H[e] = M[e]; }
+    if (h_damp != 0) {
+      syncwarp();
+      if (lane < 6) w.hes.Hbb[lane][lane] += h_damp * m.dof_damping[lane];
+      else if (lane < NV) { const int l = (lane - 6) / 3, k = (lane - 6) % 3; w.hes.Hll[l][k][k] += h_damp * m.dof_damping[lane]; }
     }
     syncwarp();
   }
@@ -1107,40 +1128,64 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // lane e owns entry (i,j), i>=j, of the contact-local symmetric 9x9 matrix Jc^T W Jc (45 entries -> two passes), so the
   // same lane always touches the same shared-memory word and no synchronisation is needed between contacts.
   QS_DEV void build_hessian() {
-    for (int e = lane; e < 144; e += 32) {
-      if (e < 36) { const int i = e / 6, j = e % 6; w.hes.Hbb[i][j] = w.Mbb[i][j]; }
-      else if (e < 108) { const int q = e - 36; (&w.hes.Hlb[0][0][0])[q] = (&w.Mlb[0][0][0])[q]; }
-      else { const int q = e - 108, l = q / 9, k = (q % 9) / 3, k2 = q % 3; w.hes.Hll[l][k][k2] = w.Mll[l][k][k2] + ((k == k2) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0)); }
-    }
-    syncwarp();
+    const int i0 = tri & 15, j0 = (tri >> 4) & 15, i1 = (tri >> 8) & 15, j1 = (tri >> 12) & 15;
+    const bool own1 = lane < 13;  // e1 = lane + 32 < 45
+    real ab = 0, a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};  // base-block entry; per-leg entries of e0 (>= 21) and e1
     const int ncon = w.ncon;
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
-      const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
       const real* Wt = w.c_W[c];
       if (Wt[0] == 0) continue;  // no active row in this contact (W00 sums the active regularisers)
-      const int nloc = body < 2 ? 21 : 45;
-      const int leg = body < 2 ? 0 : (body - 2) / 3;
-#pragma unroll 1
-      for (int e = lane; e < nloc; e += 32) {
-        int i = 0, j = e;
-        while (j > i) { j -= i + 1; i++; }  // e -> (i, j), i >= j
-        real h = 0;
-        if (MAXDIM == 3 && m.cone == 0 && dim == 3) {
-          const real a0 = w.Jc[c][0][i], a1 = w.Jc[c][1][i], a2 = w.Jc[c][2][i], b0 = w.Jc[c][0][j], b1 = w.Jc[c][1][j], b2 = w.Jc[c][2][j];
-          h = Wt[widx(0, 0)] * a0 * b0 + Wt[widx(0, 1)] * (a0 * b1 + a1 * b0) + Wt[widx(0, 2)] * (a0 * b2 + a2 * b0) + Wt[widx(1, 1)] * a1 * b1 +
-              Wt[widx(2, 2)] * a2 * b2;
-        } else {
-          for (int a = 0; a < MAXDIM; a++) {
-            if (a >= dim) break;
-            real t = 0;
-            for (int b = 0; b < MAXDIM; b++) { if (b >= dim) break; t += Wt[widx(a, b)] * w.Jc[c][b][j]; }
-            h += w.Jc[c][a][i] * t;
-          }
+      const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
+      const bool legc = body >= 2;
+      const int leg = legc ? (body - 2) / 3 : 0;
+      real h0 = 0, h1 = 0;
+      const bool on0 = lane < 21 || legc, on1 = own1 && legc;
+      if (MAXDIM == 3 && m.cone == 0 && dim == 3) {
+        const real w00 = Wt[widx(0, 0)], w01 = Wt[widx(0, 1)], w02 = Wt[widx(0, 2)], w11 = Wt[widx(1, 1)], w22 = Wt[widx(2, 2)];
+        if (on0) {
+          const real p0 = w.Jc[c][0][i0], p1 = w.Jc[c][1][i0], p2 = w.Jc[c][2][i0], q0 = w.Jc[c][0][j0], q1 = w.Jc[c][1][j0], q2 = w.Jc[c][2][j0];
+          h0 = w00 * p0 * q0 + w01 * (p0 * q1 + p1 * q0) + w02 * (p0 * q2 + p2 * q0) + w11 * p1 * q1 + w22 * p2 * q2;
         }
-        if (i < 6) w.hes.Hbb[i][j] += h;
-        else if (j < 6) w.hes.Hlb[leg][i - 6][j] += h;
-        else w.hes.Hll[leg][i - 6][j - 6] += h;
+        if (on1) {
+          const real p0 = w.Jc[c][0][i1], p1 = w.Jc[c][1][i1], p2 = w.Jc[c][2][i1], q0 = w.Jc[c][0][j1], q1 = w.Jc[c][1][j1], q2 = w.Jc[c][2][j1];
+          h1 = w00 * p0 * q0 + w01 * (p0 * q1 + p1 * q0) + w02 * (p0 * q2 + p2 * q0) + w11 * p1 * q1 + w22 * p2 * q2;
+        }
+      } else {
+        for (int a = 0; a < MAXDIM; a++) {
+          if (a >= dim) break;
+          real t0 = 0, t1 = 0;
+          for (int b = 0; b < MAXDIM; b++) {
+            if (b >= dim) break;
+            const real wab = Wt[widx(a, b)];
+            if (on0) t0 += wab * w.Jc[c][b][j0];
+            if (on1) t1 += wab * w.Jc[c][b][j1];
+          }
+          if (on0) h0 += w.Jc[c][a][i0] * t0;
+          if (on1) h1 += w.Jc[c][a][i1] * t1;
+        }
+      }
+      if (lane < 21) ab += h0;
+      else {
+#pragma unroll
+        for (int l = 0; l < 4; l++) a0[l] += (l == leg) ? h0 : real(0);
+      }
+#pragma unroll
+      for (int l = 0; l < 4; l++) a1[l] += (l == leg) ? h1 : real(0);
+    }
+    // H = M + accumulated J^T W J (+ the scalar units' weights on the leg diagonals), written once by the owning lanes
+    if (lane < 21) w.hes.Hbb[i0][j0] = w.Mbb[i0][j0] + ab;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (lane >= 21) {
+        const int k = i0 - 6;
+        if (j0 < 6) w.hes.Hlb[l][k][j0] = w.Mlb[l][k][j0] + a0[l];
+        else w.hes.Hll[l][k][j0 - 6] = w.Mll[l][k][j0 - 6] + a0[l] + ((j0 - 6 == k) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0));
+      }
+      if (own1) {
+        const int k = i1 - 6;
+        if (j1 < 6) w.hes.Hlb[l][k][j1] = w.Mlb[l][k][j1] + a1[l];
+        else w.hes.Hll[l][k][j1 - 6] = w.Mll[l][k][j1 - 6] + a1[l] + ((j1 - 6 == k) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0));
       }
     }
     syncwarp();
@@ -1224,9 +1269,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   // [MJ] mj_fwdConstraint + mj_solNewton
   QS_DEV void solve(int max_iter, real tol) {
+    QS_T0();
     // qacc_smooth = M^-1 qfrc_smooth
     copy_M_to_H(real(0));
-    factor_H(w, lane);
+    factor_H(w, lane, tri);
     solve_H(w, lane, w.fsm, w.asmooth, real(1));
     // warm start: cheaper of qacc_warmstart and qacc_smooth
     units_Jx(w.warm, w.u_r, w.c_r, true);
@@ -1250,6 +1296,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     int iter = 0;
     real cost = 0, oldcost = 0;
     solver_maxed = false;
+    QS_TACC(0);
     while (true) {
       // cost, forces, gradient at the current point
       const real ccost = units_update();
@@ -1266,14 +1313,31 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         const real gn2 = warp_sum((lane < NV) ? w.grad[lane] * w.grad[lane] : real(0));
         const real fn2 = warp_sum((lane < NV) ? w.Ma[lane] * w.Ma[lane] + w.fsm[lane] * w.fsm[lane] + w.fcon[lane] * w.fcon[lane] : real(0));
         const real imp = oldcost - cost;
+#ifdef QS_PROF_IMP
+        if (iter <= 8) tacc[iter - 1] = __float_as_uint(float(scale * imp));
+#endif
         if (scale * imp < tol || imp < kNoiseCost * (N::abs(cost) + N::abs(oldcost))) break;
         if (scale * scale * gn2 < tol * tol || gn2 < kNoise * kNoise * fn2) break;
       }
       if (iter >= max_iter) { solver_maxed = true; break; }
+      QS_TACC(1);
       // Newton direction
+#ifdef QS_PROF_REPEAT
+#pragma unroll 1
+      for (int rep = 0; rep < 2; rep++) {
+        build_hessian();
+        factor_H(w, lane, tri);
+        solve_H(w, lane, w.grad, w.search, real(-1));
+        if (rep == 0) QS_TACC(2); else QS_TACC(3);
+      }
+#else
       build_hessian();
-      factor_H(w, lane);
+      QS_TACC(2);
+      factor_H(w, lane, tri);
+      QS_TACC(3);
       solve_H(w, lane, w.grad, w.search, real(-1));
+      QS_TACC(4);
+#endif
       // exact line search
       const real snorm = N::sqrt(warp_sum((lane < NV) ? w.search[lane] * w.search[lane] : real(0)));
       if (snorm < N::minval) break;
@@ -1284,7 +1348,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const real qg1 = warp_sum((lane < NV) ? w.search[lane] * (w.Ma[lane] - w.fsm[lane]) : real(0));
       const real qg2 = warp_sum((lane < NV) ? real(0.5) * w.search[lane] * mv : real(0));
       const real slope0 = warp_sum((lane < NV) ? w.grad[lane] * w.search[lane] : real(0));
+      QS_TACC(5);
       const real alpha = line_search(gtol, gauss, qg1, qg2, cost, slope0);
+      QS_TACC(6);
       syncwarp();  // the last evaluation read the residuals that the move below updates
       if (alpha == 0) break;
       // move
@@ -1293,7 +1359,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int it2 = lane; it2 < w.ncon * MAXDIM; it2 += 32) (&w.c_r[0][0])[it2] += alpha * (&w.c_v[0][0])[it2];
       syncwarp();
       iter++;
+      QS_TACC(7);
     }
+    QS_TACC(1);
     solver_iter = iter;
   }
 
@@ -1343,7 +1411,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV void integrate(double* base64) {
     const real h = m.timestep;
     copy_M_to_H(h);
-    factor_H(w, lane);
+    factor_H(w, lane, tri);
     if (lane < NV) w.grad[lane] = w.fsm[lane] + w.fcon[lane];
     syncwarp();
     solve_H(w, lane, w.grad, w.search, real(1));

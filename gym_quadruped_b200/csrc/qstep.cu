@@ -59,7 +59,16 @@ struct KParams {
   QsResetOptions ro;
   // forward
   float* aux;
+#ifdef QS_PROF
+  unsigned* prof;  // diagnostic builds only: [N][16] per-env cycle marks
+  unsigned* prof2; // [N][8] solver sub-phase cycles
+#endif
 };
+#ifdef QS_PROF
+#define QS_MARK(k) do { if (p.prof && lane == 0 && pass == 0) p.prof[size_t(env) * 16 + (k)] = unsigned(clock64() - t_entry); } while (0)
+#else
+#define QS_MARK(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -122,6 +131,9 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     env = k < p.num_envs ? (k < n_heavy ? p.sched_in[k] : p.sched_in[p.num_envs + (k - n_heavy)]) : p.num_envs;
   }
 
+#ifdef QS_PROF
+  const long long t_entry = clock64();
+#endif
   if (threadIdx.x == 0) mbar_init(mbar, 1);
   __syncthreads();
   if (threadIdx.x == 0) tma_bulk_load(dm, p.dm, static_cast<uint32_t>(sizeof(DM)), mbar);
@@ -167,6 +179,32 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   real command[4] = {real(B.command[4 * env]), real(B.command[4 * env + 1]), real(B.command[4 * env + 2]), real(B.command[4 * env + 3])};
   float sim_time = B.sim_time[env];
   int step_count = B.step_count[env];
+
+  // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals.
+  // obs_row == nullptr advances the bias walk / counter only.
+  auto imu_step = [&](float* obs_row) {
+    unsigned tk = p.tick[env];
+    if (lane < 3) {
+      uint32_t r[4];
+      philox4x32(env_g, tk, unsigned(lane), 0x1A2Bu, p.seed_lo ^ 0x9E3779B9u, p.seed_hi, r);
+      const float u1 = fmaxf(u32_to_unit(r[0]), 5.9604645e-8f), u2 = u32_to_unit(r[1]), u3 = fmaxf(u32_to_unit(r[2]), 5.9604645e-8f), u4 = u32_to_unit(r[3]);
+      const float ra = sqrtf(-2.f * logf(u1)), rb = sqrtf(-2.f * logf(u3));
+      float s1, c1, s2, c2;
+      sincosf(6.28318530717958647692f * u2, &s1, &c1);
+      sincosf(6.28318530717958647692f * u4, &s2, &c2);
+      const float n_acc = ra * c1 * p.imu_an, n_ab = ra * s1 * p.imu_abr, n_gyr = rb * c2 * p.imu_gn, n_gb = rb * s2 * p.imu_gbr;
+      float* bias = B.imu_bias + size_t(env) * 6;
+      const float ab = bias[lane] + n_ab, gb = bias[3 + lane] + n_gb;
+      bias[lane] = ab; bias[3 + lane] = gb;
+      if (obs_row) {
+        float* io = obs_row + NOBS_BASE;
+        io[lane] = float(w.sens[lane]) + ab + n_acc; io[3 + lane] = n_acc; io[6 + lane] = ab;
+        io[9 + lane] = float(w.sens[3 + lane]) + gb + n_gyr; io[12 + lane] = n_gyr; io[15 + lane] = gb;
+      }
+    }
+    syncwarp();
+    if (lane == 0) p.tick[env] = tk + 1;
+  };
 
   // One pass = one "mj_step" with its env-side bookkeeping.  A reset is the same pass preceded by state sampling and the
   // lift loop; MODE_STEP with auto_reset runs a second (reset) pass for envs that just terminated, in the same warp.
@@ -221,8 +259,37 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         syncwarp();
         // lift until no foot (calf-body) contact, quadruped_env.py:376-388
         bool cleared = false;
+        int c_first = 0;
+        if (flat) {
+          // Flat floor: raising the base shifts every floor distance by exactly the lift, so after one collision pass the loop
+          // reduces to a scalar recurrence on the calf-body contact distances (same iterates as re-running the collision stage).
+          e.kinematics();
+          e.collide_floor();
+          real d = Num<real>::big, mg = 0;
+          bool calf = false, boxy = false;
+          if (lane < w.ncon) {
+            const int info = w.c_info[lane], bdy = (info >> 8) & 0xff, g = info & 0xff;
+            calf = bdy >= 2 && (bdy - 2) % 3 == 2;
+            d = w.c_dist[lane]; mg = m.geom_margin[g];
+            boxy = calf && m.geom_type[g] == GEOM_BOX;  // a box keeps at most 4 of its corners: not closed under lifting
+          }
+          if (!w.overflow && qs::ballot(boxy) == 0) {
+            real lift = 0;
 #pragma unroll 1
-        for (int c = 0; c <= 100; c++) {
+            for (int c = 0; c <= 100; c++) {
+              const bool in = calf && !(d + lift > mg);
+              const real pen = warp_max(in ? Num<real>::abs(d + lift) : real(0));
+              if (qs::ballot(in) == 0) { cleared = true; break; }
+              if (c == 100) break;
+              lift += pen * real(1.1);
+            }
+            if (lane == 0) w.qpos[2] += lift;
+            syncwarp();
+            c_first = 101;
+          }
+        }
+#pragma unroll 1
+        for (int c = c_first; c <= 100; c++) {
           e.kinematics();
           e.collide_floor();
           real pen = 0;
@@ -249,14 +316,52 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     }
 
     // ---- forward dynamics
+    QS_MARK(1);
     e.forward_position();
+    QS_MARK(2);
+    if (MODE == MODE_STEP && p.auto_reset && !resetting) {
+      // Same-step auto-reset returns the post-reset state / observation of an env that terminates, so once the collision stage has
+      // found a contact that terminates the episode (quadruped_env.py:1228-1248) the rest of this step cannot reach any output:
+      // raise the flags, keep the IMU bias walk in step, and go straight to the reset pass.
+      if (e.flags().invalid_mask != 0) {
+        if (lane == 0) {
+          if (p.reward) p.reward[env] = 0.f;
+          if (p.terminated) p.terminated[env] = 1;
+          if (p.truncated) p.truncated[env] = 0;
+          if (p.sched_out) { const int idx = atomicAdd(p.sched_out_cnt + 1, 1); p.sched_out[p.num_envs + idx] = env; }
+        }
+        if (p.use_imu) imu_step(nullptr);
+        QS_MARK(5);
+        resetting = true;
+        given_state = false;
+        syncwarp();
+        continue;
+      }
+    }
     if (MODE == MODE_FORWARD && p.aux) {
       float* a = p.aux + size_t(env) * AUX_STRIDE;  // body poses are only valid until the solver recycles their storage
       for (int it = lane; it < 39; it += 32) a[AUX_OFF_XPOS + it] = float(w.kin.xpos[1 + it / 3][it % 3] + (it % 3 < 2 ? real(w.org[it % 3]) : real(0)));
       syncwarp();
       e.bias_out = a + AUX_OFF_BIAS;
     }
+#ifdef QS_PROF
+    e.bias_and_smooth(); e.mass_matrix(); e.make_constraints();
+    QS_MARK(3);
+    e.solve(p.max_iter, real(p.tol));
+    if (m.has_imu) e.sensors();
+    QS_MARK(4);
+    if (p.prof && lane == 0 && pass == 0) {
+      unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.prof[size_t(env) * 16 + 8] = unsigned(e.solver_iter); p.prof[size_t(env) * 16 + 9] = unsigned(e.ls_evals);
+      p.prof[size_t(env) * 16 + 10] = unsigned(w.ncon); p.prof[size_t(env) * 16 + 11] = smid; p.prof[size_t(env) * 16 + 12] = unsigned(warp);
+      p.prof[size_t(env) * 16 + 0] = unsigned(t_entry & 0xffffffffll);
+      p.prof[size_t(env) * 16 + 7] = e.tacc[0]; p.prof[size_t(env) * 16 + 13] = e.tacc[1]; p.prof[size_t(env) * 16 + 14] = e.tacc[2];
+      p.prof[size_t(env) * 16 + 15] = e.tacc[3];
+      if (p.prof2) for (int i = 0; i < 8; i++) p.prof2[size_t(env) * 8 + i] = e.tacc[i];
+    }
+#else
     e.forward_dynamics(p.max_iter, real(p.tol));
+#endif
     typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
 
     if (MODE == MODE_FORWARD) {
@@ -367,30 +472,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       e.heightmap(ctr, Num<real>::atan2(Rn[3], Rn[0]), p.hm_rows, p.hm_cols, real(p.hm_dx), real(p.hm_dy), real(w.org[0]), real(w.org[1]),
                   obs + NOBS_BASE + (p.use_imu ? QS_NOBS_IMU : 0));
     }
-    if (p.use_imu) {
-      // IMU.step (sensors/imu.py:110-139): measurement = truth + bias + noise, bias random walk; counter-based normals
-      unsigned tk = p.tick[env];
-      if (lane < 3) {
-        uint32_t r[4];
-        philox4x32(env_g, tk, unsigned(lane), 0x1A2Bu, p.seed_lo ^ 0x9E3779B9u, p.seed_hi, r);
-        const float u1 = fmaxf(u32_to_unit(r[0]), 5.9604645e-8f), u2 = u32_to_unit(r[1]), u3 = fmaxf(u32_to_unit(r[2]), 5.9604645e-8f), u4 = u32_to_unit(r[3]);
-        const float ra = sqrtf(-2.f * logf(u1)), rb = sqrtf(-2.f * logf(u3));
-        float s1, c1, s2, c2;
-        sincosf(6.28318530717958647692f * u2, &s1, &c1);
-        sincosf(6.28318530717958647692f * u4, &s2, &c2);
-        const float n_acc = ra * c1 * p.imu_an, n_ab = ra * s1 * p.imu_abr, n_gyr = rb * c2 * p.imu_gn, n_gb = rb * s2 * p.imu_gbr;
-        float* bias = B.imu_bias + size_t(env) * 6;
-        const float ab = bias[lane] + n_ab, gb = bias[3 + lane] + n_gb;
-        bias[lane] = ab; bias[3 + lane] = gb;
-        if (obs) {
-          float* io = obs + NOBS_BASE;
-          io[lane] = float(w.sens[lane]) + ab + n_acc; io[3 + lane] = n_acc; io[6 + lane] = ab;
-          io[9 + lane] = float(w.sens[3 + lane]) + gb + n_gyr; io[12 + lane] = n_gyr; io[15 + lane] = gb;
-        }
-      }
-      syncwarp();
-      if (lane == 0) p.tick[env] = tk + 1;
-    }
+    if (p.use_imu) imu_step(obs);
     if (lane == 0) {
       B.sim_time[env] = sim_time;
       B.step_count[env] = step_count;
@@ -404,6 +486,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         if (p.truncated) p.truncated[env] = 0;
       }
     }
+    QS_MARK(5);
     if (MODE == MODE_STEP && p.sched_out && pass == 0 && lane == 0) {
       const bool heavy = w.ncon > 0 || e.solver_iter > 2;
       const int idx = atomicAdd(p.sched_out_cnt + (heavy ? 0 : 1), 1);
@@ -416,6 +499,9 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     e.ls_evals = 0;
     syncwarp();
   }
+#ifdef QS_PROF
+  if (p.prof && lane == 0) p.prof[size_t(env) * 16 + 6] = unsigned(clock64() - t_entry);
+#endif
 }
 
 // HeightMap.update_height_map for every env (sensors/heightmap.py:106-169): one warp per env, rays spread over the lanes
@@ -478,6 +564,7 @@ struct QsHandle_ {
   QsBuffers buf{};
   bool bound = false;
   KernelFn k_step = nullptr, k_reset = nullptr, k_forward = nullptr;
+  unsigned* prof = nullptr; unsigned* prof2 = nullptr;  // QS_PROF builds only
   int warps_per_cta = 8;
   size_t smem_bytes = 0;
   double timestep = 0.002;
@@ -547,6 +634,9 @@ int qs_buffers_sizeof(void) { return int(sizeof(QsBuffers)); }
 int qs_obs_dim(const QsConfig* cfg) { return QS_NOBS_BASE + (cfg->use_imu ? QS_NOBS_IMU : 0) + cfg->hm_rows * cfg->hm_cols * 3; }
 const char* qs_last_error(QsHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int qs_max_contacts(QsHandle*) { return NCON_MAX; }
+#ifdef QS_PROF
+int qs_debug_set_prof(QsHandle* h, unsigned* prof) { h->prof = prof; h->prof2 = prof ? prof + size_t(h->cfg.num_envs) * 16 : nullptr; return 0; }  // diagnostic builds only (scripts/warp_timeline.py)
+#endif
 int64_t qs_launch_count(QsHandle* h) { return h ? h->launches : 0; }
 
 int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
@@ -626,6 +716,9 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
   KParams p = base_params(h);
   p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
   if (auto_reset) { p.auto_reset = 1; p.ro = *auto_reset; }
+#ifdef QS_PROF
+  p.prof = h->prof; p.prof2 = h->prof2;
+#endif
   if (h->sched_enabled) {
     const size_t n = size_t(h->cfg.num_envs);
     if (!h->d_sched) {
