@@ -123,8 +123,14 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     int i0 = 0, j0 = lane_, i1 = 0, j1 = lane_ + 32;
     while (j0 > i0) { j0 -= i0 + 1; i0++; }
     while (j1 > i1) { j1 -= i1 + 1; i1++; }
-    tri = i0 | (j0 << 4) | (i1 << 8) | (j1 << 12);
+    const int dl = (lane_ >= 6 && lane_ < NV) ? (lane_ - 6) / 3 : 0, dk = (lane_ >= 6 && lane_ < NV) ? (lane_ - 6) % 3 : 0;
+    tri = i0 | (j0 << 4) | (i1 << 8) | (j1 << 12) | (dl << 16) | (dk << 18) | ((lane_ / 6) << 20) | ((lane_ % 6) << 23);
   }
+  // leg / joint-in-leg of dof lane 6..17 (0 elsewhere); lane / 6 and lane % 6
+  QS_DEV int dof_leg() const { return (tri >> 16) & 3; }
+  QS_DEV int dof_k() const { return (tri >> 18) & 3; }
+  QS_DEV static int tri_dof_leg(int t) { return (t >> 16) & 3; }
+  QS_DEV static int tri_dof_k(int t) { return (t >> 18) & 3; }
 
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
@@ -354,16 +360,18 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // ------------------------------------------------------------------ structured linear algebra
   // y = A x for a block matrix (bb, lb, ll); valid on dof lanes (< NV), x read from shared memory
   QS_DEV real block_matvec(const real (*Abb)[6], const real (*Alb)[3][6], const real (*All)[3][3], const real* x) const {
-    real s = 0;
-    if (lane < 6) {
-      for (int j = 0; j < 6; j++) s += Abb[lane][j] * x[j];
-      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) s += Alb[l][k][lane] * x[6 + 3 * l + k];
-    } else if (lane < NV) {
-      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
-      for (int j = 0; j < 6; j++) s += Alb[l][k][j] * x[j];
-      for (int k2 = 0; k2 < 3; k2++) s += All[l][k][k2] * x[6 + 3 * l + k2];
-    }
-    return s;
+    // both row shapes are evaluated on clamped indices and the lane keeps its own: a divergent warp would run both anyway
+    const bool isbase = lane < 6;
+    const int l = dof_leg(), k = dof_k(), bl = isbase ? lane : 0;
+    const real* row = isbase ? Abb[bl] : Alb[l][k];
+    real s = 0, sb = 0, sl = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) s += row[j] * x[j];
+#pragma unroll
+    for (int q = 0; q < 12; q++) sb += (&Alb[0][0][0])[6 * q + bl] * x[6 + q];
+#pragma unroll
+    for (int k2 = 0; k2 < 3; k2++) sl += All[l][k][k2] * x[6 + 3 * l + k2];
+    return s + (isbase ? sb : sl);
   }
 
   // Factor the block matrix in w.hes (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
@@ -371,7 +379,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_NOINLINE static void factor_H(W& w, const int lane, const int tri) {
     auto& h = w.hes;
     if (lane < 24) {
-      const int l = lane / 6, c = lane % 6;
+      const int l = (tri >> 20) & 7, c = (tri >> 23) & 7;
       // LDL^T of the 3x3 leg block, done redundantly by the 6 column lanes of a leg
       const real c00 = h.Hll[l][0][0], c10 = h.Hll[l][1][0], c20 = h.Hll[l][2][0], c11 = h.Hll[l][1][1], c21 = h.Hll[l][2][1], c22 = h.Hll[l][2][2];
       const real id0 = N::rcp(c00), l10 = c10 * id0, l20 = c20 * id0;
@@ -435,16 +443,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   }
 
   // solve (factored H) x = rhs for shared-memory vectors rhs, out (may alias); out = scale * x; all lanes participate
-  QS_NOINLINE static void solve_H(W& w, const int lane, const real* rhs, real* out, const real scale) {
+  QS_NOINLINE static void solve_H(W& w, const int lane, const int tri, const real* rhs, real* out, const real scale) {
     auto& h = w.hes;
-    real t = 0, rl = 0;
-    if (lane < 6) {
-      t = rhs[lane];
-      for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) t -= h.Y[l][k][lane] * rhs[6 + 3 * l + k];
-    } else if (lane < NV) {
-      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
-      for (int k2 = 0; k2 < 3; k2++) rl += h.Ci[l][k][k2] * rhs[6 + 3 * l + k2];
-    }
+    const int l = tri_dof_leg(tri), k = tri_dof_k(tri);
+    const bool isbase = lane < 6, isleg = lane >= 6 && lane < NV;
+    // base lanes: t = rhs_b - sum_l Y_l^T rhs_l ; leg lanes: rl = (C_l^-1 rhs_l)_k   (both forms evaluated branch-free on clamped indices)
+    const int bl = isbase ? lane : 0;
+    real t = rhs[bl], rl = 0;
+#pragma unroll
+    for (int q = 0; q < 12; q++) t -= (&h.Y[0][0][0])[6 * q + bl] * rhs[6 + q];
+#pragma unroll
+    for (int k2 = 0; k2 < 3; k2++) rl += h.Ci[l][k][k2] * rhs[6 + 3 * l + k2];
     real tb[6], xb[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) tb[i] = shfl(t, i);
@@ -452,24 +461,22 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     for (int i = 0; i < 6; i++) {
       real s = tb[i];
 #pragma unroll
-      for (int k = 0; k < i; k++) s -= h.SL[i][k] * xb[k];
+      for (int q = 0; q < i; q++) s -= h.SL[i][q] * xb[q];
       xb[i] = s * h.SLinv[i];
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
       real s = xb[i];
 #pragma unroll
-      for (int k = i + 1; k < 6; k++) s -= h.SL[k][i] * xb[k];
+      for (int q = i + 1; q < 6; q++) s -= h.SL[q][i] * xb[q];
       xb[i] = s * h.SLinv[i];
     }
+    // leg lanes: x_l = C^-1 rhs_l - Y_l x_b ; base lanes pick their own component without indexing the register array
+    real sl = rl, sb = xb[0];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { sl -= h.Y[l][k][j] * xb[j]; if (j > 0) sb = (lane == j) ? xb[j] : sb; }
     syncwarp();  // rhs fully consumed before out (possibly the same array) is written
-    if (lane < 6) out[lane] = scale * xb[lane];
-    else if (lane < NV) {
-      const int l = (lane - 6) / 3, k = (lane - 6) % 3;
-      real s = rl;
-      for (int j = 0; j < 6; j++) s -= h.Y[l][k][j] * xb[j];
-      out[lane] = scale * s;
-    }
+    if (lane < NV) out[lane] = scale * (isbase ? sb : sl);
     syncwarp();
   }
 
@@ -483,7 +490,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (h_damp != 0) {
       syncwarp();
       if (lane < 6) w.hes.Hbb[lane][lane] += h_damp * m.dof_damping[lane];
-      else if (lane < NV) { const int l = (lane - 6) / 3, k = (lane - 6) % 3; w.hes.Hll[l][k][k] += h_damp * m.dof_damping[lane]; }
+      else if (lane < NV) { const int l = dof_leg(), k = dof_k(); w.hes.Hll[l][k][k] += h_damp * m.dof_damping[lane]; }
     }
     syncwarp();
   }
@@ -1101,21 +1108,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV void constraint_force_and_grad() {
     if (lane < NV) {
       const int d = lane;
-      real s = 0;
+      const bool isleg = d >= 6;
+      const int l = dof_leg(), k = dof_k(), col = isleg ? 6 + k : d, j = isleg ? d - 6 : 0;
+      real s = isleg ? w.u_F[j] + w.u_sign[NFL + j] * w.u_F[NFL + j] : real(0);
       const int ncon = w.ncon;
-      if (d >= 6) {
-        const int j = d - 6, l = j / 3, k = j % 3;
-        s += w.u_F[j] + w.u_sign[NFL + j] * w.u_F[NFL + j];
-        for (int c = 0; c < ncon; c++) {
-          const int info = w.c_info[c], body = info_body(info);
-          if (body < 2 || (body - 2) / 3 != l) continue;
-          for (int a = 0; a < MAXDIM; a++) if (a < info_dim(info)) s += w.Jc[c][a][6 + k] * w.c_F[c][a];
-        }
-      } else {
-        for (int c = 0; c < ncon; c++) {
-          const int dim = info_dim(w.c_info[c]);
-          for (int a = 0; a < MAXDIM; a++) if (a < dim) s += w.Jc[c][a][d] * w.c_F[c][a];
-        }
+      for (int c = 0; c < ncon; c++) {
+        const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
+        const bool mine = !isleg || (body >= 2 && (body - 2) / 3 == l);
+        real t = 0;
+#pragma unroll
+        for (int a = 0; a < MAXDIM; a++) t += (a < dim) ? w.Jc[c][a][col] * w.c_F[c][a] : real(0);
+        s += mine ? t : real(0);
       }
       w.fcon[d] = s;
       w.grad[d] = w.Ma[d] - w.fsm[d] - s;
@@ -1273,7 +1276,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     // qacc_smooth = M^-1 qfrc_smooth
     copy_M_to_H(real(0));
     factor_H(w, lane, tri);
-    solve_H(w, lane, w.fsm, w.asmooth, real(1));
+    solve_H(w, lane, tri, w.fsm, w.asmooth, real(1));
     // warm start: cheaper of qacc_warmstart and qacc_smooth
     units_Jx(w.warm, w.u_r, w.c_r, true);
     real cost_w = units_cost();
@@ -1327,7 +1330,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int rep = 0; rep < 2; rep++) {
         build_hessian();
         factor_H(w, lane, tri);
-        solve_H(w, lane, w.grad, w.search, real(-1));
+        solve_H(w, lane, tri, w.grad, w.search, real(-1));
         if (rep == 0) QS_TACC(2); else QS_TACC(3);
       }
 #else
@@ -1335,7 +1338,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       QS_TACC(2);
       factor_H(w, lane, tri);
       QS_TACC(3);
-      solve_H(w, lane, w.grad, w.search, real(-1));
+      solve_H(w, lane, tri, w.grad, w.search, real(-1));
       QS_TACC(4);
 #endif
       // exact line search
@@ -1414,7 +1417,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     factor_H(w, lane, tri);
     if (lane < NV) w.grad[lane] = w.fsm[lane] + w.fcon[lane];
     syncwarp();
-    solve_H(w, lane, w.grad, w.search, real(1));
+    solve_H(w, lane, tri, w.grad, w.search, real(1));
     if (lane < NV) w.qvel[lane] += h * w.search[lane];
     syncwarp();
     if (lane < 3) {

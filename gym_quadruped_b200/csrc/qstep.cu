@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -60,12 +61,11 @@ struct KParams {
   // forward
   float* aux;
 #ifdef QS_PROF
-  unsigned* prof;  // diagnostic builds only: [N][16] per-env cycle marks
-  unsigned* prof2; // [N][8] solver sub-phase cycles
+  unsigned* prof;  // diagnostic builds only: [N][32] per-env cycle marks (0-15), solver sub-phase cycles (16-23), counters (24-31)
 #endif
 };
 #ifdef QS_PROF
-#define QS_MARK(k) do { if (p.prof && lane == 0 && pass == 0) p.prof[size_t(env) * 16 + (k)] = unsigned(clock64() - t_entry); } while (0)
+#define QS_MARK(k) do { if (p.prof && lane == 0 && pass == 0) p.prof[size_t(env) * 32 + (k)] = unsigned(clock64() - t_entry); } while (0)
 #else
 #define QS_MARK(k) do { } while (0)
 #endif
@@ -352,12 +352,10 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     QS_MARK(4);
     if (p.prof && lane == 0 && pass == 0) {
       unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.prof[size_t(env) * 16 + 8] = unsigned(e.solver_iter); p.prof[size_t(env) * 16 + 9] = unsigned(e.ls_evals);
-      p.prof[size_t(env) * 16 + 10] = unsigned(w.ncon); p.prof[size_t(env) * 16 + 11] = smid; p.prof[size_t(env) * 16 + 12] = unsigned(warp);
-      p.prof[size_t(env) * 16 + 0] = unsigned(t_entry & 0xffffffffll);
-      p.prof[size_t(env) * 16 + 7] = e.tacc[0]; p.prof[size_t(env) * 16 + 13] = e.tacc[1]; p.prof[size_t(env) * 16 + 14] = e.tacc[2];
-      p.prof[size_t(env) * 16 + 15] = e.tacc[3];
-      if (p.prof2) for (int i = 0; i < 8; i++) p.prof2[size_t(env) * 8 + i] = e.tacc[i];
+      unsigned* pr = p.prof + size_t(env) * 32;
+      pr[24] = unsigned(e.solver_iter); pr[25] = unsigned(e.ls_evals); pr[26] = unsigned(w.ncon); pr[27] = smid; pr[28] = unsigned(warp);
+      pr[0] = unsigned(t_entry & 0xffffffffll);
+      for (int i = 0; i < 8; i++) pr[16 + i] = e.tacc[i];
     }
 #else
     e.forward_dynamics(p.max_iter, real(p.tol));
@@ -423,6 +421,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
 
     // ---- integrate, then env-side bookkeeping
     e.integrate(base64);
+    QS_MARK(6);
     fl.out_of_bounds = e.flags().out_of_bounds;  // bounds are tested on the post-step base position (:1252-1256)
     const bool terminated = fl.invalid_mask != 0 || fl.out_of_bounds;
     sim_time += float(m.timestep);
@@ -444,6 +443,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     }
     syncwarp();
     e.pack_obs(command, fl.contact_mask);
+    QS_MARK(7);
 
     // ---- write back
     {
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     syncwarp();
   }
 #ifdef QS_PROF
-  if (p.prof && lane == 0) p.prof[size_t(env) * 16 + 6] = unsigned(clock64() - t_entry);
+  if (p.prof && lane == 0) p.prof[size_t(env) * 32 + 15] = unsigned(clock64() - t_entry);
 #endif
 }
 
@@ -564,7 +564,7 @@ struct QsHandle_ {
   QsBuffers buf{};
   bool bound = false;
   KernelFn k_step = nullptr, k_reset = nullptr, k_forward = nullptr;
-  unsigned* prof = nullptr; unsigned* prof2 = nullptr;  // QS_PROF builds only
+  unsigned* prof = nullptr;  // QS_PROF builds only
   int warps_per_cta = 8;
   size_t smem_bytes = 0;
   double timestep = 0.002;
@@ -608,6 +608,9 @@ template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const
   QS_CUDA(h, cudaGetDevice(&dev));
   QS_CUDA(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   int warps = LaunchCfg<real>::kMaxWarps;
+#ifdef QS_PROF
+  if (const char* ev = getenv("QS_WARPS_PER_CTA")) { const int v = atoi(ev); if (v >= 1 && v < warps) warps = v; }  // contention experiments
+#endif
   while (warps > 1 && V::dm_bytes() + 128 + warps * V::ws_bytes() > size_t(max_smem)) warps--;
   h->warps_per_cta = warps;
   h->smem_bytes = V::dm_bytes() + 128 + warps * V::ws_bytes();
@@ -635,7 +638,7 @@ int qs_obs_dim(const QsConfig* cfg) { return QS_NOBS_BASE + (cfg->use_imu ? QS_N
 const char* qs_last_error(QsHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int qs_max_contacts(QsHandle*) { return NCON_MAX; }
 #ifdef QS_PROF
-int qs_debug_set_prof(QsHandle* h, unsigned* prof) { h->prof = prof; h->prof2 = prof ? prof + size_t(h->cfg.num_envs) * 16 : nullptr; return 0; }  // diagnostic builds only (scripts/warp_timeline.py)
+int qs_debug_set_prof(QsHandle* h, unsigned* prof) { h->prof = prof; return 0; }  // diagnostic builds only (scripts/warp_timeline.py)
 #endif
 int64_t qs_launch_count(QsHandle* h) { return h ? h->launches : 0; }
 
@@ -717,7 +720,7 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
   p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
   if (auto_reset) { p.auto_reset = 1; p.ro = *auto_reset; }
 #ifdef QS_PROF
-  p.prof = h->prof; p.prof2 = h->prof2;
+  p.prof = h->prof;
 #endif
   if (h->sched_enabled) {
     const size_t n = size_t(h->cfg.num_envs);

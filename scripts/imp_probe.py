@@ -6,7 +6,7 @@ from gym_quadruped_b200.model import Model
 import bench
 model = Model('mini_cheetah', 'flat'); n=4096
 sim = BatchSim(model, n, device=0); opt = sim.make_reset_options(**bench.RESET_KW); sim.reset(options=opt)
-prof = torch.zeros(n * 24, dtype=torch.int32, device='cuda')
+prof = torch.zeros(n * 32, dtype=torch.int32, device='cuda')
 sim.L.qs_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
 g = torch.Generator(device='cuda').manual_seed(0)
 for t in range(300): sim.step_autoreset(torch.randn(n, 12, device='cuda', generator=g) * 50, opt)
@@ -15,7 +15,7 @@ rows=[]
 for t in range(30):
     sim.step_autoreset(torch.randn(n, 12, device='cuda', generator=g) * 50, opt); torch.cuda.synchronize()
     raw = prof.cpu().numpy()
-    P = raw[:n*16].reshape(n,16); S = raw[n*16:].reshape(n,8).view(np.float32)
+    P = raw.reshape(n,32); S = P[:,16:24].copy().view(np.float32); P = P[:, 16:].copy(); P[:, 8] = raw.reshape(n,32)[:,24]
     it = P[:,8]
     for i in np.where(it>=4)[0]: rows.append((it[i], S[i].copy()))
 print('envs with iters>=4:', len(rows))

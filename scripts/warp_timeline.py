@@ -14,50 +14,56 @@ from gym_quadruped_b200.model import Model
 import bench
 
 model = Model('mini_cheetah', 'flat')
-n = 4096
+import os
+n = int(os.environ.get('QS_N', '4096'))
 sim = BatchSim(model, n, device=0)
 opt = sim.make_reset_options(**bench.RESET_KW)
 sim.reset(options=opt)
-prof = torch.zeros(n * 24, dtype=torch.int32, device='cuda')
+prof = torch.zeros(n, 32, dtype=torch.int32, device='cuda')
 sim.L.qs_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
 g = torch.Generator(device='cuda').manual_seed(0)
 for t in range(300):
     sim.step_autoreset(torch.randn(n, 12, device='cuda', generator=g) * 50, opt)
 sim.L.qs_debug_set_prof(sim.h, C.c_void_p(prof.data_ptr()))
-names = ['load', 'position', 'vel+M+constraints', 'solve', 'integrate+obs+writeback', 'reset pass']
-agg = []; sagg = []
+names = ['load', 'position', 'vel+M+constraints', 'solve', 'integrate', 'pack_obs', 'writeback', 'reset pass']
+agg = []
 for t in range(20):
     sim.step_autoreset(torch.randn(n, 12, device='cuda', generator=g) * 50, opt)
     torch.cuda.synchronize()
-    raw = prof.cpu().numpy().astype(np.int64) & 0xffffffff
-    P = raw[:n * 16].reshape(n, 16); S = raw[n * 16:].reshape(n, 8)
-    t1, t2, t3, t4, t5, t6 = (P[:, k] for k in (1, 2, 3, 4, 5, 6))
-    it, ls, nc, sm = P[:, 8], P[:, 9], P[:, 10], P[:, 11]
-    agg.append(P.copy()); sagg.append(S.copy())
-    if t < 4:
-        print(f'--- step {t}: makespan(max end) {t6.max()} cycles; mean end {t6.mean():.0f}; p50 {np.percentile(t6,50):.0f} p90 {np.percentile(t6,90):.0f} p99 {np.percentile(t6,99):.0f}')
-        ph = [t1, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5]
+    P = prof.cpu().numpy().astype(np.int64) & 0xffffffff
+    agg.append(P.copy())
+    t1, t2, t3, t4, t5, t6, t7, tend = (P[:, k] for k in (1, 2, 3, 4, 5, 6, 7, 15))
+    it, ls, nc, sm = P[:, 24], P[:, 25], P[:, 26], P[:, 27]
+    early = t5 < t3  # early-out envs (terminated by the collision stage): mark 5 is set right after mark 2
+    if t < 3:
+        print(f'--- step {t}: makespan {tend.max()} cycles; mean end {tend.mean():.0f}; p50 {np.percentile(tend,50):.0f} p90 {np.percentile(tend,90):.0f} '
+              f'p99 {np.percentile(tend,99):.0f}; early-out envs {early.sum()}')
+        ok = ~early
+        ph = [t1, t2 - t1, t3 - t2, t4 - t3, t6 - t4, t7 - t6, t5 - t7]
         for nm, d in zip(names, ph):
+            d = d[ok]
             print(f'   {nm:28s} mean {d.mean():9.0f}  p99 {np.percentile(d,99):9.0f}  max {d.max():9.0f}')
-        order = np.argsort(-t6)[:8]
-        for i in order:
-            print(f'   slow env {i}: end {t6[i]} pass0 {t5[i]} solve {t4[i]-t3[i]} iters {it[i]} ls {ls[i]} ncon {nc[i]} sm {sm[i]} reset {int(t6[i]-t5[i] > 2000)}')
-        # per-SM makespan
-        smax = np.array([t6[sm == s].max() for s in np.unique(sm)])
+        if early.any():
+            print(f'   reset pass (early-out envs)  mean {(tend - t5)[early].mean():9.0f}  max {(tend - t5)[early].max():9.0f}')
+        for i in np.argsort(-tend)[:6]:
+            print(f'   slow env {i}: end {tend[i]} solve {t4[i]-t3[i]} iters {it[i]} ls {ls[i]} ncon {nc[i]} sm {sm[i]} early-out {int(early[i])}')
+        smax = np.array([tend[sm == s].max() for s in np.unique(sm)])
         print(f'   per-SM end: mean {smax.mean():.0f} min {smax.min()} max {smax.max()}')
 P = np.concatenate(agg)
-it = P[:, 8]; solve = P[:, 4] - P[:, 3]
-A = np.vstack([np.ones_like(it), it, P[:, 9], P[:, 10]]).T.astype(float)
+ok = P[:, 5] > P[:, 3]
+P = P[ok]
+it = P[:, 24]; solve = P[:, 4] - P[:, 3]
+A = np.vstack([np.ones_like(it), it, P[:, 25], P[:, 26]]).T.astype(float)
 coef, *_ = np.linalg.lstsq(A, solve.astype(float), rcond=None)
 print('solve cycles ~ %.0f + %.0f*iters + %.0f*ls_evals + %.0f*ncon' % tuple(coef))
 for k in range(0, 10):
     sel = it == k
     if sel.sum():
         print(f'iters={k}: frac {sel.mean():.4f} solve mean {solve[sel].mean():.0f} end-of-pass0 mean {P[sel,5].mean():.0f}')
-S = np.concatenate(sagg)
+S = P[:, 16:24]
 snames = ['pre-loop (M factor, warm start)', 'update+grad+convergence', 'build_hessian', 'factor_H', 'solve_H', 'pre line search', 'line search', 'move']
 print('solver sub-phases, mean cycles per env-step | for envs with iters>=4:')
 sel = it >= 4
 for k, nm in enumerate(snames):
     print(f'   {nm:34s} {S[:, k].mean():9.0f} | {S[sel, k].mean():9.0f}  per-iter {S[sel, k].sum() / max(1, it[sel].sum()):8.0f}')
-print('   ls evals per iteration (heavy):', P[sel, 9].sum() / max(1, it[sel].sum()))
+print('   ls evals per iteration (heavy):', P[sel, 25].sum() / max(1, it[sel].sum()))
