@@ -32,11 +32,31 @@ TORQUE_SCALE = 50.0
 RESET_KW = dict(lin_vel_range=(0.5, 1.0), ang_vel_range=(0.0, 0.0), friction_range=(0.2, 1.5), command_mode=1 | 4)
 METRIC = 'env-steps/sec (total batch) mini_cheetah/flat @4096 envs/GPU'
 UNIT = 'env-steps/s'
+USE_IMU, HEIGHTMAP = False, None
+# BASELINE.json configs[1] is the bench workload; configs[2..4] are parity-test cases (tests/test_gpu_parity.py) that can also
+# be timed for information with --workload (per-GPU batch sizes of section 8(d))
+WORKLOADS = {
+    'cfg2': dict(robot='mini_cheetah', scene='flat', envs=4096, imu=False, hm=None),
+    'cfg3': dict(robot='aliengo', scene='perlin', envs=8192, imu=False, hm=(5, 5, 0.1, 0.1)),
+    'cfg4': dict(robot='go2', scene='random_boxes', envs=4096, imu=False, hm=None),
+    'cfg5': dict(robot='hyqreal1', scene='flat', envs=8192, imu=True, hm=None),
+}
+
+
+def select_workload(name):
+    global ROBOT, SCENE, ENVS_PER_GPU, OBS_DIM, BYTES_PER_ENV_STEP, METRIC, USE_IMU, HEIGHTMAP
+    wl = WORKLOADS[name]
+    ROBOT, SCENE, ENVS_PER_GPU, USE_IMU, HEIGHTMAP = wl['robot'], wl['scene'], wl['envs'], wl['imu'], wl['hm']
+    OBS_DIM = 227 + (18 if USE_IMU else 0) + (HEIGHTMAP[0] * HEIGHTMAP[1] * 3 if HEIGHTMAP else 0)
+    # section 8(d): state read + written, observation row, reward / flags (+ IMU bias read and written)
+    BYTES_PER_ENV_STEP = 4 * (19 + 18 + 18 + 12) + 4 * (19 + 18 + 18) + 4 * OBS_DIM + 6 + (48 if USE_IMU else 0)
+    if name != 'cfg2':
+        METRIC = f'env-steps/sec (total batch) {ROBOT}/{SCENE} @{ENVS_PER_GPU} envs/GPU [informational workload {name}]'
 
 
 def workload_config(n_gpus, envs):
     return {
-        'workload': f'{ROBOT}/{SCENE}, ALL_OBS (D=227), {envs} envs per GPU, ctrl = 50*N(0,1) per actuator, '
+        'workload': f'{ROBOT}/{SCENE}, ALL_OBS (D={OBS_DIM}), {envs} envs per GPU, ctrl = 50*N(0,1) per actuator, '
                     f'random-reset initial states, auto-reset on termination',
         'robot': ROBOT, 'scene': SCENE, 'envs_per_gpu': envs, 'global_envs': envs * n_gpus, 'obs_dim': OBS_DIM,
         'sim_dt': 0.002, 'algorithmic_bytes_per_env_step': BYTES_PER_ENV_STEP, 'parallelism': f'env-sharded x{n_gpus}',
@@ -208,7 +228,7 @@ def run_gpu(args):
     K, W = args.steps, max(3, args.warmup)
 
     model = Model(ROBOT, SCENE)
-    sim = BatchSim(model, envs, device=dev, seed=args.seed, env_id_offset=rank * envs)
+    sim = BatchSim(model, envs, device=dev, seed=args.seed, env_id_offset=rank * envs, use_imu=USE_IMU, heightmap=HEIGHTMAP)
     opt = sim.make_reset_options(**RESET_KW)
     sim.reset(options=opt)
 
@@ -315,7 +335,7 @@ def run_gpu(args):
         achieved = envs * BYTES_PER_ENV_STEP / (step_kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = ROOT / 'profiles' / 'traffic.json'
-        if tp.exists():
+        if tp.exists() and args.workload == 'cfg2':
             try:
                 traffic = json.loads(tp.read_text()).get('step_kernel_dram_bytes_per_launch')
             except Exception:
@@ -332,7 +352,7 @@ def run_gpu(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': peak_src, 'kernel': 'env_kernel<float,16,3,MODE_STEP>', 'kernel_ms_per_launch': step_kernel_ms,
+                         'peak_source': peak_src, 'kernel': 'env_kernel<float,16,%d,MODE_STEP>' % (6 if ROBOT == 'go2' else 3), 'kernel_ms_per_launch': step_kernel_ms,
                          'note': 'latency/issue-bound path (about 1.4 kB and 60 kFLOP of dependent fp32 work per env-step): a low HBM fraction is expected'},
             'cpu_baseline': cpu,
             'e2e': {'value': n_gpus * envs * ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ke,
@@ -355,11 +375,15 @@ def main():
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='envs per GPU')
+    ap.add_argument('--envs', type=int, default=None, help='envs per GPU (default: the workload\'s)')
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS), help='cfg2 = BASELINE configs[1] (the bench line)')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--small-ring', action='store_true', help='64-entry action ring (profiling runs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.envs is None:
+        args.envs = ENVS_PER_GPU
     if args.impl == 'reference':
         run_reference(args)
         return

@@ -132,6 +132,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV static int tri_dof_leg(int t) { return (t >> 16) & 3; }
   QS_DEV static int tri_dof_k(int t) { return (t >> 18) & 3; }
 
+  bool calf_only = false;  // collision stage restricted to the calf-body geoms (the reset lift loop looks at nothing else)
+  QS_DEV bool geom_on(int g) const {
+    if (g >= m.ngeom) return false;
+    const int b = m.geom_body[g];
+    return !calf_only || (b >= 2 && (b - 2) % 3 == 2);
+  }
+
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
   QS_DEV static int info_dim(int info) { return info >> 16; }
@@ -636,13 +643,30 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     const int g = lane;
     real yh[3] = {0, 0, 0};
     bool is_caps = false;
-    if (g < m.ngeom && m.geom_type[g] != GEOM_MESH) {
+    if (geom_on(g) && m.geom_type[g] != GEOM_MESH) {
       const int b = m.geom_body[g], type = m.geom_type[g];
       real gx[3], tmp[3];
       mul_mv(tmp, w.kin.xmat[b], m.geom_pos[g]);
       for (int i = 0; i < 3; i++) gx[i] = w.kin.xpos[b][i] + tmp[i];
       const real margin = N::max(m.geom_margin[g], m.terr_margin);
       const real* sz = m.geom_size[g];
+      if (m.terrain_type == 2) {
+        // per-geom cull of the warp-wide candidate set: bounding sphere of the geom against the bounding sphere of each box
+        // (a superset of what the per-feature test below accepts, so the contact set is unchanged)
+        const real rb = m.geom_rbound[g] + margin + real(0.01);
+        for (int wd = 0; wd < 4; wd++) {
+          unsigned mask = boxmask[wd], keep = 0;
+          while (mask) {
+            const int bit = ctz(mask);
+            mask &= mask - 1;
+            const DBox<real>& bx = boxes[32 * wd + bit];
+            const real rel[3] = {gx[0] - bx.pos[0], gx[1] - bx.pos[1], gx[2] - bx.pos[2]};
+            const real reach = bx.rad + rb;
+            if (dot3(rel, rel) <= reach * reach) keep |= 1u << bit;
+          }
+          boxmask[wd] = keep;
+        }
+      }
       if (type == GEOM_SPHERE) {
         point_vs_terrain(gx, sz[0], margin, true, boxmask, list, n);
       } else if (type == GEOM_CAPSULE) {
@@ -729,7 +753,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     real cd[4], cp[4][3], yh[3] = {0, 0, 0};
     int nc = 0;
     const int g = lane;
-    if (g < m.ngeom && m.geom_type[g] != GEOM_MESH) {
+    if (geom_on(g) && m.geom_type[g] != GEOM_MESH) {
       const int b = m.geom_body[g];
       real gx[3], tmp[3];
       mul_mv(tmp, w.kin.xmat[b], m.geom_pos[g]);
@@ -783,7 +807,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     unsigned cand;
     {
       bool near = false;
-      if (g < m.ngeom && m.geom_type[g] == GEOM_MESH) {
+      if (geom_on(g) && m.geom_type[g] == GEOM_MESH) {
         const int b = m.geom_body[g];
         const real* R = w.kin.xmat[b];
         const real cz = w.kin.xpos[b][2] + R[6] * m.geom_bcenter[g][0] + R[7] * m.geom_bcenter[g][1] + R[8] * m.geom_bcenter[g][2];

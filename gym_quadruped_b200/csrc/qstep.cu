@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
             c_first = 101;
           }
         }
+        e.calf_only = true;
 #pragma unroll 1
         for (int c = c_first; c <= 100; c++) {
           e.kinematics();
@@ -304,7 +305,11 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
           if (c == 100) break;
           if (lane == 0) w.qpos[2] += pen * real(1.1);
           syncwarp();
+#ifdef QS_PROF
+          if (p.prof && lane == 0) { p.prof[size_t(env) * 32 + 29] = unsigned(c + 1); p.prof[size_t(env) * 32 + 30] = __float_as_uint(float(pen)); }
+#endif
         }
+        e.calf_only = false;
         if (!cleared) status |= 8u;
       }
       // zero ctrl / applied wrench / warm start / clock (quadruped_env.py:332-335, :394-395)

@@ -414,3 +414,48 @@ def test_terrain_scenes_match_oracle(robot, scene, xy, z0, cuda_device):
         qo = q1[i]
         yaw = np.arctan2(2 * (qo[3] * qo[6] + qo[4] * qo[5]), 1 - 2 * (qo[5] ** 2 + qo[6] ** 2))
         np.testing.assert_allclose(hm[i], o.heightmap(qo[:3], yaw, 5, 5, 0.1, 0.1), atol=2e-3)
+
+
+@pytest.mark.parametrize('robot,scene,n,imu,hm', [('aliengo', 'perlin', 8192, False, (5, 5, 0.1, 0.1)),   # BASELINE configs[2]
+                                                  ('go2', 'random_boxes', 4096, False, None),             # configs[3]: 16384 = 4 x 4096
+                                                  ('hyqreal1', 'flat', 8192, True, None)])                # configs[4]: 65536 = 8 x 8192
+def test_full_size_configs_properties_and_sharding_invariance(robot, scene, n, imu, hm, cuda_device):
+    """BASELINE configs 3-5 at their per-GPU sizes: size-independent properties of a random-action auto-reset rollout, and the
+    sharding contract of section 8(e): a batch split over two handles with env_id_offset reproduces the single batch bit for bit,
+    so results do not depend on the number of GPUs."""
+    m = Model(robot, scene)
+    kw = dict(use_imu=imu, heightmap=hm, seed=5)
+    full = BatchSim(m, n, device=cuda_device, **kw)
+    halves = [BatchSim(m, n // 2, device=cuda_device, env_id_offset=k * (n // 2), **kw) for k in range(2)]
+    opt = full.make_reset_options(lin_vel_range=(0.5, 1.0), friction_range=(0.2, 1.5), command_mode=1 | 4)
+    for s in [full] + halves:
+        s.reset(options=opt)
+    D = 227 + (18 if imu else 0) + (75 if hm else 0)
+    assert full.obs_dim == D
+    g = torch.Generator(device='cpu').manual_seed(11)
+    n_term = 0
+    for t in range(40):
+        ctrl = (torch.randn(n, 12, generator=g) * 50).to(cuda_device)
+        full.step_autoreset(ctrl, opt)
+        for k, s in enumerate(halves):
+            s.step_autoreset(ctrl[k * (n // 2):(k + 1) * (n // 2)].contiguous(), opt)
+        n_term += int(full.terminated.sum())
+    torch.cuda.synchronize()
+    both = lambda name: torch.cat([getattr(s, name) for s in halves])
+    for name in ('obs', 'qpos', 'qvel', 'terminated', 'command', 'friction', 'step_count', 'base_pos64'):
+        assert torch.equal(getattr(full, name), both(name)), f'{name} depends on the sharding'
+    assert n_term > 0
+    assert torch.isfinite(full.obs).all() and (full.status & 1 == 0).all()
+    q = full.obs[:, 21:25]
+    assert torch.allclose(q.norm(dim=1), torch.ones(n, device=cuda_device), atol=1e-5)
+    R = full.obs[:, 25:34].reshape(n, 3, 3)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, device=cuda_device).expand(n, 3, 3), atol=1e-5)
+    assert torch.equal(full.obs[:, 71:89], full.qvel)
+    cs = full.obs[:, 199:203]
+    assert ((cs == 0) | (cs == 1)).all()
+    if hm:  # ray-cast hit points lie on or above the floor plane and below the sensor origin
+        pts = full.obs[:, 227:].reshape(n, 5, 5, 3)
+        assert (pts[..., 2] > -1e-4).all() and (pts[..., 2] <= full.obs[:, 2].reshape(n, 1, 1) + 0.6).all()
+    if imu:  # measurement = truth + bias + noise: the three stored parts must add up
+        io = full.obs[:, 227:245]
+        assert torch.isfinite(io).all() and (io[:, 3:6].abs() < 0.2).all() and (io[:, 12:15].abs() < 0.2).all()
