@@ -21,11 +21,12 @@ CSRC = Path(__file__).resolve().parent / 'csrc'
 LIB_PATH = Path(os.environ['QSTEP_LIB']).resolve() if os.environ.get('QSTEP_LIB') else CSRC / 'libqstep.so'
 
 FIELD_MASS_MATRIX, FIELD_QFRC_BIAS, FIELD_QFRC_PASSIVE, FIELD_FEET_JACP, FIELD_FEET_POS, FIELD_COM, FIELD_CONTACTS, \
-    FIELD_QFRC_SMOOTH, FIELD_QFRC_CONSTRAINT, FIELD_XPOS, FIELD_SENSOR_IMU = range(11)
+    FIELD_QFRC_SMOOTH, FIELD_QFRC_CONSTRAINT, FIELD_XPOS, FIELD_SENSOR_IMU, FIELD_FEET_JACR, FIELD_FEET_JACP_DOT, \
+    FIELD_FEET_JACR_DOT = range(14)
 _FIELD_SHAPE = {
     FIELD_MASS_MATRIX: (18, 18), FIELD_QFRC_BIAS: (18,), FIELD_QFRC_PASSIVE: (18,), FIELD_FEET_JACP: (4, 3, 18),
     FIELD_FEET_POS: (4, 3), FIELD_COM: (3,), FIELD_QFRC_SMOOTH: (18,), FIELD_QFRC_CONSTRAINT: (18,), FIELD_XPOS: (13, 3),
-    FIELD_SENSOR_IMU: (6,),
+    FIELD_SENSOR_IMU: (6,), FIELD_FEET_JACR: (4, 3, 18), FIELD_FEET_JACP_DOT: (4, 3, 18), FIELD_FEET_JACR_DOT: (4, 3, 18),
 }
 
 CMD_FORWARD, CMD_RANDOM, CMD_ROTATE, CMD_RESET = 1, 2, 4, 8

@@ -364,6 +364,31 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
   }
 
+  // Accessor tables for mj_jac (rotational part) and mj_jacDot users (quadruped_env.py:681-797): per foot l and dof d, the
+  // rotational Jacobian and the time derivatives of both Jacobians of the calf body at the foot point, as [4][3][18] floats each.
+  // [MJ] mj_jacDot: free-joint rotations rebuild cdof_dot from the full body velocity.  Valid right after bias_and_smooth().
+  QS_DEV void dump_jacobian_tables(float* jacr, float* jacp_dot, float* jacr_dot) const {
+    for (int it = lane; it < 4 * NV; it += 32) {
+      const int l = it / NV, d = it % NV, body = 4 + 3 * l;
+      real jr[3] = {0, 0, 0}, jpd[3] = {0, 0, 0}, jrd[3] = {0, 0, 0};
+      if (d < 6 || (d - 6) / 3 == l) {
+        const real off[3] = {w.footpos[l][0] - w.com[0], w.footpos[l][1] - w.com[1], w.footpos[l][2] - w.com[2]};
+        real cv[6], cd[6], cdd[6] = {0, 0, 0, 0, 0, 0}, pvel[3], t1[3], t2[3];
+        for (int i = 0; i < 6; i++) { cv[i] = w.tmp.cvel[body][i]; cd[i] = w.cdof[d][i]; }
+        cross3(t1, cv, off);
+        for (int i = 0; i < 3; i++) pvel[i] = cv[3 + i] + t1[i];
+        if (d >= 6) for (int i = 0; i < 6; i++) cdd[i] = w.tmp.cdofdot[d][i];
+        else if (d >= 3) { real cb[6]; for (int i = 0; i < 6; i++) cb[i] = w.tmp.cvel[1][i]; cross_motion(cdd, cb, cd); }
+        cross3(t1, cdd, off);
+        cross3(t2, cd, pvel);
+        for (int i = 0; i < 3; i++) { jr[i] = cd[i]; jpd[i] = cdd[3 + i] + t1[i] + t2[i]; jrd[i] = cdd[i]; }
+      }
+      for (int i = 0; i < 3; i++) {
+        jacr[(l * 3 + i) * NV + d] = float(jr[i]); jacp_dot[(l * 3 + i) * NV + d] = float(jpd[i]); jacr_dot[(l * 3 + i) * NV + d] = float(jrd[i]);
+      }
+    }
+  }
+
   // ------------------------------------------------------------------ structured linear algebra
   // y = A x for a block matrix (bb, lb, ll); valid on dof lanes (< NV), x read from shared memory
   QS_DEV real block_matvec(const real (*Abb)[6], const real (*Alb)[3][6], const real (*All)[3][3], const real* x) const {

@@ -16,6 +16,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "qs_host_model.h"
@@ -25,10 +26,11 @@ using namespace qs;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 constexpr int NCON_MAX = 16;
-constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6;  // 992
+constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6 + 3 * 216;  // 1640
 constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_JACP = 360, AUX_OFF_FEETPOS = 576, AUX_OFF_COM = 588,
               AUX_OFF_CONTACTS = 591, AUX_OFF_SMOOTH = 591 + QS_CONTACT_STRIDE * NCON_MAX, AUX_OFF_CONSTRAINT = AUX_OFF_SMOOTH + 18,
-              AUX_OFF_XPOS = AUX_OFF_CONSTRAINT + 18, AUX_OFF_IMU = AUX_OFF_XPOS + 39;
+              AUX_OFF_XPOS = AUX_OFF_CONSTRAINT + 18, AUX_OFF_IMU = AUX_OFF_XPOS + 39, AUX_OFF_JACR = AUX_OFF_IMU + 6,
+              AUX_OFF_JACP_DOT = AUX_OFF_JACR + 216, AUX_OFF_JACR_DOT = AUX_OFF_JACP_DOT + 216;
 
 struct KParams {
   const void* dm;      // DModel<real>
@@ -363,7 +365,17 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       for (int i = 0; i < 8; i++) pr[16 + i] = e.tacc[i];
     }
 #else
-    e.forward_dynamics(p.max_iter, real(p.tol));
+    if (MODE == MODE_FORWARD && p.aux) {
+      // body velocities / cdof_dot live in storage that the constraint stage recycles: export the Jacobian tables in between
+      e.bias_and_smooth();
+      float* a = p.aux + size_t(env) * AUX_STRIDE;
+      e.dump_jacobian_tables(a + AUX_OFF_JACR, a + AUX_OFF_JACP_DOT, a + AUX_OFF_JACR_DOT);
+      syncwarp();
+      e.mass_matrix(); e.make_constraints(); e.solve(p.max_iter, real(p.tol));
+      if (m.has_imu) e.sensors();
+    } else {
+      e.forward_dynamics(p.max_iter, real(p.tol));
+    }
 #endif
     typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
 
@@ -629,7 +641,7 @@ template <typename real, int MAXDIM> static int setup_variant(QsHandle* h, const
 template <typename T> static T* mapped_alias(T* host) {
   if (!host) return nullptr;
   cudaPointerAttributes a{};
-  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaPointerGetAttributes(&a, const_cast<typename std::remove_const<T>::type*>(host)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return a.type == cudaMemoryTypeHost ? static_cast<T*>(a.devicePointer) : nullptr;
 }
 
@@ -765,13 +777,16 @@ int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_rese
     QS_CUDA(h, cudaMalloc(&h->d_term, n));
     QS_CUDA(h, cudaMalloc(&h->d_trunc, n));
   }
-  QS_CUDA(h, cudaMemcpyAsync(h->d_ctrl, ctrl, n * NU * sizeof(float), cudaMemcpyHostToDevice, s));
+  // ctrl: a pinned buffer is read by the kernel through its mapped alias (48 B per env, one coalesced row per warp, overlapped with
+  // the TMA staging of the model) -- no separate H2D copy in front of the launch; pageable memory is staged with cudaMemcpyAsync.
+  const float* k_ctrl = mapped_alias(ctrl);
+  if (!k_ctrl) QS_CUDA(h, cudaMemcpyAsync(h->d_ctrl, ctrl, n * NU * sizeof(float), cudaMemcpyHostToDevice, s));
   // Pinned host buffers are written by the kernel itself through their mapped device alias (zero-copy): every warp streams its
   // 908-B observation row over PCIe as soon as its env is done, so the transfer overlaps with the envs still being solved instead
   // of following the kernel.  Pageable buffers fall back to staging + cudaMemcpyAsync.
   float* k_obs = mapped_alias(obs); float* k_rew = mapped_alias(reward);
   uint8_t* k_term = mapped_alias(terminated); uint8_t* k_trunc = mapped_alias(truncated);
-  int rc = step_impl(h, h->d_ctrl, obs ? (k_obs ? k_obs : h->d_obs) : nullptr, reward ? (k_rew ? k_rew : h->d_reward) : nullptr,
+  int rc = step_impl(h, k_ctrl ? k_ctrl : h->d_ctrl, obs ? (k_obs ? k_obs : h->d_obs) : nullptr, reward ? (k_rew ? k_rew : h->d_reward) : nullptr,
                      terminated ? (k_term ? k_term : h->d_term) : h->d_term, truncated ? (k_trunc ? k_trunc : h->d_trunc) : nullptr,
                      auto_reset, stream);
   if (rc) return rc;
@@ -824,6 +839,9 @@ int qs_get(QsHandle* h, int field, float* dst, void* stream) {
     case QS_FIELD_QFRC_CONSTRAINT: off = AUX_OFF_CONSTRAINT; width = 18; break;
     case QS_FIELD_XPOS: off = AUX_OFF_XPOS; width = 39; break;
     case QS_FIELD_SENSOR_IMU: off = AUX_OFF_IMU; width = 6; break;
+    case QS_FIELD_FEET_JACR: off = AUX_OFF_JACR; width = 216; break;
+    case QS_FIELD_FEET_JACP_DOT: off = AUX_OFF_JACP_DOT; width = 216; break;
+    case QS_FIELD_FEET_JACR_DOT: off = AUX_OFF_JACR_DOT; width = 216; break;
     default: return fail(h, 1, "qs_get: unknown field");
   }
   QS_CUDA(h, cudaMemcpy2DAsync(dst, width * sizeof(float), h->d_aux + off, AUX_STRIDE * sizeof(float), width * sizeof(float), h->cfg.num_envs,

@@ -329,17 +329,32 @@ class QuadrupedEnv(Env):
         self.sim.forward()
         return self.sim.get(field)
 
-    def feet_jacobians(self, frame='world', return_rot_jac=False):
-        """Translational foot Jacobians (4 x 3 x nv) at the current state (mj_jac, :681-740)."""
-        if return_rot_jac:
-            raise NotImplementedError('rotational foot Jacobians are not exported yet')
-        J = self._tables(backend.FIELD_FEET_JACP)
+    def _jac_tables(self, fields, frame):
+        self.sim.forward()
         if frame == 'base':
             R = self.sim.obs[:, 25:34].reshape(-1, 3, 3)
-            J = torch.einsum('nji,nljd->nlid', R, J)
         elif frame != 'world':
             raise ValueError(f"Invalid frame: {frame} != 'world' or 'base'")
-        return LegsAttr(**{leg: self._np(J[:, k]) for k, leg in enumerate(_MODEL_LEGS)})
+        out = []
+        for f in fields:
+            J = self.sim.get(f)
+            if frame == 'base':
+                J = torch.einsum('nji,nljd->nlid', R, J)
+            out.append(LegsAttr(**{leg: self._np(J[:, k]) for k, leg in enumerate(_MODEL_LEGS)}))
+        return out
+
+    def feet_jacobians(self, frame='world', return_rot_jac=False):
+        """Foot Jacobians (per leg 3 x nv, batched [N, 3, nv]) at the current state: translational, and with
+        `return_rot_jac` also the rotational one of the calf body (mj_jac, :681-740)."""
+        fields = (backend.FIELD_FEET_JACP, backend.FIELD_FEET_JACR) if return_rot_jac else (backend.FIELD_FEET_JACP,)
+        res = self._jac_tables(fields, frame)
+        return tuple(res) if return_rot_jac else res[0]
+
+    def feet_jacobians_dot(self, frame='world', return_rot_jac=False):
+        """Time derivative of the foot Jacobians at the current (qpos, qvel) (mj_jacDot, :742-797)."""
+        fields = (backend.FIELD_FEET_JACP_DOT, backend.FIELD_FEET_JACR_DOT) if return_rot_jac else (backend.FIELD_FEET_JACP_DOT,)
+        res = self._jac_tables(fields, frame)
+        return tuple(res) if return_rot_jac else res[0]
 
     @property
     def mass_matrix(self):

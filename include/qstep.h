@@ -264,7 +264,10 @@ enum { QS_FIELD_MASS_MATRIX = 0, /* [N,18,18] */
        QS_FIELD_QFRC_SMOOTH = 7, /* [N,18] */
        QS_FIELD_QFRC_CONSTRAINT = 8, /* [N,18] */
        QS_FIELD_XPOS = 9,        /* [N,13,3] body positions (bodies 1..13) */
-       QS_FIELD_SENSOR_IMU = 10  /* [N,6] noiseless accelerometer + gyro */ };
+       QS_FIELD_SENSOR_IMU = 10, /* [N,6] noiseless accelerometer + gyro */
+       QS_FIELD_FEET_JACR = 11,  /* [N,4,3,18] rotational Jacobian of each calf body (mj_jac jacr, quadruped_env.py:728-735) */
+       QS_FIELD_FEET_JACP_DOT = 12, /* [N,4,3,18] d/dt of QS_FIELD_FEET_JACP (mj_jacDot jacp, quadruped_env.py:785-792) */
+       QS_FIELD_FEET_JACR_DOT = 13  /* [N,4,3,18] d/dt of QS_FIELD_FEET_JACR (mj_jacDot jacr) */ };
 int qs_get(QsHandle* h, int field, float* dev_dst, void* cuda_stream);
 int qs_max_contacts(QsHandle* h);
 #define QS_CONTACT_STRIDE 20 /* dist, pos[3], frame[9], force[3], geom, body, mu, pad */

@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'build' / 'liboracle.so'
 
 F_M, F_BIAS, F_PASSIVE, F_FEET_JACP, F_FEET_POS, F_COM, F_CONTACTS, F_SMOOTH, F_CONSTRAINT, F_XPOS, F_IMU, \
-    F_QACC_SMOOTH, F_EFC, F_FLAGS = range(14)
+    F_QACC_SMOOTH, F_EFC, F_FLAGS, F_FEET_JACR, F_FEET_JACP_DOT, F_FEET_JACR_DOT = range(17)
 
 
 def build(force: bool = False) -> Path:
@@ -130,7 +130,7 @@ class Oracle:
         n = self.L.orc_get(self.h, field, _p(buf))
         if field == F_M:
             return buf[:324].reshape(18, 18).copy()
-        if field == F_FEET_JACP:
+        if field in (F_FEET_JACP, F_FEET_JACR, F_FEET_JACP_DOT, F_FEET_JACR_DOT):
             return buf[:n].reshape(4, 3, 18).copy()
         if field == F_FEET_POS:
             return buf[:12].reshape(4, 3).copy()

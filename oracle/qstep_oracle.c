@@ -314,6 +314,31 @@ static void jacPoint(const OData* d, double jp[3][NV], double jr[3][NV], const d
   }
 }
 
+/* [MJ] mj_jacDot (quadruped_env.py:785): time derivative of the point Jacobian of `body` at `point`.  Needs comVel results.
+ * Free-joint rotations (dofs 3..5) carry no stored cdof_dot: it is rebuilt from the full body velocity, as the engine does for
+ * quaternion dofs.  Pinned by tests/test_oracle_physics.py against a finite difference of jacPoint along the flow of qvel. */
+static void jacDotPoint(const OData* d, double jp[3][NV], double jr[3][NV], const double* point, int body) {
+  double off[3], pvel[3], c[3];
+  for (int i = 0; i < 3; i++) off[i] = point[i] - d->com[i];
+  cross3(c, d->cvel[body], off);
+  for (int i = 0; i < 3; i++) pvel[i] = d->cvel[body][3 + i] + c[i];
+  memset(jp, 0, 3 * NV * sizeof(double));
+  if (jr) memset(jr, 0, 3 * NV * sizeof(double));
+  int b = body;
+  while (b > 0) {
+    int d0 = (b == 1) ? 0 : 6 + (b - 2), nd = (b == 1) ? 6 : 1;
+    for (int k = d0; k < d0 + nd; k++) {
+      double cdd[6], t1[3], t2[3];
+      memcpy(cdd, d->cdof_dot[k], sizeof(cdd));
+      if (b == 1 && k >= 3) crossMotion(cdd, d->cvel[1], d->cdof[k]);
+      cross3(t1, cdd, off);
+      cross3(t2, d->cdof[k], pvel);
+      for (int i = 0; i < 3; i++) { jp[i][k] = cdd[3 + i] + t1[i] + t2[i]; if (jr) jr[i][k] = cdd[i]; }
+    }
+    b = d->m.body_parent[b];
+  }
+}
+
 /* ------------------------------------------------------------------ collision */
 static void mixParams(const QsGeomParams* a /*world*/, const QsGeomParams* b /*robot*/, const double* fa, const double* fb,
                       OContact* c) {
@@ -1268,7 +1293,7 @@ int orc_lift(void* h) {
 }
 
 enum { F_M = 0, F_BIAS = 1, F_PASSIVE = 2, F_FEET_JACP = 3, F_FEET_POS = 4, F_COM = 5, F_CONTACTS = 6, F_SMOOTH = 7, F_CONSTRAINT = 8,
-       F_XPOS = 9, F_IMU = 10, F_QACC_SMOOTH = 11, F_EFC = 12, F_FLAGS = 13 };
+       F_XPOS = 9, F_IMU = 10, F_QACC_SMOOTH = 11, F_EFC = 12, F_FLAGS = 13, F_FEET_JACR = 14, F_FEET_JACP_DOT = 15, F_FEET_JACR_DOT = 16 };
 int orc_get(void* h, int field, double* dst) {
   OData* d = (OData*)h;
   switch (field) {
@@ -1277,6 +1302,14 @@ int orc_get(void* h, int field, double* dst) {
     case F_PASSIVE: memcpy(dst, d->qfrc_passive, sizeof(d->qfrc_passive)); return NV;
     case F_FEET_JACP:
       for (int l = 0; l < 4; l++) { double jp[3][NV]; jacPoint(d, jp, NULL, d->geom_xpos[d->m.foot_geom[l]], 4 + 3 * l); memcpy(dst + l * 3 * NV, jp, sizeof(jp)); }
+      return 4 * 3 * NV;
+    case F_FEET_JACR: case F_FEET_JACP_DOT: case F_FEET_JACR_DOT:
+      for (int l = 0; l < 4; l++) {
+        double jp[3][NV], jr[3][NV];
+        if (field == F_FEET_JACR) jacPoint(d, jp, jr, d->geom_xpos[d->m.foot_geom[l]], 4 + 3 * l);
+        else jacDotPoint(d, jp, jr, d->geom_xpos[d->m.foot_geom[l]], 4 + 3 * l);
+        memcpy(dst + l * 3 * NV, field == F_FEET_JACP_DOT ? jp : jr, sizeof(jp));
+      }
       return 4 * 3 * NV;
     case F_FEET_POS: for (int l = 0; l < 4; l++) memcpy(dst + 3 * l, d->geom_xpos[d->m.foot_geom[l]], 3 * sizeof(double)); return 12;
     case F_COM: memcpy(dst, d->com, sizeof(d->com)); return 3;

@@ -7,10 +7,11 @@ import numpy as np
 import pytest
 import torch
 
-from gym_quadruped_b200.backend import (FIELD_CONTACTS, FIELD_FEET_JACP, FIELD_FEET_POS, FIELD_MASS_MATRIX, FIELD_QFRC_BIAS,
-                                        FIELD_QFRC_SMOOTH, BatchSim)
+from gym_quadruped_b200.backend import (FIELD_CONTACTS, FIELD_FEET_JACP, FIELD_FEET_JACP_DOT, FIELD_FEET_JACR, FIELD_FEET_JACR_DOT,
+                                        FIELD_FEET_POS, FIELD_MASS_MATRIX, FIELD_QFRC_BIAS, FIELD_QFRC_SMOOTH, BatchSim)
 from gym_quadruped_b200.model import Model
-from oracle.oracle import F_BIAS, F_CONTACTS, F_FEET_JACP, F_FEET_POS, F_M, F_SMOOTH, Oracle
+from oracle.oracle import (F_BIAS, F_CONTACTS, F_FEET_JACP, F_FEET_JACP_DOT, F_FEET_JACR, F_FEET_JACR_DOT, F_FEET_POS, F_M, F_SMOOTH,
+                           Oracle)
 from tests.helpers import oracle_rollout, seeded_states
 
 pytestmark = pytest.mark.gpu
@@ -37,10 +38,14 @@ def test_forward_tables_match_oracle(model, cuda_device, precision, tol):
     M = sim.get(FIELD_MASS_MATRIX).cpu().numpy(); bias = sim.get(FIELD_QFRC_BIAS).cpu().numpy()
     fsm = sim.get(FIELD_QFRC_SMOOTH).cpu().numpy(); jac = sim.get(FIELD_FEET_JACP).cpu().numpy(); fpos = sim.get(FIELD_FEET_POS).cpu().numpy()
     con = sim.get(FIELD_CONTACTS).cpu().numpy(); ncon = sim.ncon.cpu().numpy(); qacc = sim.qacc.cpu().numpy()
+    jacr = sim.get(FIELD_FEET_JACR).cpu().numpy(); jpd = sim.get(FIELD_FEET_JACP_DOT).cpu().numpy(); jrd = sim.get(FIELD_FEET_JACR_DOT).cpu().numpy()
     for i in range(n):
         o = Oracle(model)
         o.set_state(qpos[i], qvel[i], np.zeros(18))
         o.forward(np.zeros(12))
+        np.testing.assert_allclose(jacr[i], o.get(F_FEET_JACR), atol=tol)          # mj_jac rotational part
+        np.testing.assert_allclose(jpd[i], o.get(F_FEET_JACP_DOT), atol=tol * 5)   # mj_jacDot
+        np.testing.assert_allclose(jrd[i], o.get(F_FEET_JACR_DOT), atol=tol * 5)
         np.testing.assert_allclose(M[i], o.get(F_M), atol=tol)
         np.testing.assert_allclose(bias[i], o.get(F_BIAS), atol=tol * 50)
         np.testing.assert_allclose(fsm[i], o.get(F_SMOOTH), atol=tol * 50)
@@ -339,6 +344,11 @@ def test_quadruped_env_surface(cuda_device):
         assert env.feet_pos().FL.shape == (3,) and env.base_lin_vel('base').shape == (3,)
         J = env.feet_jacobians()
         assert J.FR.shape == (3, 18) and env.legs_mass_matrix.RL.shape == (3, 3) and env.com.shape == (3,)
+        Jp, Jr = env.feet_jacobians(frame='base', return_rot_jac=True)
+        Jpd, Jrd = env.feet_jacobians_dot(return_rot_jac=True)
+        assert Jr.FL.shape == (3, 18) and Jpd.RR.shape == (3, 18) and np.isfinite(Jrd.RL).all()
+        # foot velocity = J qvel in the same frame (feet_vel is packed from the same forward pass one step earlier: compare fresh)
+        assert np.abs(Jr.FL[:, :3]).max() == 0  # base translations do not rotate the calf
         env.close()
     # batched + IMU + legs_order permutation
     env = QuadrupedEnv('hyqreal1', state_obs_names=('qpos', 'feet_pos', 'contact_state', 'imu_acc', 'imu_gyro_bias'), sensors=(IMU,),

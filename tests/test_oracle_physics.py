@@ -161,6 +161,33 @@ def test_feet_jacobian_matches_finite_differences():
         np.testing.assert_allclose(J[:, :, d], fd, atol=2e-6)
 
 
+@pytest.mark.parametrize('robot', ['aliengo', 'mini_cheetah'])
+def test_feet_jacobian_dot_matches_finite_difference_along_the_flow(robot):
+    """mj_jacDot users (quadruped_env.py:742-797): Jdot(q, v) = d/dt J(q(t)) with q advanced along qvel (free-joint rotation in
+    the body frame), for the translational and the rotational foot Jacobians."""
+    from oracle.oracle import F_FEET_JACP_DOT, F_FEET_JACR, F_FEET_JACR_DOT
+    m = Model(robot, 'flat')
+    rng = np.random.RandomState(7)
+    q = _airborne(m, rng)
+    v = rng.uniform(-1.5, 1.5, 18)
+    o = Oracle(m)
+    o.set_state(q, v, np.zeros(18)); o.forward(np.zeros(12))
+    Jp_dot, Jr_dot = o.get(F_FEET_JACP_DOT), o.get(F_FEET_JACR_DOT)
+    J = {}
+    eps = 1e-6
+    for sgn in (-1, 1):
+        qq = q.copy()
+        qq[:3] += sgn * eps * v[:3]
+        qq[3:7] = (Rotation.from_quat(q[[4, 5, 6, 3]]) * Rotation.from_rotvec(sgn * eps * v[3:6])).as_quat()[[3, 0, 1, 2]]
+        qq[7:] += sgn * eps * v[6:]
+        o2 = Oracle(m)
+        o2.set_state(qq, v, np.zeros(18)); o2.forward(np.zeros(12))
+        J[sgn] = (o2.get(F_FEET_JACP), o2.get(F_FEET_JACR))
+    np.testing.assert_allclose(Jp_dot, (J[1][0] - J[-1][0]) / (2 * eps), atol=5e-6)
+    np.testing.assert_allclose(Jr_dot, (J[1][1] - J[-1][1]) / (2 * eps), atol=5e-6)
+    assert np.abs(Jp_dot).max() > 0.1 and np.abs(Jr_dot).max() > 0.1
+
+
 def test_joint_limit_pushes_back():
     m = Model('aliengo', 'flat')
     o = Oracle(m)
