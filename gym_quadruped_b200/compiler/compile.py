@@ -26,6 +26,9 @@ ROBOTS = {
     'aliengo': ('aliengo/aliengo.xml', 0.35, None),
     'go2': ('go2/go2.xml', 0.28, None),
     'hyqreal1': ('hyqreal1/hyqreal1.xml', 0.498, None),
+    'hyqreal2': ('hyqreal2/hyqreal2.xml', 0.498, None),   # joint-level actuatorfrcrange clamps
+    'go1': ('go1/go1.xml', 0.3, None),                    # fromto capsules, cylinders, condim-6 priority feet
+    'b2': ('b2/b2.xml', 0.485, None),                     # cylinders
 }
 
 
@@ -122,7 +125,7 @@ def compile_robot(reference_root: Path, robot: str) -> dict:
     bodies, joints, geoms = r['bodies'], r['joints'], r['geoms']
 
     names = [b['name'] for b in bodies]
-    assert names == EXPECTED_BODIES, f'unexpected body tree {names}'
+    assert names[1:] == EXPECTED_BODIES[1:], f'unexpected body tree {names}'  # the root body may be called base / trunk
     assert joints[0]['type'] == 'free' and joints[0]['body'] == 1
     hinges = joints[1:]
     assert len(hinges) == 12
@@ -195,6 +198,8 @@ def compile_robot(reference_root: Path, robot: str) -> dict:
                 entry['rbound'] = float(s[0] + s[1])
             elif g['type'] == 'box':
                 entry['rbound'] = float(np.linalg.norm(s))
+            elif g['type'] == 'cylinder':
+                entry['rbound'] = float(np.hypot(s[0], s[1]))
             else:
                 raise ValueError(f'unsupported collision geom type {g["type"]}')
         if g['name'] in LEGS:
@@ -219,6 +224,16 @@ def compile_robot(reference_root: Path, robot: str) -> dict:
     for s in r['sensors']:
         sensor_adr[s['name']] = adr
         adr += dims[s['type']]
+
+    # [MJ] actuatorfrcrange clamps the summed actuator force of a joint after the per-actuator forcerange; with one unit-gear
+    # motor per hinge the two clamps nest into one interval
+    for k, a in enumerate(r['actuators']):
+        fr = hinges[k].get('actuatorfrcrange')
+        if fr is not None:
+            if a['forcelimited']:
+                a['forcerange'] = np.array([max(a['forcerange'][0], fr[0]), min(a['forcerange'][1], fr[1])])
+            else:
+                a['forcerange'], a['forcelimited'] = np.asarray(fr, dtype=np.float64), True
 
     model = {
         'robot': robot, 'mjcf': rel, 'hip_height': hip_height,

@@ -197,8 +197,11 @@ def parse_robot(xml_path: str | Path) -> dict:
             has_range = 'range' in a
             lim = a.get('limited', 'auto')
             limited = has_range if lim == 'auto' else (lim == 'true')
-            assert 'actuatorfrcrange' not in a, 'actuatorfrcrange not supported (hyqreal2 only)'
+            # joint-level clamp of the total actuator force (hyqreal2.xml:36); `actuatorfrclimited` follows autolimits
+            frc_lim = a.get('actuatorfrclimited', 'auto')
+            has_frc = ('actuatorfrcrange' in a) if frc_lim == 'auto' else (frc_lim == 'true')
             joints.append({
+                'actuatorfrcrange': _vec(a['actuatorfrcrange']) if has_frc else None,
                 'name': a['name'], 'type': 'hinge', 'body': bid,
                 'pos': _vec(a['pos']), 'axis': quat_normalize(_vec(a['axis'])),
                 'range': _vec(a['range']) if has_range else np.zeros(2), 'limited': bool(limited),
@@ -213,10 +216,29 @@ def parse_robot(xml_path: str | Path) -> dict:
             contype, conaff = int(a['contype']), int(a['conaffinity'])
             if contype == 0 and conaff == 0:
                 continue  # visual only; bodies carry explicit inertials so these never matter
-            assert 'fromto' not in a, 'fromto geoms not supported'
             gtype = a['type']
             if 'mesh' in a and 'type' not in g.attrib and gtype == 'sphere':
                 gtype = 'mesh'
+            if 'fromto' in a:
+                # [MJ] fromto (go1.xml:47-59): centre at the midpoint, half-length from the segment, z axis along from - to
+                # (shortest-arc rotation of +z, as the engine's z2quat)
+                assert gtype in ('capsule', 'cylinder'), 'fromto only for capsules / cylinders'
+                ft = _vec(a['fromto'])
+                p1, p2 = ft[:3], ft[3:]
+                vec = p1 - p2
+                length = float(np.linalg.norm(vec))
+                z = vec / length
+                axis = np.cross([0.0, 0.0, 1.0], z)
+                sn = float(np.linalg.norm(axis))
+                ang = float(np.arctan2(sn, z[2]))
+                if sn < 1e-10:
+                    quat = np.array([1.0, 0, 0, 0]) if z[2] > 0 else np.array([0.0, 1.0, 0, 0])
+                else:
+                    quat = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * axis / sn])
+                a = dict(a)
+                a['pos'] = ' '.join(repr(float(x)) for x in 0.5 * (p1 + p2))
+                a['quat'] = ' '.join(repr(float(x)) for x in quat)
+                a['size'] = f"{float(_vec(a['size'], 3, (0, 0, 0))[0])!r} {0.5 * length!r}"
             geoms.append({
                 'name': a.get('name', ''), 'body': bid, 'type': gtype, 'mesh': a.get('mesh'),
                 'size': _vec(a['size'], 3, (0, 0, 0)), 'pos': _vec(a['pos']), 'quat': quat_normalize(_vec(a['quat'])),

@@ -21,7 +21,7 @@ constexpr int NOBS_BASE = 227;
 constexpr int NFL = 12;   // friction-loss units (one per hinge)
 constexpr int NLIM = 12;  // joint-limit units (one slot per hinge; lower and upper cannot be active together)
 
-enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_BOX = 6, GEOM_MESH = 7 };
+enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_CYLINDER = 5, GEOM_BOX = 6, GEOM_MESH = 7 };
 
 template <typename real> struct alignas(16) Vert4 { real x, y, z, w; };
 // static terrain box (random_boxes scene): centre, rotation (row-major), half sizes, bounding radius
@@ -703,15 +703,18 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           const real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
           point_vs_terrain(p, sz[0], margin, true, boxmask, list, n);
         }
-      } else if (type == GEOM_BOX) {
+      } else if (type == GEOM_BOX || type == GEOM_CYLINDER) {
+        // box corners / eight cylinder rim points (four per cap) as point features
         real gm[9];
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.kin.xmat[b][3 * r] * m.geom_mat[g][c] + w.kin.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.kin.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
+        const bool cyl = type == GEOM_CYLINDER;
         for (int i = 0; i < 8; i++) {
-          const real v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]};
+          real v[3] = {(i & 1) ? sz[0] : -sz[0], (i & 2) ? sz[1] : -sz[1], (i & 4) ? sz[2] : -sz[2]};
+          if (cyl) { const real a = v[0]; v[0] = (i & 2) ? a : real(0); v[1] = (i & 2) ? real(0) : a; v[2] = (i & 4) ? sz[1] : -sz[1]; }
           real corner[3];
           mul_mv(corner, gm, v);
           const real p[3] = {corner[0] + gx[0], corner[1] + gx[1], corner[2] + gx[2]};
-          point_vs_terrain(p, real(0), margin, false, boxmask, list, n);
+          point_vs_terrain(p, real(0), margin, cyl, boxmask, list, n);
         }
       }
     }
@@ -800,6 +803,40 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           real dist = p[2] - sz[0];
           if (dist > margin) continue;
           cd[nc] = dist; cp[nc][0] = p[0]; cp[nc][1] = p[1]; cp[nc][2] = p[2] - (sz[0] + real(0.5) * dist); nc++;
+        }
+      } else if (type == GEOM_CYLINDER) {
+        // [MJ] mjc_PlaneCylinder: nearest rim point of the lower cap, its twin on the other cap, two more lower-rim points at +-120 deg
+        real gxa[3] = {m.geom_mat[g][0], m.geom_mat[g][3], m.geom_mat[g][6]}, gza[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]};
+        real xax[3], axis[3], vec[3];
+        mul_mv(xax, w.kin.xmat[b], gxa);
+        mul_mv(axis, w.kin.xmat[b], gza);
+        real prjaxis = axis[2];
+        if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
+        const real dist0 = gx[2];
+        vec[0] = axis[0] * prjaxis; vec[1] = axis[1] * prjaxis; vec[2] = axis[2] * prjaxis - 1;
+        const real len_sqr = dot3(vec, vec);
+        if (len_sqr >= real(1e-30)) { const real scl = sz[0] * N::rsqrt(len_sqr); for (int i = 0; i < 3; i++) vec[i] *= scl; }
+        else for (int i = 0; i < 3; i++) vec[i] = xax[i] * sz[0];
+        const real prjvec = vec[2];
+        const real ax[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
+        prjaxis *= sz[1];
+        real dist = dist0 + prjaxis + prjvec;
+        if (!(dist > margin)) {
+          cd[0] = dist; for (int i = 0; i < 3; i++) cp[0][i] = gx[i] + vec[i] + ax[i]; cp[0][2] -= real(0.5) * dist; nc = 1;
+          dist = dist0 - prjaxis + prjvec;
+          if (!(dist > margin)) { cd[nc] = dist; for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + vec[i] - ax[i]; cp[nc][2] -= real(0.5) * dist; nc++; }
+          dist = dist0 + prjaxis - real(0.5) * prjvec;
+          if (!(dist > margin)) {
+            real vec1[3];
+            cross3(vec1, vec, ax);
+            const real n2 = dot3(vec1, vec1), scl = n2 > 0 ? sz[0] * real(0.86602540378443864676) * N::rsqrt(n2) : real(0);
+            for (int sgn = 1; sgn >= -1; sgn -= 2) {
+              cd[nc] = dist;
+              for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + sgn * scl * vec1[i] + ax[i] - real(0.5) * vec[i];
+              cp[nc][2] -= real(0.5) * dist;
+              nc++;
+            }
+          }
         }
       } else if (type == GEOM_BOX) {
         real gm[9];

@@ -110,7 +110,7 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   for (int g = 0; g < s.ngeom; g++) {
     const QsGeomParams& gp = s.geom_par[g];
     const int t = s.geom_type[g];
-    if (!(t == QS_GEOM_SPHERE || t == QS_GEOM_CAPSULE || t == QS_GEOM_BOX || t == QS_GEOM_MESH)) return "unsupported geom type";
+    if (!(t == QS_GEOM_SPHERE || t == QS_GEOM_CAPSULE || t == QS_GEOM_CYLINDER || t == QS_GEOM_BOX || t == QS_GEOM_MESH)) return "unsupported geom type";
     d.geom_type[g] = t; d.geom_body[g] = s.geom_body[g]; d.geom_leg[g] = s.geom_foot_leg[g];
     d.geom_vertadr[g] = s.geom_vertadr[g]; d.geom_vertnum[g] = s.geom_vertnum[g];
     double m9[9];

@@ -439,6 +439,38 @@ static void collideFloor(OData* d) {
           cnt++;
         }
       } break;
+      case QS_GEOM_CYLINDER: {
+        /* [MJ] mjc_PlaneCylinder (b2.xml:96, go1.xml:27-44): the rim point nearest to the plane on the lower cap, the matching
+         * point of the other cap, and two more points of the lower rim at +-120 degrees */
+        double axis[3] = {gm[2], gm[5], gm[8]}, prjaxis = axis[2], vec[3];
+        if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
+        const double dist0 = gx[2];
+        for (int i = 0; i < 3; i++) vec[i] = axis[i] * prjaxis - n[i];
+        const double len_sqr = dot3(vec, vec);
+        if (len_sqr >= 1e-30) { const double scl = sz[0] / sqrt(len_sqr); for (int i = 0; i < 3; i++) vec[i] *= scl; }
+        else { vec[0] = gm[0] * sz[0]; vec[1] = gm[3] * sz[0]; vec[2] = gm[6] * sz[0]; }
+        const double prjvec = vec[2];
+        double ax[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
+        prjaxis *= sz[1];
+        double dist = dist0 + prjaxis + prjvec;
+        if (dist > margin) break;
+        { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + vec[i] + ax[i] - n[i] * dist * 0.5;
+          addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri); }
+        dist = dist0 - prjaxis + prjvec;
+        if (!(dist > margin)) { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + vec[i] - ax[i] - n[i] * dist * 0.5;
+          addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri); }
+        dist = dist0 + prjaxis - 0.5 * prjvec;
+        if (!(dist > margin)) {
+          double vec1[3];
+          cross3(vec1, vec, ax);
+          const double nv = norm3(vec1), scl = nv > 0 ? sz[0] * sqrt(3.0) * 0.5 / nv : 0.0;
+          for (int sgn = 1; sgn >= -1; sgn -= 2) {
+            double pos[3];
+            for (int i = 0; i < 3; i++) pos[i] = gx[i] + sgn * scl * vec1[i] + ax[i] - 0.5 * vec[i] - n[i] * dist * 0.5;
+            addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri);
+          }
+        }
+      } break;
       case QS_GEOM_MESH: {
         /* support vertex in -normal direction; vertices are stored in the body frame */
         double c[3], tmp[3];
@@ -529,7 +561,7 @@ static void collidePointTerrain(OData* d, int g, const double* p, double r, int 
       mulMatVec3(nw, R, nl); /* box -> point */
       double pos[3] = {p[0] - nw[0] * (r + 0.5 * dist), p[1] - nw[1] * (r + 0.5 * dist), p[2] - nw[2] * (r + 0.5 * dist)};
       /* geom1/geom2 ordered by type: sphere / capsule sort before box, so the robot geom is geom1 and the normal flips [MJ] */
-      int robot_first = geom_type == QS_GEOM_SPHERE || geom_type == QS_GEOM_CAPSULE;
+      int robot_first = geom_type == QS_GEOM_SPHERE || geom_type == QS_GEOM_CAPSULE || geom_type == QS_GEOM_CYLINDER;
       double nn[3] = {robot_first ? -nw[0] : nw[0], robot_first ? -nw[1] : nw[1], robot_first ? -nw[2] : nw[2]};
       addContact(d, g, 1 + b, robot_first ? -1 : 1, dist, pos, nn, yaxis, &m->box_par, m->box_par.friction);
     }
@@ -557,6 +589,15 @@ static void collideTerrain(OData* d) {
           mulMatVec3(c, gm, v);
           double p[3] = {c[0] + gx[0], c[1] + gx[1], c[2] + gx[2]};
           collidePointTerrain(d, g, p, 0.0, QS_GEOM_BOX, NULL);
+        }
+        break;
+      case QS_GEOM_CYLINDER:  /* eight rim points (four per cap) as point features: an approximation, like the box corners */
+        for (int i = 0; i < 8; i++) {
+          const double a = (i & 1) ? sz[0] : -sz[0];
+          double v[3] = {(i & 2) ? a : 0.0, (i & 2) ? 0.0 : a, (i & 4) ? sz[1] : -sz[1]}, c[3];
+          mulMatVec3(c, gm, v);
+          double p[3] = {c[0] + gx[0], c[1] + gx[1], c[2] + gx[2]};
+          collidePointTerrain(d, g, p, 0.0, QS_GEOM_CYLINDER, NULL);
         }
         break;
       default: break;

@@ -244,7 +244,7 @@ def test_fused_autoreset_equals_step_then_reset(model, cuda_device):
 # elliptic cones with impratio 100 (go2, hyqreal1) are ~100x stiffer in the friction directions and amplify fp32 rounding:
 # the 1e-4 bar of north_star is met by the pyramidal robots, the elliptic ones are held to 5e-4 here (fp64 build: 1e-10, see
 # tests/test_emulator_parity.py)
-@pytest.mark.parametrize('robot,tol', [('aliengo', 1e-4), ('go2', 5e-4), ('hyqreal1', 5e-4)])
+@pytest.mark.parametrize('robot,tol', [('aliengo', 1e-4), ('go2', 5e-4), ('hyqreal1', 5e-4), ('hyqreal2', 1e-4), ('b2', 1e-4)])
 def test_other_robots_rollout_matches_oracle(robot, tol, cuda_device):
     """Pyramidal + primitives + joint limits (aliengo), elliptic cone with condim-6 feet (go2), elliptic + meshes (hyqreal1)."""
     m = Model(robot, 'flat')
