@@ -39,6 +39,7 @@ template <typename real> struct alignas(16) DModel {
   real mass_total, robot_radius, pad_r[2];
   real hf_size[4], hf_pos[4];          // height field: half-x, half-y, z-scale, base; position
   real terr_fri[4], terr_margin, terr_pad[3];  // hfield / box geoms carry default parameters
+  real terr_bounds[4];                         // x_max, x_min, y_max, y_min of everything that is not the floor plane, padded by the robot's reach
   real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_imat[NB][9], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
   real jnt_pos[NJ][3], jnt_axis[NJ][3], jnt_range[NJ][2], jnt_K[NJ], jnt_B[NJ], jnt_solimp[NJ][5], jnt_margin[NJ];
   real qpos0[20], key_qpos[20];
@@ -132,6 +133,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV static int tri_dof_leg(int t) { return (t >> 16) & 3; }
   QS_DEV static int tri_dof_k(int t) { return (t >> 18) & 3; }
 
+  bool terrain_on = true;  // false: the base is out of reach of everything but the floor plane (internal frame re-centred like 'flat')
   bool calf_only = false;  // collision stage restricted to the calf-body geoms (the reset lift loop looks at nothing else)
   QS_DEV bool geom_on(int g) const {
     if (g >= m.ngeom) return false;
@@ -731,6 +733,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // downward ray from `org` against the static terrain: distance to the nearest hit or -1 ([MJ] mj_ray, heightmap.py:77-99)
   QS_DEV real ray_down(const real* org) const {
     real best = org[2] >= 0 ? org[2] : real(-1);  // floor plane z = 0
+    if (!terrain_on) return best;
     if (m.terrain_type == 1) {
       real z, nn[3];
       if (hfield_height(org[0], org[1], z, nn) && org[2] >= z) { const real t = org[2] - z; if (best < 0 || t < best) best = t; }
@@ -863,7 +866,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       ncon += popc(mask);
     }
-    if (m.terrain_type != 0) collide_terrain(ncon);
+    if (m.terrain_type != 0 && terrain_on) collide_terrain(ncon);
     // convex meshes. Broad phase: lanes test the body-frame bounding box of every mesh against the plane (a lower bound of the
     // hull's lowest point, tight for long thin links); only the survivors are scanned, by the whole warp, for their support vertex.
     unsigned cand;

@@ -68,6 +68,21 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   for (int i = 0; i < 4; i++) d.hf_size[i] = real(s.hf_size[i]);
   for (int i = 0; i < 3; i++) { d.hf_pos[i] = real(s.hf_pos[i]); d.terr_fri[i] = real(s.box_par.friction[i]); }
   d.terr_margin = real(s.box_par.margin);
+  {  // bounding rectangle of the non-floor terrain, padded by the robot's reach: outside it an env sees the floor plane only
+    double b[4] = {-big, big, -big, big};
+    const double pad = double(d.robot_radius) + 1.0;
+    if (s.terrain_type == QS_TERRAIN_HFIELD) {
+      b[0] = s.hf_pos[0] + s.hf_size[0]; b[1] = s.hf_pos[0] - s.hf_size[0]; b[2] = s.hf_pos[1] + s.hf_size[1]; b[3] = s.hf_pos[1] - s.hf_size[1];
+    } else if (s.terrain_type == QS_TERRAIN_BOXES) {
+      for (int k = 0; k < s.nbox; k++) {
+        const double* h = s.box_half[k];
+        const double r = std::sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);
+        b[0] = std::max(b[0], s.box_pos[k][0] + r); b[1] = std::min(b[1], s.box_pos[k][0] - r);
+        b[2] = std::max(b[2], s.box_pos[k][1] + r); b[3] = std::min(b[3], s.box_pos[k][1] - r);
+      }
+    }
+    d.terr_bounds[0] = real(b[0] + pad); d.terr_bounds[1] = real(b[1] - pad); d.terr_bounds[2] = real(b[2] + pad); d.terr_bounds[3] = real(b[3] - pad);
+  }
   d.hf_nrow = s.hf_nrow; d.hf_ncol = s.hf_ncol;
   if (s.terrain_type == QS_TERRAIN_HFIELD && (s.hf_nrow < 2 || s.hf_ncol < 2 || !s.hf_data)) return "height field data missing";
   if (s.terrain_type == QS_TERRAIN_BOXES && (s.nbox < 0 || s.nbox > QS_MAXBOX)) return "nbox out of range";

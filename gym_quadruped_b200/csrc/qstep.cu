@@ -160,10 +160,23 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   mbar_wait(mbar, 0);
   if (!active) return;
   const DM& m = *dm;
-  const bool flat = m.terrain_type == 0;
   double* base64 = B.base_pos64 + size_t(env) * 3;
+  // "flat here": the scene is the floor plane alone, or the base is out of reach of every other terrain surface (the reference
+  // spawns robots over +-10 km in the stairs / ramp scenes).  Then the internal frame is re-centred on the base and the terrain
+  // colliders are skipped; near the terrain the frame is the world frame.
+  auto flat_at = [&](double x, double y) {
+    return m.terrain_type == 0 || x > double(m.terr_bounds[0]) || x < double(m.terr_bounds[1]) || y > double(m.terr_bounds[2]) || y < double(m.terr_bounds[3]);
+  };
+  bool flat;
+  syncwarp();  // the state rows written above are read across lanes
+  {
+    const double x0 = (MODE == MODE_RESET && given_state) ? double(w.qpos[0]) : base64[0];
+    const double y0 = (MODE == MODE_RESET && given_state) ? double(w.qpos[1]) : base64[1];
+    flat = flat_at(x0, y0);
+  }
+  syncwarp();
   if (lane < 2) {
-    // fp64 master copy of the base position; internal frame is re-centred on flat terrain (resets scatter envs over +-1e4 m)
+    // fp64 master copy of the base position (resets scatter envs over +-1e4 m)
     double x = (MODE == MODE_RESET && given_state) ? double(w.qpos[lane]) : base64[lane];
     if (MODE == MODE_RESET && given_state) base64[lane] = x;
     const double o = flat ? rint(x) : 0.0;
@@ -177,6 +190,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   Env<real, NCON, MAXDIM> e(m, w, reinterpret_cast<const Vert4<real>*>(p.vert), lane);
   e.hf = reinterpret_cast<const real*>(p.hf);
   e.boxes = reinterpret_cast<const DBox<real>*>(p.boxes);
+  e.terrain_on = !flat;
   const unsigned env_g = unsigned(env + p.env_id_offset);
   real command[4] = {real(B.command[4 * env]), real(B.command[4 * env + 1]), real(B.command[4 * env + 2]), real(B.command[4 * env + 3])};
   float sim_time = B.sim_time[env];
@@ -253,6 +267,8 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
           }
         }
         syncwarp();
+        flat = flat_at(bx, by);
+        e.terrain_on = !flat;
         if (lane == 0) {
           const double ox = flat ? rint(bx) : 0.0, oy = flat ? rint(by) : 0.0;
           w.org[0] = ox; w.org[1] = oy;
@@ -534,7 +550,9 @@ __global__ void __launch_bounds__(256) raycast_kernel(const KParams p) {
   e.boxes = reinterpret_cast<const DBox<real>*>(p.boxes);
   const double* b64 = p.b.base_pos64 + size_t(env) * 3;
   const float* qp = p.b.qpos + size_t(env) * NQ;
-  const bool flat = m.terrain_type == 0;
+  const bool flat = m.terrain_type == 0 || b64[0] > double(m.terr_bounds[0]) || b64[0] < double(m.terr_bounds[1]) ||
+                    b64[1] > double(m.terr_bounds[2]) || b64[1] < double(m.terr_bounds[3]);
+  e.terrain_on = !flat;
   const double ox = flat ? rint(b64[0]) : 0.0, oy = flat ? rint(b64[1]) : 0.0;
   real qq[4] = {real(qp[3]), real(qp[4]), real(qp[5]), real(qp[6])}, R[9];
   quat_normalize(qq);

@@ -5,6 +5,9 @@ Restates what `gym_quadruped/utils/mujoco/terrain.py:309-365` builds for the sce
 * ``flat``          -- the `floor` plane of scene_flat.xml:32, limits (1e4,-1e4,1e4,-1e4)            terrain.py:357-359
 * ``random_boxes``  -- floor + 10x10 randomly sized / tilted static boxes                             terrain.py:145-238,325-335
 * ``perlin``        -- floor + a 128x128 height field of 5-octave Perlin noise                        terrain.py:25-119,345-356
+* ``stairs``        -- floor + 50 static steps (robot_model/scene_stairs.xml:38-89), flat limits           terrain.py:319-321
+* ``ramp``          -- floor + one tilted slab (robot_model/scene_ramp.xml:37)                             terrain.py:319-321
+* ``random_pyramids`` -- floor + a stack of shrinking slabs                                            terrain.py:240-292,336-344
 
 All scenes are generated under the reference's fixed seed 10 (quadruped_env.py:155, terrain.py:299-306) with NumPy's
 legacy MT19937 stream, so every env instance of a robot sees the same terrain.  `random_boxes` is pinned bit-for-bit by
@@ -160,6 +163,59 @@ def perlin_heightfield(hip_height: float):
             'terrain_limits': (radius, -radius, radius, -radius)}
 
 
+def stairs_scene():
+    """robot_model/scene_stairs.xml: 50 steps of half size (0.05, 1.25, 0.025); the XML's positions are running sums (0.1 k + 1 and
+    0.05 k - 0.025, accumulated in double precision), reproduced here the same way and pinned by tests/golden/terrain_static.json."""
+    pos, lx, z = [], 0.0, -0.025
+    for _ in range(50):  # local x and z accumulate step by step; the stair case starts 1 m in front of the origin
+        lx += 0.1
+        z += 0.05
+        pos.append([lx + 1.0, 0.0, z])
+    n = len(pos)
+    return {'type': 'boxes', 'box_pos': np.array(pos), 'box_quat': np.tile([1.0, 0, 0, 0], (n, 1)),
+            'box_half': np.tile([0.05, 1.25, 0.025], (n, 1)), 'terrain_limits': FLAT_LIMITS}
+
+
+def ramp_scene():
+    """robot_model/scene_ramp.xml:37: one slab pitched by quat (1, 0, -0.2, 0) (normalised by the engine's compiler)."""
+    q = np.array([1.0, 0.0, -0.20, 0.0])
+    return {'type': 'boxes', 'box_pos': np.array([[0.5, 0.0, 0.025]]), 'box_quat': (q / np.linalg.norm(q))[None],
+            'box_half': np.array([[4.05, 1.25, 0.025]]), 'terrain_limits': FLAT_LIMITS}
+
+
+def world_of_pyramid(hip_height: float, seed: int = 10):
+    """terrain.py:336-344 -> add_world_of_pyramid(:240-292).  Draw order: stair_nums (an argument, drawn by the caller), then
+    height_rand, stride_rand."""
+    rng = np.random.RandomState(seed)
+    stair_nums = rng.uniform(2, 8, 1)
+    init_pos = [3.0, 0.0, 0.02]
+    width, max_height, length = 10 * hip_height, 5 * hip_height, 10 * hip_height
+    local_z = -0.05
+    height_rand = rng.uniform(0.08, max_height, 1)
+    stride_rand = rng.uniform(0.5, 1.0, 1)
+    pos, half = [], []
+    max_abs_x = max_abs_y = 0.0
+    center = (0.0, 0.0)
+    for i in range(int(stair_nums[0])):
+        local_z += height_rand[0]
+        new_width, new_length = width - stride_rand[0] * i, length - stride_rand[0] * i
+        if new_width < 0.3 or new_length < 0.3:
+            break
+        pos.append([0.0 + init_pos[0], 0.0 + init_pos[1], local_z])
+        half.append(0.5 * np.array([new_width, new_length, height_rand[0]]))
+        if i == 0:
+            max_abs_x = abs(init_pos[0] + new_width / 2.0)
+            max_abs_y = abs(init_pos[1] + new_length / 2.0)
+            center = (init_pos[0], init_pos[1])
+    if max_abs_x >= max_abs_y:
+        radius = 1.5 * np.sqrt(2 * (max_abs_x - center[0]) * (max_abs_x - center[0]))
+    else:
+        radius = 1.5 * np.sqrt(2 * (max_abs_y - center[1]) * (max_abs_y - center[1]))
+    n = len(pos)
+    return {'type': 'boxes', 'box_pos': np.array(pos), 'box_quat': np.tile([1.0, 0, 0, 0], (n, 1)), 'box_half': np.array(half),
+            'terrain_limits': (center[0] + radius, center[0] - radius, center[1] + radius, center[1] - radius)}
+
+
 def generate_terrain(scene: str, hip_height: float, seed: int = 10) -> dict:
     if scene == 'flat':
         return {'type': 'flat', 'terrain_limits': FLAT_LIMITS}
@@ -167,5 +223,11 @@ def generate_terrain(scene: str, hip_height: float, seed: int = 10) -> dict:
         return world_of_boxes(hip_height, seed)
     if scene == 'perlin':
         return perlin_heightfield(hip_height)
-    raise ValueError(f'Invalid scene name: {scene}, available are: flat, random_boxes, perlin '
-                     f'(random_pyramids, stairs, ramp, slippery are not built yet)')
+    if scene == 'stairs':
+        return stairs_scene()
+    if scene == 'ramp':
+        return ramp_scene()
+    if scene == 'random_pyramids':
+        return world_of_pyramid(hip_height, seed)
+    raise ValueError(f'Invalid scene name: {scene}, available are: flat, random_boxes, random_pyramids, perlin, stairs, ramp '
+                     f'(slippery needs per-surface friction priorities and is not built yet)')

@@ -36,3 +36,25 @@ for robot, hip in (('mini_cheetah', 0.225), ('aliengo', 0.35), ('go2', 0.28), ('
            'quat': [[float(x) for x in g.attrib['quat'].split()] for g in boxes]}
     (out_dir / f'terrain_boxes_{robot}.json').write_text(json.dumps(rec))
     print(robot, len(boxes), limits)
+
+
+# static XML scenes (stairs, ramp) and the procedural pyramid stack -> tests/golden/terrain_static.json
+def _boxes_of(scene):
+    geoms = scene.getroot().find('worldbody').findall('geom')
+    boxes = [g for g in geoms if g.attrib.get('type') == 'box']
+    return {'pos': [[float(x) for x in g.attrib['pos'].split()] for g in boxes],
+            'half': [[float(x) for x in g.attrib['size'].split()] for g in boxes],
+            'quat': [[float(x) for x in g.attrib.get('quat', '1 0 0 0').split()] for g in boxes]}
+
+
+static = {}
+for name in ('stairs', 'ramp'):
+    scene, limits = ref_terrain.generate_terrain(Path(f'/root/reference/gym_quadruped/robot_model/scene_{name}.xml'), REF / 'assets',
+                                                 0.35, name, seed=10)
+    static[name] = dict(_boxes_of(scene), terrain_limits=[float(x) for x in limits])
+for robot, hip in (('mini_cheetah', 0.225), ('aliengo', 0.35), ('go2', 0.28), ('hyqreal1', 0.498)):
+    scene, limits = ref_terrain.generate_terrain(Path('/nonexistent/scene_random_pyramids.xml'), REF / 'assets', hip,
+                                                 'random_pyramids', seed=10)
+    static[f'random_pyramids_{robot}'] = dict(_boxes_of(scene), terrain_limits=[float(x) for x in limits], hip_height=hip)
+(out_dir / 'terrain_static.json').write_text(json.dumps(static))
+print({k: len(v['pos']) for k, v in static.items()})

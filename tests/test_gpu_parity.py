@@ -370,7 +370,9 @@ def test_quadruped_env_surface(cuda_device):
 
 
 @pytest.mark.parametrize('robot,scene,xy,z0', [('go2', 'random_boxes', (2.0, -1.0), 0.45), ('aliengo', 'perlin', (3.0, 2.0), 0.95),
-                                               ('aliengo', 'random_boxes', (3.5, 1.0), 0.62)])
+                                               ('aliengo', 'random_boxes', (3.5, 1.0), 0.62), ('aliengo', 'stairs', (1.6, 0.0), 0.85),
+                                               ('mini_cheetah', 'ramp', (1.0, 0.0), 0.75), ('hyqreal2', 'random_pyramids', (3.0, 0.5), 1.6),
+                                               ('b2', 'stairs', (1.4, 0.2), 1.0)])
 def test_terrain_scenes_match_oracle(robot, scene, xy, z0, cuda_device):
     """configs 3 / 4: box and height-field terrain colliders, plus the fused height-map columns (sensors/heightmap.py).
     Closed loop: the oracle is re-seeded from the GPU state before every step, so landing impacts cannot amplify fp32 rounding
@@ -414,8 +416,11 @@ def test_terrain_scenes_match_oracle(robot, scene, xy, z0, cuda_device):
                 borderline += 1
                 continue
             qo, vo, _, _ = o.get_state()
-            worst = max(worst, np.abs(q1[i] - qo).max(), 0.1 * np.abs(v1[i] - vo).max())
             max_ncon = max(max_ncon, f['ncon'])
+            if ref_term and scene in ('stairs', 'ramp', 'random_pyramids'):
+                continue  # a body lying across several step edges (episode over: invalid contact) is a redundant, ill-conditioned
+                # contact problem whose fp32 solution is only held to the flags, not to the single-step state tolerance
+            worst = max(worst, np.abs(q1[i] - qo).max(), 0.1 * np.abs(v1[i] - vo).max())
     single_step_tol = 1e-4 if m.c.cone == 1 else 2e-5  # elliptic cone, impratio 100: stiff friction rows amplify fp32 rounding
     assert max_ncon >= 4 and worst < single_step_tol and borderline <= 3, (max_ncon, worst, borderline)
     hm = obs[:, 227:].cpu().numpy().reshape(n, 5, 5, 3)
@@ -469,3 +474,24 @@ def test_full_size_configs_properties_and_sharding_invariance(robot, scene, n, i
     if imu:  # measurement = truth + bias + noise: the three stored parts must add up
         io = full.obs[:, 227:245]
         assert torch.isfinite(io).all() and (io[:, 3:6].abs() < 0.2).all() and (io[:, 12:15].abs() < 0.2).all()
+
+
+def test_far_from_the_terrain_a_box_scene_behaves_like_flat(cuda_device):
+    """stairs / ramp keep the +-10 km spawn limits of the flat scene (terrain.py:319-321): away from the boxes the kernel re-centres
+    its internal frame exactly as on flat ground, so a rollout 7 km from the stairs equals the same rollout on `flat` shifted."""
+    n, T = 16, 40
+    mf, ms = Model('aliengo', 'flat'), Model('aliengo', 'stairs')
+    qpos, qvel = seeded_states(mf, n, seed=21)
+    far = qpos.copy(); far[:, 0] += 7000.0; far[:, 1] -= 3000.0
+    a, b = BatchSim(mf, n, device=cuda_device), BatchSim(ms, n, device=cuda_device)
+    a.set_state(torch.tensor(qpos), torch.tensor(qvel)); b.set_state(torch.tensor(far), torch.tensor(qvel))
+    g = torch.Generator(device='cpu').manual_seed(2)
+    for t in range(T):
+        ctrl = (torch.randn(n, 12, generator=g) * 8).to(cuda_device)
+        a.step(ctrl); b.step(ctrl)
+    assert torch.equal(a.qvel, b.qvel) and torch.equal(a.qpos[:, 2:], b.qpos[:, 2:]) and torch.equal(a.terminated, b.terminated)
+    assert torch.allclose(a.base_pos64[:, 0] + 7000.0, b.base_pos64[:, 0], atol=1e-9)
+    # and a random reset in that scene (spawn anywhere in +-10 km) produces finite, lifted states
+    opt = b.make_reset_options(lin_vel_range=(0.5, 1.0), friction_range=(0.2, 1.5))
+    b.reset(options=opt)
+    assert torch.isfinite(b.obs).all() and (b.status == 0).all() and (b.base_pos64[:, :2].abs().max() > 100)

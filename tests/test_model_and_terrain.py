@@ -32,7 +32,21 @@ def test_flat_and_perlin_scene_tables():
     assert (img.min(), img.max()) == (64, 195) and list(img[0, :6]) == [127, 136, 129, 135, 143, 143]
     assert list(img[64, 60:66]) == [158, 152, 152, 159, 164, 177]
     with pytest.raises(ValueError):
-        generate_terrain('stairs', 0.3)
+        generate_terrain('slippery', 0.3)
+
+
+@pytest.mark.parametrize('key,scene,hip', [('stairs', 'stairs', 0.35), ('ramp', 'ramp', 0.35), ('random_pyramids_mini_cheetah', 'random_pyramids', 0.225),
+                                           ('random_pyramids_aliengo', 'random_pyramids', 0.35), ('random_pyramids_go2', 'random_pyramids', 0.28),
+                                           ('random_pyramids_hyqreal1', 'random_pyramids', 0.498)])
+def test_static_box_scenes_against_reference_generator(key, scene, hip):
+    """stairs / ramp (the reference's XML scenes) and random_pyramids (its generator run here) -> tests/golden/terrain_static.json."""
+    g = json.loads((GOLDEN / 'terrain_static.json').read_text())[key]
+    t = generate_terrain(scene, hip)
+    assert t['type'] == 'boxes' and len(t['box_pos']) == len(g['pos']) > 0
+    assert np.array_equal(t['box_pos'], np.array(g['pos'])) and np.array_equal(t['box_half'], np.array(g['half']))
+    q = np.array(g['quat'])
+    np.testing.assert_allclose(t['box_quat'], q / np.linalg.norm(q, axis=1, keepdims=True), atol=1e-15)
+    assert tuple(float(x) for x in t['terrain_limits']) == tuple(g['terrain_limits'])
 
 
 def test_model_constants_from_the_mjcf():
