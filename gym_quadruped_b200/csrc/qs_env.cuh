@@ -1309,6 +1309,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   //   refinement with Newton steps from both ends plus the midpoint.
   QS_DEV real line_search(real gtol, real qg0, real qg1, real qg2, real cost0, real slope0) {
     constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);
+    constexpr real kNoiseCost = sizeof(real) == 4 ? real(1e-7) : real(1e-15);
     int state = 1, it = 0, dir = 1, ci = 3;
     LsPoint p0{}, p1{}, p2{}, lo{}, hi{};
     // The point alpha = 0 needs no evaluation: its cost is the current cost, its slope is grad . search and, because the search
@@ -1339,6 +1340,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         if (N::abs(p.d1) < gtol) return p.alpha;
         if ((p.d1 < 0) == (lo.d1 < 0)) lo = p; else hi = p;
         moved = true;
+        // precision-aware stop: once the two ends of the bracket cost the same to ~2 ulp, bisecting further only chases the
+        // rounding noise of the derivative (measured in fp32: tails of 20-50 evaluations that do not change the result)
+        if (N::abs(lo.cost - hi.cost) <= kNoiseCost * (N::abs(lo.cost) + N::abs(hi.cost))) return lo.cost < hi.cost ? lo.alpha : hi.alpha;
       }
       if (state == 2) {
         if (p1.d1 * dir <= -gtol && it < ls_iter) { a = p1.alpha - N::div(p1.d1, p1.d2); continue; }

@@ -4,7 +4,8 @@ import numpy as np, torch
 from gym_quadruped_b200.backend import BatchSim
 from gym_quadruped_b200.model import Model
 import bench
-model = Model('mini_cheetah', 'flat'); n=4096
+import os
+model = Model(os.environ.get('QS_ROBOT', 'mini_cheetah'), 'flat'); n=4096
 sim = BatchSim(model, n, device=0); opt = sim.make_reset_options(**bench.RESET_KW); sim.reset(options=opt)
 prof = torch.zeros(n * 32, dtype=torch.int32, device='cuda')
 sim.L.qs_debug_set_prof.argtypes = [C.c_void_p, C.c_void_p]
