@@ -1169,7 +1169,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     return cost;
   }
 
-  // states / forces / weights at the current residuals (w.u_r, w.c_r); returns the constraint cost (warp-uniform)
+  // states / forces / weights at the current residuals (w.u_r, w.c_r); returns this lane's share of the constraint cost
   QS_DEV real units_update() {
     real cost = 0;
     if (lane < NFL + NLIM) {
@@ -1188,9 +1188,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
     const int ncon = w.ncon;
     for (int c = lane; c < ncon; c += 32) cost += contact_unit_update(c);
-    cost = warp_sum(cost);
     syncwarp();
-    return cost;
+    return cost;  // per-lane partial: the caller reduces it together with its other sums
   }
 
   // qfrc_constraint = J^T F (into w.fcon) and grad = Ma - fsm - fcon; dof lanes
@@ -1297,9 +1296,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
     LsPoint p;
     p.alpha = alpha;
-    p.cost = warp_sum(cost) + alpha * alpha * qg2 + alpha * qg1 + qg0;
-    p.d1 = warp_sum(d1) + 2 * alpha * qg2 + qg1;
-    p.d2 = warp_sum(d2) + 2 * qg2;
+    warp_sum3(cost, d1, d2);
+    p.cost = cost + alpha * alpha * qg2 + alpha * qg1 + qg0;
+    p.d1 = d1 + 2 * alpha * qg2 + qg1;
+    p.d2 = d2 + 2 * qg2;
     return p;
   }
 
@@ -1309,7 +1309,6 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   //   refinement with Newton steps from both ends plus the midpoint.
   QS_DEV real line_search(real gtol, real qg0, real qg1, real qg2, real cost0, real slope0) {
     constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);
-    constexpr real kNoiseCost = sizeof(real) == 4 ? real(1e-7) : real(1e-15);
     int state = 1, it = 0, dir = 1, ci = 3;
     LsPoint p0{}, p1{}, p2{}, lo{}, hi{};
     // The point alpha = 0 needs no evaluation: its cost is the current cost, its slope is grad . search and, because the search
@@ -1340,9 +1339,6 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         if (N::abs(p.d1) < gtol) return p.alpha;
         if ((p.d1 < 0) == (lo.d1 < 0)) lo = p; else hi = p;
         moved = true;
-        // precision-aware stop: once the two ends of the bracket cost the same to ~2 ulp, bisecting further only chases the
-        // rounding noise of the derivative (measured in fp32: tails of 20-50 evaluations that do not change the result)
-        if (N::abs(lo.cost - hi.cost) <= kNoiseCost * (N::abs(lo.cost) + N::abs(hi.cost))) return lo.cost < hi.cost ? lo.alpha : hi.alpha;
       }
       if (state == 2) {
         if (p1.d1 * dir <= -gtol && it < ls_iter) { a = p1.alpha - N::div(p1.d1, p1.d2); continue; }
@@ -1395,8 +1391,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     QS_TACC(0);
     while (true) {
       // cost, forces, gradient at the current point
-      const real ccost = units_update();
-      const real gauss = warp_sum((lane < NV) ? real(0.5) * (w.Ma[lane] - w.fsm[lane]) * (w.qacc[lane] - w.asmooth[lane]) : real(0));
+      real ccost = units_update();
+      const int dl_ = lane < NV ? lane : 0;
+      real gauss = (lane < NV) ? real(0.5) * (w.Ma[dl_] - w.fsm[dl_]) * (w.qacc[dl_] - w.asmooth[dl_]) : real(0);
+      warp_sum2(ccost, gauss);
       oldcost = cost;
       cost = gauss + ccost;
       constraint_force_and_grad();
@@ -1406,8 +1404,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         // loop alive with ~50% probability per iteration.
         constexpr real kNoise = sizeof(real) == 4 ? real(1e-6) : real(1e-14);    // ~16 ulp: force-balance residual floor
         constexpr real kNoiseCost = sizeof(real) == 4 ? real(1e-7) : real(1e-15);  // ~2 ulp: cost did not move at all
-        const real gn2 = warp_sum((lane < NV) ? w.grad[lane] * w.grad[lane] : real(0));
-        const real fn2 = warp_sum((lane < NV) ? w.Ma[lane] * w.Ma[lane] + w.fsm[lane] * w.fsm[lane] + w.fcon[lane] * w.fcon[lane] : real(0));
+        real gn2 = (lane < NV) ? w.grad[dl_] * w.grad[dl_] : real(0);
+        real fn2 = (lane < NV) ? w.Ma[dl_] * w.Ma[dl_] + w.fsm[dl_] * w.fsm[dl_] + w.fcon[dl_] * w.fcon[dl_] : real(0);
+        warp_sum2(gn2, fn2);
         const real imp = oldcost - cost;
 #ifdef QS_PROF_IMP
         if (iter <= 8) tacc[iter - 1] = __float_as_uint(float(scale * imp));
@@ -1435,15 +1434,15 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       QS_TACC(4);
 #endif
       // exact line search
-      const real snorm = N::sqrt(warp_sum((lane < NV) ? w.search[lane] * w.search[lane] : real(0)));
-      if (snorm < N::minval) break;
-      const real gtol = tol * m.ls_tolerance * snorm / scale;
       const real mv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.search);
       if (lane < NV) w.Mv[lane] = mv;
       units_Jx(w.search, w.u_v, w.c_v, false);
-      const real qg1 = warp_sum((lane < NV) ? w.search[lane] * (w.Ma[lane] - w.fsm[lane]) : real(0));
-      const real qg2 = warp_sum((lane < NV) ? real(0.5) * w.search[lane] * mv : real(0));
-      const real slope0 = warp_sum((lane < NV) ? w.grad[lane] * w.search[lane] : real(0));
+      const real sd = (lane < NV) ? w.search[dl_] : real(0);
+      real sn2 = sd * sd, qg1 = sd * (w.Ma[dl_] - w.fsm[dl_]), qg2 = real(0.5) * sd * mv, slope0 = w.grad[dl_] * sd;
+      warp_sum4(sn2, qg1, qg2, slope0);
+      const real snorm = N::sqrt(sn2);
+      if (snorm < N::minval) break;
+      const real gtol = tol * m.ls_tolerance * snorm / scale;
       QS_TACC(5);
       const real alpha = line_search(gtol, gauss, qg1, qg2, cost, slope0);
       QS_TACC(6);
@@ -1561,65 +1560,78 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     quat_normalize(q);
     quat_to_mat(R, q);
     const real yaw = N::atan2(R[3], R[0]);
-    real sy, cy;
-    N::sincos(yaw, &sy, &cy);
+    // cos / sin of yaw = atan2(R10, R00) without trigonometry (heading frame of :990-997)
+    const real h2 = R[0] * R[0] + R[3] * R[3];
+    const real hinv = h2 > N::minval ? N::rsqrt(h2) : real(0);
+    const real cy = h2 > N::minval ? R[0] * hinv : real(1), sy = R[3] * hinv;
     const real vref[3] = {cy * command[0] - sy * command[1], sy * command[0] + cy * command[1], command[2]};
-    const real wref[3] = {0, 0, command[3]};
     const real* v = w.qvel;
     const real* wb = w.qvel + 3;
     real* o = w.obs;
     const real ox = real(w.org[0]), oy = real(w.org[1]);
     // kinetic energy / work first: they need nothing from the recycled region
     const real mvv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qvel), maa = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
-    const real ke = warp_sum((lane < NV) ? real(0.5) * w.qvel[lane] * mvv : real(0));
-    const real wk = warp_sum((lane < NV) ? maa * w.qvel[lane] : real(0));
+    const int dl_ = lane < NV ? lane : 0;
+    real ke = (lane < NV) ? real(0.5) * w.qvel[dl_] * mvv : real(0), wk = (lane < NV) ? maa * w.qvel[dl_] : real(0);
+    warp_sum2(ke, wk);
+    // spatial velocity of each calf body with the post-step qvel (feet_vel = J qvel, :652-664): lanes (leg, component), parked in the
+    // IMU scratch (consumed by sensors() earlier in the step)
+    if (lane < 24) {
+      const int l = (tri >> 20) & 7, i = (tri >> 23) & 7;
+      real sv = 0;
+      for (int d = 0; d < 6; d++) sv += w.cdof[d][i] * w.qvel[d];
+      for (int k = 0; k < 3; k++) { const int d = 6 + 3 * l + k; sv += w.cdof[d][i] * w.qvel[d]; }
+      w.sens_tmp[lane] = sv;
+    }
     syncwarp();
-    if (lane == 0) {
-      real t[3], t2[3];
-      o[0] = real(w.org[0] + double(w.qpos[0])); o[1] = real(w.org[1] + double(w.qpos[1])); o[2] = w.qpos[2];
-      for (int i = 0; i < 3; i++) { o[3 + i] = v[i]; o[6 + i] = vref[i] - v[i]; o[9 + i] = w.qacc[i]; }
-      mul_mv(t, R, wb);
-      for (int i = 0; i < 3; i++) { o[12 + i] = t[i]; o[15 + i] = wref[i] - t[i]; }
-      o[18] = N::atan2(R[7], R[8]); o[19] = -N::asin(N::max(real(-1), N::min(real(1), R[6]))); o[20] = yaw;
+    // base block: lane i < 3 owns component i of every 3-vector (rows / columns of R picked without indexing the register array)
+    if (lane < 3) {
+      const int i = lane;
+      const real Ri0 = i == 0 ? R[0] : (i == 1 ? R[3] : R[6]), Ri1 = i == 0 ? R[1] : (i == 1 ? R[4] : R[7]), Ri2 = i == 0 ? R[2] : (i == 1 ? R[5] : R[8]);
+      const real Ci0 = i == 0 ? R[0] : (i == 1 ? R[1] : R[2]), Ci1 = i == 0 ? R[3] : (i == 1 ? R[4] : R[5]), Ci2 = i == 0 ? R[6] : (i == 1 ? R[7] : R[8]);
+      const real vi = v[i], wbi = wb[i], vrefi = i == 0 ? vref[0] : (i == 1 ? vref[1] : vref[2]), wrefi = i == 2 ? command[3] : real(0);
+      const real Rwb = Ri0 * wb[0] + Ri1 * wb[1] + Ri2 * wb[2];
+      o[i] = i < 2 ? real(w.org[i] + double(w.qpos[i])) : w.qpos[2];
+      o[3 + i] = vi; o[6 + i] = vrefi - vi; o[9 + i] = w.qacc[i];
+      o[12 + i] = Rwb; o[15 + i] = wrefi - Rwb;
+      o[18 + i] = i == 0 ? N::atan2(R[7], R[8]) : (i == 1 ? -N::asin(N::max(real(-1), N::min(real(1), R[6]))) : yaw);
+      o[25 + 3 * i] = Ri0; o[26 + 3 * i] = Ri1; o[27 + 3 * i] = Ri2;
+      o[34 + i] = -Ci2;
+      const real RTv = Ci0 * v[0] + Ci1 * v[1] + Ci2 * v[2], RTvref = Ci0 * vref[0] + Ci1 * vref[1] + Ci2 * vref[2];
+      o[37 + i] = RTv; o[40 + i] = RTvref - RTv;
+      o[43 + i] = Ci0 * w.qacc[0] + Ci1 * w.qacc[1] + Ci2 * w.qacc[2];
+      o[46 + i] = wbi;
+      o[49 + i] = (Ci0 * real(0) + Ci1 * real(0) + Ci2 * command[3]) - wbi;
+    } else if (lane == 3) {
       for (int i = 0; i < 4; i++) o[21 + i] = w.qpos[3 + i];
-      for (int i = 0; i < 9; i++) o[25 + i] = R[i];
-      o[34] = -R[6]; o[35] = -R[7]; o[36] = -R[8];
-      mul_mtv(t, R, v);
-      mul_mtv(t2, R, vref);
-      for (int i = 0; i < 3; i++) { o[37 + i] = t[i]; o[40 + i] = t2[i] - t[i]; }
-      mul_mtv(t, R, w.qacc);
-      for (int i = 0; i < 3; i++) { o[43 + i] = t[i]; o[46 + i] = wb[i]; }
-      mul_mtv(t, R, wref);
-      for (int i = 0; i < 3; i++) o[49 + i] = t[i] - wb[i];
       o[125] = ke; o[126] = wk;
     }
     if (lane < NQ) o[52 + lane] = (lane < 2) ? real(w.org[lane] + double(w.qpos[lane])) : w.qpos[lane];
     if (lane < NV) o[71 + lane] = w.qvel[lane];
     if (lane < NU) { o[89 + lane] = w.ctrl[lane]; o[101 + lane] = w.qpos[7 + lane]; o[113 + lane] = w.qvel[6 + lane]; }
-    if (lane >= 4 && lane < 8) {
-      const int l = lane - 4;
-      real cv6[6] = {0, 0, 0, 0, 0, 0};
-      for (int d = 0; d < 6; d++) for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d];
-      for (int k = 0; k < 3; k++) { const int d = 6 + 3 * l + k; for (int i = 0; i < 6; i++) cv6[i] += w.cdof[d][i] * w.qvel[d]; }
+    // feet block: lane (leg l, component c) on the dof lanes 6..17
+    if (lane >= 6 && lane < NV) {
+      const int l = dof_leg(), c = dof_k();
+      const real* cv6 = w.sens_tmp + 6 * l;
       const real* p = w.footpos[l];
       const real off[3] = {p[0] - w.com[0], p[1] - w.com[1], p[2] - w.com[2]};
-      real cr[3], fv[3], fr[3], t[3];
+      real cr[3], fv[3], fr[3];
       cross3(cr, cv6, off);
       for (int i = 0; i < 3; i++) fv[i] = cv6[3 + i] + cr[i];
       const real rb[3] = {p[0] - w.qpos[0], p[1] - w.qpos[1], p[2] - w.qpos[2]};
       cross3(cr, wb, rb);
       for (int i = 0; i < 3; i++) fr[i] = fv[i] - v[i] - cr[i];
-      o[127 + 3 * l] = p[0] + ox; o[128 + 3 * l] = p[1] + oy; o[129 + 3 * l] = p[2];
-      mul_mtv(t, R, rb);
-      for (int i = 0; i < 3; i++) { o[139 + 3 * l + i] = t[i]; o[151 + 3 * l + i] = fv[i]; o[163 + 3 * l + i] = fr[i]; }
-      mul_mtv(t, R, fv);
-      for (int i = 0; i < 3; i++) o[175 + 3 * l + i] = t[i];
-      mul_mtv(t, R, fr);
-      for (int i = 0; i < 3; i++) o[187 + 3 * l + i] = t[i];
-      o[199 + l] = (contact_mask >> l) & 1u ? real(1) : real(0);
-    }
-    if (lane >= 8 && lane < 12) {
-      const int l = lane - 8;
+      const real Cc0 = c == 0 ? R[0] : (c == 1 ? R[1] : R[2]), Cc1 = c == 0 ? R[3] : (c == 1 ? R[4] : R[5]), Cc2 = c == 0 ? R[6] : (c == 1 ? R[7] : R[8]);
+      const int k = 3 * l + c;
+      o[127 + k] = p[c] + (c == 0 ? ox : (c == 1 ? oy : real(0)));
+      o[139 + k] = Cc0 * rb[0] + Cc1 * rb[1] + Cc2 * rb[2];
+      o[151 + k] = c == 0 ? fv[0] : (c == 1 ? fv[1] : fv[2]);
+      o[163 + k] = c == 0 ? fr[0] : (c == 1 ? fr[1] : fr[2]);
+      o[175 + k] = Cc0 * fv[0] + Cc1 * fv[1] + Cc2 * fv[2];
+      o[187 + k] = Cc0 * fr[0] + Cc1 * fr[1] + Cc2 * fr[2];
+      if (c == 0) o[199 + l] = (contact_mask >> l) & 1u ? real(1) : real(0);
+    } else if (lane >= 18 && lane < 22) {
+      const int l = lane - 18;
       real cf[3] = {0, 0, 0}, t[3];
       for (int c = 0; c < w.ncon; c++) {
         const int info = w.c_info[c];

@@ -135,6 +135,22 @@ template <typename T> QS_DEV T warp_sum(T v) {
   for (int o = 16; o > 0; o >>= 1) v += shfl_xor(v, o);
   return v;
 }
+// several independent butterfly sums interleaved: same result per value as warp_sum, one dependent chain instead of k
+template <typename T> QS_DEV void warp_sum2(T& a, T& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const T ta = shfl_xor(a, o), tb = shfl_xor(b, o); a += ta; b += tb; }
+}
+template <typename T> QS_DEV void warp_sum3(T& a, T& b, T& c) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const T ta = shfl_xor(a, o), tb = shfl_xor(b, o), tc = shfl_xor(c, o); a += ta; b += tb; c += tc; }
+}
+template <typename T> QS_DEV void warp_sum4(T& a, T& b, T& c, T& d) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T ta = shfl_xor(a, o), tb = shfl_xor(b, o), tc = shfl_xor(c, o), td = shfl_xor(d, o);
+    a += ta; b += tb; c += tc; d += td;
+  }
+}
 template <typename T> QS_DEV T warp_max(T v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { T w = shfl_xor(v, o); v = w > v ? w : v; }
