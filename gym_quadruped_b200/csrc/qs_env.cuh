@@ -16,7 +16,7 @@
 
 namespace qs {
 
-constexpr int NB = 14, NJ = 12, NQ = 19, NV = 18, NU = 12, MAXGEOM = 40;
+constexpr int NB = 14, NJ = 12, NQ = 19, NV = 18, NU = 12, MAXGEOM = 48;
 constexpr int NOBS_BASE = 227;
 constexpr int NFL = 12;   // friction-loss units (one per hinge)
 constexpr int NLIM = 12;  // joint-limit units (one slot per hinge; lower and upper cannot be active together)
@@ -651,7 +651,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // Primitive robot geoms against the perlin height field / the static boxes, as feature points (sphere centre + radius, capsule
   // end spheres, box corners) -- exact for sphere-box and plane-like cases, an approximation of the engine's capsule-box,
   // box-box and prism-based hfield routines otherwise (documented in DESIGN.md).  Appends after the floor contacts.
-  QS_DEV void collide_terrain(int& ncon) {
+  QS_DEV void collide_terrain(int& ncon, const int gbase) {
     unsigned boxmask[4] = {0, 0, 0, 0};
     if (m.terrain_type == 2) {
       for (int wd = 0; wd < 4; wd++) {
@@ -667,7 +667,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
     Cand list[4];
     int n = 0;
-    const int g = lane;
+    const int g = gbase + lane;
     real yh[3] = {0, 0, 0};
     bool is_caps = false;
     if (geom_on(g) && m.geom_type[g] != GEOM_MESH) {
@@ -780,10 +780,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
   QS_DEV void collide_floor() {
     int ncon = 0;
+    // one lane per geom; robots with more than 32 collision geoms (go1: 42) take a second round
+#pragma unroll 1
+    for (int gbase = 0; gbase < m.ngeom; gbase += 32) collide_round(gbase, ncon);
+    if (lane == 0) { w.overflow = ncon > NCON; w.ncon = ncon > NCON ? NCON : ncon; }
+    syncwarp();
+  }
+  QS_DEV void collide_round(const int gbase, int& ncon) {
     // primitives: one lane per geom, up to 4 candidate contacts each
     real cd[4], cp[4][3], yh[3] = {0, 0, 0};
     int nc = 0;
-    const int g = lane;
+    const int g = gbase + lane;
     if (geom_on(g) && m.geom_type[g] != GEOM_MESH) {
       const int b = m.geom_body[g];
       real gx[3], tmp[3];
@@ -866,7 +873,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       ncon += popc(mask);
     }
-    if (m.terrain_type != 0 && terrain_on) collide_terrain(ncon);
+    if (m.terrain_type != 0 && terrain_on) collide_terrain(ncon, gbase);
     // convex meshes. Broad phase: lanes test the body-frame bounding box of every mesh against the plane (a lower bound of the
     // hull's lowest point, tight for long thin links); only the survivors are scanned, by the whole warp, for their support vertex.
     unsigned cand;
@@ -882,7 +889,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       cand = ballot(near);
     }
     while (cand) {
-      const int gm_ = ctz(cand);
+      const int gm_ = gbase + ctz(cand);
       cand &= cand - 1;
       const int b = m.geom_body[gm_];
       const real margin = m.geom_margin[gm_];
@@ -913,8 +920,6 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       ncon++;
     }
-    if (lane == 0) { w.overflow = ncon > NCON; w.ncon = ncon > NCON ? NCON : ncon; }
-    syncwarp();
   }
 
   // ------------------------------------------------------------------ constraint construction

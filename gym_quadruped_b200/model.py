@@ -17,9 +17,9 @@ from .terrain import generate_terrain
 
 ASSET_DIR = Path(__file__).resolve().parent / 'assets'
 
-QS_ABI_VERSION = 3
+QS_ABI_VERSION = 4
 QS_NBODY, QS_NJNT, QS_NQ, QS_NV, QS_NU, QS_NLEG = 14, 12, 19, 18, 12, 4
-QS_MAXGEOM, QS_MAXBOX = 40, 128
+QS_MAXGEOM, QS_MAXBOX = 48, 128
 QS_NOBS_BASE, QS_NOBS_IMU = 227, 18
 QS_CONTACT_STRIDE = 20
 

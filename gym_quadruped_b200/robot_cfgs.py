@@ -30,9 +30,8 @@ class RobotConfig:
     tables: str = ''  # name of the compiled table set under gym_quadruped_b200/assets
 
 
-# go1: 42 collision geoms exceed the kernel's one-lane-per-geom collision stage (32); spot: implicitfast integrator and contact
-# excludes; pegasus: no MJCF in the reference checkout
-_NOT_BUILT = {'go1': 0.3, 'spot': 0.46, 'pegasus': 0.5}
+# spot: implicitfast integrator and contact excludes; pegasus: no MJCF in the reference checkout
+_NOT_BUILT = {'spot': 0.46, 'pegasus': 0.5}
 
 
 def get_robot_config(robot_name: str) -> RobotConfig:
@@ -40,6 +39,8 @@ def get_robot_config(robot_name: str) -> RobotConfig:
     if 'mini_cheetah' in name:
         return RobotConfig('mini_cheetah/mini_cheetah.xml', 0.225, qpos0_js=[0, -np.pi / 2, 0] * 2 + [0, np.pi / 2, 0] * 2,
                            tables='mini_cheetah')
+    if name == 'go1':
+        return RobotConfig('go1/go1.xml', 0.3, tables='go1')
     if name == 'go2':
         return RobotConfig('go2/go2.xml', 0.28, tables='go2')
     if name == 'aliengo':

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 3
+#define QS_ABI_VERSION 4
 
 /* ---- fixed topology of every robot in robot_cfgs.py: ----
  * world -> base(free joint) -> 4 x {hip, thigh, calf} (one hinge each)           */
@@ -42,7 +42,7 @@ extern "C" {
 #define QS_NV 18
 #define QS_NU 12
 #define QS_NLEG 4
-#define QS_MAXGEOM 40  /* robot collision geoms (go2: 31)                           */
+#define QS_MAXGEOM 48  /* robot collision geoms (go2: 31, go1: 42)                  */
 #define QS_MAXBOX 128  /* static boxes of the random_boxes scene (terrain.py:145)   */
 #define QS_NOBS_BASE 227 /* ALL_OBS, quadruped_env.py:35-81                          */
 #define QS_NOBS_IMU 18   /* sensors/imu.py:16-17                                     */

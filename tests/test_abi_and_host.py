@@ -36,7 +36,7 @@ def test_library_loads_and_struct_sizes_agree():
     from gym_quadruped_b200 import backend
     from gym_quadruped_b200.model import QsBuffers, QsConfig, QsModel
     L = backend.load_library()  # dlopen only: no CUDA call is made without a GPU
-    assert L.qs_abi_version() == 3
+    assert L.qs_abi_version() == 4
     assert L.qs_model_sizeof() == ctypes.sizeof(QsModel) and L.qs_config_sizeof() == ctypes.sizeof(QsConfig)
     assert L.qs_buffers_sizeof() == ctypes.sizeof(QsBuffers)
     cfg = QsConfig(); cfg.use_imu = 1
@@ -92,7 +92,8 @@ def test_command_modes_robot_cfgs_and_action_space():
     with pytest.raises(ValueError):
         get_robot_config('hyqreal')
     with pytest.raises(NotImplementedError):
-        get_robot_config('go1')
+        get_robot_config('spot')
+    assert [get_robot_config(r).tables for r in ('b2', 'go1', 'go2', 'hyqreal2', 'aliengo')] == ['b2', 'go1', 'go2', 'hyqreal2', 'aliengo']
     box = Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
     s = box.sample()
     assert s.shape == (12,) and s.dtype == np.float32 and np.abs(s).max() < 10  # unbounded Box samples N(0,1) (App. B.6)

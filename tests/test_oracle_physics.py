@@ -7,9 +7,9 @@ from scipy.spatial.transform import Rotation
 from gym_quadruped_b200.model import Model
 from oracle.oracle import F_CONTACTS, F_EFC, F_FEET_JACP, F_FEET_POS, F_M, F_XPOS, Oracle
 
-ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2']
+ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2', 'go1']
 MASS = {'mini_cheetah': 12.473, 'aliengo': 24.638, 'go2': 15.206, 'hyqreal1': 107.573,
-        'hyqreal2': 126.694, 'b2': 83.498}  # sum of the <inertial mass=...> attributes of hyqreal2.xml / b2.xml
+        'hyqreal2': 126.694, 'b2': 83.498, 'go1': 12.743}  # sum of the <inertial mass=...> attributes of hyqreal2.xml / b2.xml
 
 
 def _airborne(model, rng, z=2.0):
