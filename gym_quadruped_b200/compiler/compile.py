@@ -29,6 +29,7 @@ ROBOTS = {
     'hyqreal2': ('hyqreal2/hyqreal2.xml', 0.498, None),   # joint-level actuatorfrcrange clamps
     'go1': ('go1/go1.xml', 0.3, None),                    # fromto capsules, cylinders, condim-6 priority feet
     'b2': ('b2/b2.xml', 0.485, None),                     # cylinders
+    'spot': ('spot/spot.xml', 0.46, None),                # implicitfast (== Euler + implicit damping here), OBJ hulls, contact excludes
 }
 
 

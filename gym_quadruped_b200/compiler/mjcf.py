@@ -156,7 +156,9 @@ def parse_robot(xml_path: str | Path) -> dict:
         'impratio': float(opt.get('impratio', 1.0)),
         'integrator': opt.get('integrator', 'Euler'),
     }
-    assert out['integrator'] == 'Euler', 'only the Euler integrator is implemented'
+    # [MJ] implicitfast (spot.xml:4) solves (M - h dF/dv) qacc = f with dF/dv restricted to passive and actuator forces; for these
+    # models (joint damping only, velocity-independent motors) that is the Euler step with implicit joint damping, (M + h D).
+    assert out['integrator'] in ('Euler', 'implicitfast'), f"integrator {out['integrator']} is not implemented"
 
     meshes = {}
     asset = root.find('asset')

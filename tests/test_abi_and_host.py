@@ -92,8 +92,8 @@ def test_command_modes_robot_cfgs_and_action_space():
     with pytest.raises(ValueError):
         get_robot_config('hyqreal')
     with pytest.raises(NotImplementedError):
-        get_robot_config('spot')
-    assert [get_robot_config(r).tables for r in ('b2', 'go1', 'go2', 'hyqreal2', 'aliengo')] == ['b2', 'go1', 'go2', 'hyqreal2', 'aliengo']
+        get_robot_config('pegasus')
+    assert [get_robot_config(r).tables for r in ('b2', 'go1', 'go2', 'hyqreal2', 'aliengo', 'spot')] == ['b2', 'go1', 'go2', 'hyqreal2', 'aliengo', 'spot']
     box = Box(low=-np.inf, high=np.inf, shape=(12,), dtype=np.float32)
     s = box.sample()
     assert s.shape == (12,) and s.dtype == np.float32 and np.abs(s).max() < 10  # unbounded Box samples N(0,1) (App. B.6)

@@ -8,7 +8,7 @@ from gym_quadruped_b200.model import Model
 from oracle.oracle import F_BIAS, F_CONTACTS, F_IMU, F_M, F_QACC_SMOOTH, Oracle
 from tests.emu.emu import emu_step
 
-ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2', 'go1']  # pyramidal/mesh, pyramidal/primitives+limits, elliptic condim 6, elliptic/mesh
+ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2', 'go1', 'spot']  # pyramidal/mesh, pyramidal/primitives+limits, elliptic condim 6, elliptic/mesh
 
 
 def _start(model, rng):

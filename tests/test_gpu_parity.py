@@ -244,7 +244,7 @@ def test_fused_autoreset_equals_step_then_reset(model, cuda_device):
 # elliptic cones with impratio 100 (go2, hyqreal1) are ~100x stiffer in the friction directions and amplify fp32 rounding:
 # the 1e-4 bar of north_star is met by the pyramidal robots, the elliptic ones are held to 5e-4 here (fp64 build: 1e-10, see
 # tests/test_emulator_parity.py)
-@pytest.mark.parametrize('robot,tol', [('aliengo', 1e-4), ('go2', 5e-4), ('hyqreal1', 5e-4), ('hyqreal2', 1e-4), ('b2', 1e-4), ('go1', 5e-4)])
+@pytest.mark.parametrize('robot,tol', [('aliengo', 1e-4), ('go2', 5e-4), ('hyqreal1', 5e-4), ('hyqreal2', 1e-4), ('b2', 1e-4), ('go1', 5e-4), ('spot', 5e-4)])
 def test_other_robots_rollout_matches_oracle(robot, tol, cuda_device):
     """Pyramidal + primitives + joint limits (aliengo), elliptic cone with condim-6 feet (go2), elliptic + meshes (hyqreal1)."""
     m = Model(robot, 'flat')
@@ -497,10 +497,10 @@ def test_far_from_the_terrain_a_box_scene_behaves_like_flat(cuda_device):
     assert torch.isfinite(b.obs).all() and (b.status == 0).all() and (b.base_pos64[:, :2].abs().max() > 100)
 
 
-@pytest.mark.parametrize('robot_name', ['b2', 'go1', 'go2', 'hyqreal1', 'hyqreal2', 'mini_cheetah', 'aliengo'])
+@pytest.mark.parametrize('robot_name', ['b2', 'go1', 'go2', 'hyqreal1', 'hyqreal2', 'mini_cheetah', 'aliengo', 'spot'])
 @pytest.mark.parametrize('terrain_type', ['flat', 'perlin'])
 def test_robot_env(robot_name, terrain_type, cuda_device):
-    """The reference's own test (tests/env_test.py:14-53), verbatim in structure: 7 robots x {flat, perlin}, ALL_OBS, three kinds of
+    """The reference's own test (tests/env_test.py:14-53), verbatim in structure: its 7 robots (plus spot) x {flat, perlin}, ALL_OBS, three kinds of
     reset, shape contract of every observable, ten random-action steps."""
     from gym_quadruped_b200.quadruped_env import QuadrupedEnv
     state_observables_names = tuple(QuadrupedEnv.ALL_OBS)

@@ -7,9 +7,9 @@ from scipy.spatial.transform import Rotation
 from gym_quadruped_b200.model import Model
 from oracle.oracle import F_CONTACTS, F_EFC, F_FEET_JACP, F_FEET_POS, F_M, F_XPOS, Oracle
 
-ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2', 'go1']
+ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'b2', 'go1', 'spot']
 MASS = {'mini_cheetah': 12.473, 'aliengo': 24.638, 'go2': 15.206, 'hyqreal1': 107.573,
-        'hyqreal2': 126.694, 'b2': 83.498, 'go1': 12.743}  # sum of the <inertial mass=...> attributes of hyqreal2.xml / b2.xml
+        'hyqreal2': 126.694, 'b2': 83.498, 'go1': 12.743, 'spot': 50.34}  # sum of the <inertial mass=...> attributes of hyqreal2.xml / b2.xml
 
 
 def _airborne(model, rng, z=2.0):
@@ -123,7 +123,7 @@ def test_standing_reaction_force_equals_weight(robot):
     key = np.array(m.c.key_qpos)
     o.set_state(key, np.zeros(18), np.zeros(18))
     assert o.lift() >= 0
-    kp, kd = {'hyqreal1': (400.0, 20.0), 'hyqreal2': (3000.0, 60.0), 'b2': (1500.0, 40.0)}.get(robot, (60.0, 3.0))  # heavy robots: stiffer hold
+    kp, kd = {'hyqreal1': (400.0, 20.0), 'hyqreal2': (3000.0, 60.0), 'b2': (1500.0, 40.0), 'spot': (800.0, 30.0)}.get(robot, (60.0, 3.0))  # heavy robots: stiffer hold
     for _ in range(5000):
         q, v, _, _ = o.get_state()
         o.step(kp * (key[7:] - q[7:]) - kd * v[6:])
