@@ -25,7 +25,7 @@ enum { GEOM_PLANE = 0, GEOM_HFIELD = 1, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_
 
 template <typename real> struct alignas(16) Vert4 { real x, y, z, w; };
 // static terrain box (random_boxes scene): centre, rotation (row-major), half sizes, bounding radius
-template <typename real> struct alignas(16) DBox { real pos[3], mat[9], half[3], rad; };
+template <typename real> struct alignas(16) DBox { real pos[3], mat[9], half[3], rad, fri[4]; };
 
 // Robot + scene constants in the kernel's precision; built on the host from QsModel (qstep.cu: build_dmodel),
 // staged into shared memory once per CTA with one TMA bulk copy.
@@ -38,7 +38,8 @@ template <typename real> struct alignas(16) DModel {
   real imu_mat[12];
   real mass_total, robot_radius, pad_r[2];
   real hf_size[4], hf_pos[4];          // height field: half-x, half-y, z-scale, base; position
-  real terr_fri[4], terr_margin, terr_pad[3];  // hfield / box geoms carry default parameters
+  real terr_fri[4], terr_margin, terr_K, terr_B, terr_pad;  // hfield: default parameters; boxes: friction per box (DBox), the rest per scene
+  real terr_solimp[8];                         // contact parameters when the scene's boxes out-rank every robot geom (terr_wins)
   real terr_bounds[4];                         // x_max, x_min, y_max, y_min of everything that is not the floor plane, padded by the robot's reach
   real body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_imat[NB][9], body_mass[NB], body_inertia[NB][3], body_iw[NB][2];
   real jnt_pos[NJ][3], jnt_axis[NJ][3], jnt_range[NJ][2], jnt_K[NJ], jnt_B[NJ], jnt_solimp[NJ][5], jnt_margin[NJ];
@@ -48,7 +49,7 @@ template <typename real> struct alignas(16) DModel {
   real geom_pos[MAXGEOM][3], geom_mat[MAXGEOM][9], geom_size[MAXGEOM][3], geom_bcenter[MAXGEOM][3], geom_bhalf[MAXGEOM][3], geom_rbound[MAXGEOM],
       geom_fri[MAXGEOM][3], geom_margin[MAXGEOM], geom_incmargin[MAXGEOM], geom_K[MAXGEOM], geom_B[MAXGEOM], geom_solimp[MAXGEOM][5];
   int cone, iterations, ls_iterations, ngeom, nvert, terrain_type, nbox, has_imu;
-  int hf_nrow, hf_ncol, terr_pad_i[2];
+  int hf_nrow, hf_ncol, terr_dim, terr_wins;
   int jnt_limited[NJ];
   int geom_type[MAXGEOM], geom_body[MAXGEOM], geom_leg[MAXGEOM], geom_vertadr[MAXGEOM], geom_vertnum[MAXGEOM], geom_dim[MAXGEOM],
       geom_prio[MAXGEOM];
@@ -143,7 +144,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
-  QS_DEV static int info_dim(int info) { return info >> 16; }
+  QS_DEV static int info_dim(int info) { return (info >> 16) & 0xff; }
+  QS_DEV static bool info_terrain_wins(int info) { return (info >> 27) & 1; }  // parameters of a higher-priority terrain box apply
   QS_DEV static int widx(int a, int b) { return a <= b ? a * MAXDIM - (a * (a - 1)) / 2 + (b - a) : b * MAXDIM - (b * (b - 1)) / 2 + (a - b); }
 
   // ------------------------------------------------------------------ position stage
@@ -530,12 +532,16 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   }
 
   // ------------------------------------------------------------------ collision with the terrain
-  QS_DEV void contact_friction(int g, bool world_is_floor, real* fri) const {
+  // wg: world geom of the contact (WG_FLOOR, WG_HFIELD, or the index of a static box)
+  enum { WG_FLOOR = -1, WG_HFIELD = -2 };
+  QS_DEV void contact_friction(int g, int wg, real* fri) const {
+    const bool world_is_floor = wg == WG_FLOOR;
     real gf[3] = {m.geom_fri[g][0], m.geom_fri[g][1], m.geom_fri[g][2]};
     if (m.geom_leg[g] >= 0 && w.mu_feet >= 0) { gf[0] = w.mu_feet; gf[1] = real(0.005); gf[2] = 0; }   // quadruped_env.py:1290-1296
     real wf[3] = {world_is_floor ? m.floor_fri[0] : m.terr_fri[0], world_is_floor ? m.floor_fri[1] : m.terr_fri[1], world_is_floor ? m.floor_fri[2] : m.terr_fri[2]};
+    if (wg >= 0) for (int i = 0; i < 3; i++) wf[i] = boxes[wg].fri[i];
     if (world_is_floor && w.mu_floor >= 0) { wf[0] = w.mu_floor; wf[1] = real(0.005); wf[2] = 0; }
-    const int prio = m.geom_prio[g];
+    const int prio = (wg >= 0 && m.terr_wins) ? -1 : m.geom_prio[g];
     for (int i = 0; i < 3; i++) {
       real f = prio == 0 ? N::max(gf[i], wf[i]) : (prio > 0 ? gf[i] : wf[i]);
       fri[i] = N::max(f, real(1e-5));  // [MJ] mjMINMU
@@ -543,9 +549,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   }
 
   // store one contact (called by a single lane); normal given, yhint optional second-axis guess
-  QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, bool world_is_floor) {
+  QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, int wg) {
     w.c_dist[slot] = dist; w.c_sign[slot] = sign;
-    w.c_info[slot] = g | (m.geom_body[g] << 8) | (m.geom_dim[g] << 16);
+    const bool tw = wg >= 0 && m.terr_wins;
+    w.c_info[slot] = g | (m.geom_body[g] << 8) | ((tw ? m.terr_dim : m.geom_dim[g]) << 16) | (tw ? (1 << 27) : 0);
     real f[6];
     for (int i = 0; i < 3; i++) { w.c_pos[slot][i] = pos[i]; f[i] = normal[i]; f[3 + i] = yhint ? yhint[i] : real(0); }
     // [MJ] mju_makeFrame (third axis = normal x second axis, rebuilt on demand)
@@ -556,7 +563,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     for (int i = 0; i < 3; i++) f[3 + i] *= inv;
     for (int i = 0; i < 6; i++) w.c_frame[slot][i] = f[i];
     real fri[3];
-    contact_friction(g, world_is_floor, fri);
+    contact_friction(g, wg, fri);
     for (int i = 0; i < 3; i++) w.c_fri[slot][i] = fri[i];
   }
   // row k (0 normal, 1, 2 tangents) of the contact frame
@@ -590,7 +597,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   }
 
   // candidate terrain contact kept in registers by the geom's lane (the 4 deepest per geom survive)
-  struct Cand { real dist, pos[3], nrm[3], sign; };
+  struct Cand { real dist, pos[3], nrm[3], sign; int wg; };
   QS_DEV static void cand_insert(Cand* list, int& n, const Cand& c) {
     int k = n < 4 ? n : 4;
     if (n >= 4 && !(c.dist < list[3].dist)) return;
@@ -608,7 +615,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const real dist = (p[2] - z) * nn[2] - r;
       if (dist > margin) return;
       Cand c;
-      c.dist = dist; c.sign = 1;
+      c.dist = dist; c.sign = 1; c.wg = WG_HFIELD;
       for (int i = 0; i < 3; i++) { c.nrm[i] = nn[i]; c.pos[i] = p[i] - nn[i] * (r + real(0.5) * dist); }
       cand_insert(list, n, c);
     } else if (m.terrain_type == 2) {
@@ -640,7 +647,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           real nw[3];
           mul_mv(nw, bx.mat, nl);
           Cand c;
-          c.dist = dist; c.sign = robot_first ? real(-1) : real(1);
+          c.dist = dist; c.sign = robot_first ? real(-1) : real(1); c.wg = b;
           for (int i = 0; i < 3; i++) { c.pos[i] = p[i] - nw[i] * (r + real(0.5) * dist); c.nrm[i] = robot_first ? -nw[i] : nw[i]; }
           cand_insert(list, n, c);
         }
@@ -725,7 +732,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const unsigned mask = ballot(has);
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
-      if (has && slot < NCON) store_contact(slot, g, list[r].sign, list[r].dist, list[r].pos, list[r].nrm, is_caps ? yh : nullptr, false);
+      if (has && slot < NCON) store_contact(slot, g, list[r].sign, list[r].dist, list[r].pos, list[r].nrm, is_caps ? yh : nullptr, list[r].wg);
       ncon += popc(mask);
     }
   }
@@ -869,7 +876,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
       if (has) {
-        if (slot < NCON) store_contact(slot, g, real(1), cd[r], cp[r], nrm, (m.geom_type[g] == GEOM_CAPSULE) ? yh : nullptr, true);
+        if (slot < NCON) store_contact(slot, g, real(1), cd[r], cp[r], nrm, (m.geom_type[g] == GEOM_CAPSULE) ? yh : nullptr, WG_FLOOR);
       }
       ncon += popc(mask);
     }
@@ -916,7 +923,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (dist > margin) continue;
       if (lane == 0 && ncon < NCON) {
         const real pos[3] = {pw[0], pw[1], pw[2] - real(0.5) * dist};
-        store_contact(ncon, gm_, real(1), dist, pos, nrm, nullptr, true);
+        store_contact(ncon, gm_, real(1), dist, pos, nrm, nullptr, WG_FLOOR);
       }
       ncon++;
     }
@@ -1004,9 +1011,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       const real x = w.c_dist[c] - m.geom_incmargin[g];
       const bool active = w.c_dist[c] < m.geom_incmargin[g];
-      const real imp = impedance(m.geom_solimp[g], x);
+      const bool tw = info_terrain_wins(info);
+      const real imp = impedance(tw ? m.terr_solimp : m.geom_solimp[g], x);
       const real tran = m.body_iw[body][0];
-      const real K = m.geom_K[g], B = m.geom_B[g];
+      const real K = tw ? m.terr_K : m.geom_K[g], B = tw ? m.terr_B : m.geom_B[g];
       const real f0 = w.c_fri[c][0];
       for (int k = 0; k < MAXDIM; k++) { w.c_D[c][k] = 0; w.c_ar[c][k] = -B * velc[k]; }
       w.c_ar[c][0] -= K * imp * x;
@@ -1391,7 +1399,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     syncwarp();
     const real scale = real(1) / (m.meaninertia * NV);
     int iter = 0;
-    real cost = 0, oldcost = 0;
+    real cost = 0, oldcost = 0, pred_prev = 0;
     solver_maxed = false;
     QS_TACC(0);
     while (true) {
@@ -1416,7 +1424,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 #ifdef QS_PROF_IMP
         if (iter <= 8) tacc[iter - 1] = __float_as_uint(float(scale * imp));
 #endif
-        if (scale * imp < tol || imp < kNoiseCost * (N::abs(cost) + N::abs(oldcost))) break;
+        // The measured improvement of a stiff problem (tiny friction -> huge pyramid regularisers) is a difference of two large
+        // costs: once it drops below what this precision resolves it reads as "no progress" long before the solution is reached.
+        // In that regime the decrease predicted by the Newton step just taken (-1/2 grad . search: built from the gradient, not
+        // from cost differences) stands in for it.
+        const bool resolved = N::abs(imp) > kNoiseCost * (N::abs(cost) + N::abs(oldcost));
+        const real imp_eff = (resolved || sizeof(real) == 8) ? imp : pred_prev;
+        if (scale * imp_eff < tol || (sizeof(real) == 8 && !resolved)) break;
         if (scale * scale * gn2 < tol * tol || gn2 < kNoise * kNoise * fn2) break;
       }
       if (iter >= max_iter) { solver_maxed = true; break; }
@@ -1447,6 +1461,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       warp_sum4(sn2, qg1, qg2, slope0);
       const real snorm = N::sqrt(sn2);
       if (snorm < N::minval) break;
+      pred_prev = real(-0.5) * slope0;  // Newton decrement of this step
       const real gtol = tol * m.ls_tolerance * snorm / scale;
       QS_TACC(5);
       const real alpha = line_search(gtol, gauss, qg1, qg2, cost, slope0);

@@ -68,6 +68,21 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   for (int i = 0; i < 4; i++) d.hf_size[i] = real(s.hf_size[i]);
   for (int i = 0; i < 3; i++) { d.hf_pos[i] = real(s.hf_pos[i]); d.terr_fri[i] = real(s.box_par.friction[i]); }
   d.terr_margin = real(s.box_par.margin);
+  {  // boxes that out-rank every robot geom (scene_slippery.xml: priority 2) impose their own contact parameters [MJ mj_contactParam]
+    int max_prio = -1000000;
+    for (int g = 0; g < s.ngeom; g++) max_prio = std::max(max_prio, int(s.geom_par[g].priority));
+    d.terr_wins = (s.terrain_type == QS_TERRAIN_BOXES && s.box_par.priority > max_prio) ? 1 : 0;
+    if (s.terrain_type == QS_TERRAIN_BOXES && s.box_par.priority != 0 && !d.terr_wins) return "box priority must be 0 or above every robot geom";
+    if (s.box_par.margin != s.floor_par.margin || s.box_par.gap != s.floor_par.gap) return "terrain boxes must share the floor's margin / gap";
+    double K = 0, B = 0;
+    if (d.terr_wins) {
+      if (s.box_par.solref[0] <= 0) return "direct (negative) solref not supported";
+      solparam(s.box_par.solref, s.box_par.solimp, s.timestep, &K, &B);
+      if (!(s.box_par.condim == 1 || s.box_par.condim == 3)) return "unsupported box contact dimensionality";
+    }
+    d.terr_K = real(K); d.terr_B = real(B); d.terr_dim = s.box_par.condim;
+    for (int i = 0; i < 5; i++) d.terr_solimp[i] = real(s.box_par.solimp[i]);
+  }
   {  // bounding rectangle of the non-floor terrain, padded by the robot's reach: outside it an env sees the floor plane only
     double b[4] = {-big, big, -big, big};
     const double pad = double(d.robot_radius) + 1.0;
@@ -187,6 +202,8 @@ template <typename real> std::vector<DBox<real>> build_boxes(const QsModel& s) {
     for (int i = 0; i < 3; i++) { out[b].pos[i] = real(s.box_pos[b][i]); out[b].half[i] = real(s.box_half[b][i]); r2 += s.box_half[b][i] * s.box_half[b][i]; }
     for (int i = 0; i < 9; i++) out[b].mat[i] = real(m9[i]);
     out[b].rad = real(std::sqrt(r2));
+    for (int i = 0; i < 3; i++) out[b].fri[i] = real(s.box_friction[b][i]);
+    out[b].fri[3] = 0;
   }
   return out;
 }

@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         for (int c = lane; c < NCON; c += 32) {
           float* o = a + AUX_OFF_CONTACTS + QS_CONTACT_STRIDE * c;
           if (c < w.ncon) {
-            const int info = w.c_info[c], dim = info >> 16;
+            const int info = w.c_info[c], dim = (info >> 16) & 0xff;
             o[0] = float(w.c_dist[c]);
             o[1] = float(w.c_pos[c][0] + real(w.org[0])); o[2] = float(w.c_pos[c][1] + real(w.org[1])); o[3] = float(w.c_pos[c][2]);
             real t2[3];
@@ -740,7 +740,7 @@ static KParams base_params(QsHandle* h) {
   p.dm = h->d_dm; p.vert = h->d_vert; p.hf = h->d_hf; p.boxes = h->d_boxes;
   p.hm_rows = h->cfg.hm_rows; p.hm_cols = h->cfg.hm_cols; p.hm_dx = float(h->cfg.hm_dx); p.hm_dy = float(h->cfg.hm_dy);
   p.num_envs = h->cfg.num_envs; p.obs_dim = h->obs_dim; p.use_imu = h->cfg.use_imu;
-  p.max_iter = h->cfg.solver_max_iter > 0 ? h->cfg.solver_max_iter : (h->cfg.precision == 0 ? 12 : 100);
+  p.max_iter = h->cfg.solver_max_iter > 0 ? h->cfg.solver_max_iter : (h->cfg.precision == 0 ? 50 : 100);
   p.tol = h->cfg.precision == 0 ? 1e-6f : 1e-8f;
   p.env_id_offset = h->cfg.env_id_offset;
   p.seed_lo = unsigned(h->cfg.seed & 0xffffffffu); p.seed_hi = unsigned(h->cfg.seed >> 32);

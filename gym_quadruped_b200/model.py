@@ -61,7 +61,7 @@ class QsModel(C.Structure):
         ('hf_nrow', i32), ('hf_ncol', i32), ('hf_size', d * 4), ('hf_pos', d * 3), ('hf_data', C.POINTER(C.c_float)),
         ('hf_par', QsGeomParams),
         ('box_pos', d * 3 * QS_MAXBOX), ('box_quat', d * 4 * QS_MAXBOX), ('box_half', d * 3 * QS_MAXBOX),
-        ('box_par', QsGeomParams),
+        ('box_friction', d * 3 * QS_MAXBOX), ('box_par', QsGeomParams),
         ('has_imu', i32), ('pad1', i32), ('imu_pos', d * 3), ('imu_quat', d * 4),
     ]
 
@@ -183,6 +183,9 @@ class Model:
             assert n <= QS_MAXBOX
             m.nbox = n
             _set2d(m.box_pos, terr['box_pos']); _set2d(m.box_quat, terr['box_quat']); _set2d(m.box_half, terr['box_half'])
+            fri = terr.get('box_friction')
+            _set2d(m.box_friction, fri if fri is not None else np.tile(DEFAULT_GEOM['friction'], (n, 1)))
+            m.box_par.priority = int(terr.get('box_priority', 0))
 
         imu = t.get('imu')
         m.has_imu = 1 if imu else 0

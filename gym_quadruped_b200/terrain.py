@@ -8,6 +8,7 @@ Restates what `gym_quadruped/utils/mujoco/terrain.py:309-365` builds for the sce
 * ``stairs``        -- floor + 50 static steps (robot_model/scene_stairs.xml:38-89), flat limits           terrain.py:319-321
 * ``ramp``          -- floor + one tilted slab (robot_model/scene_ramp.xml:37)                             terrain.py:319-321
 * ``random_pyramids`` -- floor + a stack of shrinking slabs                                            terrain.py:240-292,336-344
+* ``slippery``      -- floor + two priority-2 strips with their own friction (robot_model/scene_slippery.xml:39-40)
 
 All scenes are generated under the reference's fixed seed 10 (quadruped_env.py:155, terrain.py:299-306) with NumPy's
 legacy MT19937 stream, so every env instance of a robot sees the same terrain.  `random_boxes` is pinned bit-for-bit by
@@ -183,6 +184,14 @@ def ramp_scene():
             'box_half': np.array([[4.05, 1.25, 0.025]]), 'terrain_limits': FLAT_LIMITS}
 
 
+def slippery_scene():
+    """robot_model/scene_slippery.xml:39-40: two 1 m wide strips, 1 cm above the floor, whose priority 2 makes their own friction
+    triple win over every robot geom (the feet carry priority 0 or 1)."""
+    return {'type': 'boxes', 'box_pos': np.array([[18.0, 0.0, -0.19], [2.0, 0.0, -0.19]]), 'box_quat': np.tile([1.0, 0, 0, 0], (2, 1)),
+            'box_half': np.array([[13.0, 0.5, 0.2], [3.0, 0.5, 0.2]]), 'box_friction': np.array([[0.03, 0.05, 0.07], [0.8, 0.2, 0.3]]),
+            'box_priority': 2, 'terrain_limits': FLAT_LIMITS}
+
+
 def world_of_pyramid(hip_height: float, seed: int = 10):
     """terrain.py:336-344 -> add_world_of_pyramid(:240-292).  Draw order: stair_nums (an argument, drawn by the caller), then
     height_rand, stride_rand."""
@@ -229,5 +238,6 @@ def generate_terrain(scene: str, hip_height: float, seed: int = 10) -> dict:
         return ramp_scene()
     if scene == 'random_pyramids':
         return world_of_pyramid(hip_height, seed)
-    raise ValueError(f'Invalid scene name: {scene}, available are: flat, random_boxes, random_pyramids, perlin, stairs, ramp '
-                     f'(slippery needs per-surface friction priorities and is not built yet)')
+    if scene == 'slippery':
+        return slippery_scene()
+    raise ValueError(f'Invalid scene name: {scene}, available are: flat, random_boxes, random_pyramids, perlin, stairs, ramp, slippery')

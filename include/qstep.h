@@ -152,7 +152,8 @@ typedef struct QsModel {
   double box_pos[QS_MAXBOX][3];
   double box_quat[QS_MAXBOX][4];
   double box_half[QS_MAXBOX][3];
-  QsGeomParams box_par;
+  double box_friction[QS_MAXBOX][3]; /* per-box slide / spin / roll friction (scene_slippery.xml:39-40) */
+  QsGeomParams box_par;              /* everything else is shared by the boxes of a scene (priority 2 in `slippery`) */
 
   /* IMU site (sensors/imu.py): accelerometer + gyro attached to a site on the base body */
   int32_t has_imu;

@@ -563,7 +563,7 @@ static void collidePointTerrain(OData* d, int g, const double* p, double r, int 
       /* geom1/geom2 ordered by type: sphere / capsule sort before box, so the robot geom is geom1 and the normal flips [MJ] */
       int robot_first = geom_type == QS_GEOM_SPHERE || geom_type == QS_GEOM_CAPSULE || geom_type == QS_GEOM_CYLINDER;
       double nn[3] = {robot_first ? -nw[0] : nw[0], robot_first ? -nw[1] : nw[1], robot_first ? -nw[2] : nw[2]};
-      addContact(d, g, 1 + b, robot_first ? -1 : 1, dist, pos, nn, yaxis, &m->box_par, m->box_par.friction);
+      addContact(d, g, 1 + b, robot_first ? -1 : 1, dist, pos, nn, yaxis, &m->box_par, m->box_friction[b]);
     }
   }
 }

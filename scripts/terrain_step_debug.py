@@ -3,7 +3,9 @@ import numpy as np, torch
 from gym_quadruped_b200.backend import BatchSim, FIELD_CONTACTS
 from gym_quadruped_b200.model import Model
 from oracle.oracle import Oracle, F_CONTACTS
-robot, scene, xy, z0 = 'aliengo','stairs',(1.6,0.0),0.85
+import os
+robot, scene = os.environ.get('QS_ROBOT','aliengo'), os.environ.get('QS_SCENE','stairs')
+xy, z0 = (float(os.environ.get('QS_X','1.6')), float(os.environ.get('QS_Y','0.0'))), float(os.environ.get('QS_Z','0.85'))
 m = Model(robot, scene); n, T = 6, 220
 rng = np.random.RandomState(3); key = np.array(m.c.key_qpos)
 qpos = np.tile(key,(n,1)); qvel=np.zeros((n,18))
@@ -33,5 +35,7 @@ for t in range(T):
             print(' geoms', oc[:,16].astype(int), gc[:,16].astype(int))
             print(' max pos diff', np.abs(oc[:,:4]-gc[:,:4]).max(), 'dist orc', np.round(oc[:,0],5), 'gpu', np.round(gc[:,0],5))
             print(' force orc', np.round(oc[:,13],2), 'gpu', np.round(gc[:,13],2))
+            print(' fric orc', oc[:,18], 'gpu', gc[:,18], 'dim orc', oc[:,19], 'gpu', gc[:,19])
+            print(' ft orc', np.round(oc[:,14:16],3).tolist(), 'gpu', np.round(gc[:,14:16],3).tolist())
             raise SystemExit
 print('no big error')

@@ -90,7 +90,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       }
     // contacts, 422: per contact dist,pos3,frame9,F3,geom,body,mu,dim
     for (int c = 0; c < ws->ncon; c++) {
-      const int info = ws->c_info[c], dim = info >> 16;
+      const int info = ws->c_info[c], dim = (info >> 16) & 0xff;
       misc[k++] = ws->c_dist[c];
       misc[k++] = ws->c_pos[c][0] + ws->org[0]; misc[k++] = ws->c_pos[c][1] + ws->org[1]; misc[k++] = ws->c_pos[c][2];
       const real* f = ws->c_frame[c];

@@ -48,10 +48,14 @@ def _boxes_of(scene):
 
 
 static = {}
-for name in ('stairs', 'ramp'):
+for name in ('stairs', 'ramp', 'slippery'):
     scene, limits = ref_terrain.generate_terrain(Path(f'/root/reference/gym_quadruped/robot_model/scene_{name}.xml'), REF / 'assets',
                                                  0.35, name, seed=10)
     static[name] = dict(_boxes_of(scene), terrain_limits=[float(x) for x in limits])
+    if name == 'slippery':
+        boxes = [g for g in scene.getroot().find('worldbody').findall('geom') if g.attrib.get('type') == 'box']
+        static[name]['friction'] = [[float(x) for x in g.attrib['friction'].split()] for g in boxes]
+        static[name]['priority'] = [int(g.attrib['priority']) for g in boxes]
 for robot, hip in (('mini_cheetah', 0.225), ('aliengo', 0.35), ('go2', 0.28), ('hyqreal1', 0.498)):
     scene, limits = ref_terrain.generate_terrain(Path('/nonexistent/scene_random_pyramids.xml'), REF / 'assets', hip,
                                                  'random_pyramids', seed=10)

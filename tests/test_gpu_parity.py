@@ -372,7 +372,8 @@ def test_quadruped_env_surface(cuda_device):
 @pytest.mark.parametrize('robot,scene,xy,z0', [('go2', 'random_boxes', (2.0, -1.0), 0.45), ('aliengo', 'perlin', (3.0, 2.0), 0.95),
                                                ('aliengo', 'random_boxes', (3.5, 1.0), 0.62), ('aliengo', 'stairs', (1.6, 0.0), 0.85),
                                                ('mini_cheetah', 'ramp', (1.0, 0.0), 0.75), ('hyqreal2', 'random_pyramids', (3.0, 0.5), 1.6),
-                                               ('b2', 'stairs', (1.4, 0.2), 1.0)])
+                                               ('b2', 'stairs', (1.4, 0.2), 1.0), ('go2', 'slippery', (2.0, 0.0), 0.45),
+                                               ('aliengo', 'slippery', (12.0, 0.1), 0.55)])
 def test_terrain_scenes_match_oracle(robot, scene, xy, z0, cuda_device):
     """configs 3 / 4: box and height-field terrain colliders, plus the fused height-map columns (sensors/heightmap.py).
     Closed loop: the oracle is re-seeded from the GPU state before every step, so landing impacts cannot amplify fp32 rounding
@@ -421,7 +422,9 @@ def test_terrain_scenes_match_oracle(robot, scene, xy, z0, cuda_device):
                 continue  # a body lying across several step edges (episode over: invalid contact) is a redundant, ill-conditioned
                 # contact problem whose fp32 solution is only held to the flags, not to the single-step state tolerance
             worst = max(worst, np.abs(q1[i] - qo).max(), 0.1 * np.abs(v1[i] - vo).max())
-    single_step_tol = 1e-4 if m.c.cone == 1 else 2e-5  # elliptic cone, impratio 100: stiff friction rows amplify fp32 rounding
+    # elliptic cone with impratio 100, or the 0.03-friction strip of `slippery` (pyramid regularisers ~ 1 / mu^2): stiff friction
+    # rows amplify fp32 rounding
+    single_step_tol = 1e-4 if (m.c.cone == 1 or scene == 'slippery') else 2e-5
     assert max_ncon >= 4 and worst < single_step_tol and borderline <= 3, (max_ncon, worst, borderline)
     hm = obs[:, 227:].cpu().numpy().reshape(n, 5, 5, 3)
     q1 = sim.qpos.cpu().numpy().astype(np.float64)
@@ -519,3 +522,40 @@ def test_robot_env(robot_name, terrain_type, cuda_device):
         state, reward, is_terminated, is_truncated, info = env.step(action=action)
         assert all(np.isfinite(np.asarray(v)).all() for v in state.values())
     env.close()
+
+
+def test_slippery_strips_impose_their_own_contact_parameters(cuda_device):
+    """scene_slippery.xml:39-40: the two strips carry priority 2, so on them the contact takes the strip's friction triple and its
+    condim 3 -- even for go2's condim-6, priority-1 feet and for a friction override of the feet (quadruped_env.py:1277-1298)."""
+    m = Model('go2', 'slippery')
+    key = np.array(m.c.key_qpos)
+    spots = [(2.0, 0.0, (0.8, 0.2, 0.3)), (12.0, 0.2, (0.03, 0.05, 0.07)), (2.0, 3.0, None)]  # strip 2, strip 1, bare floor
+    n = len(spots)
+    qpos = np.tile(key, (n, 1))
+    for i, (x, y, _) in enumerate(spots):
+        qpos[i, 0:2] = (x, y)
+        o = Oracle(m)
+        for z in np.arange(0.5, 0.2, -0.001):  # lower the robot until all four feet touch the surface they stand on
+            qpos[i, 2] = z
+            o.set_state(qpos[i], np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+            if o.flags()['contact_state'].all():
+                break
+        qpos[i, 2] -= 0.002  # 2-3 mm of penetration (strip top at z = 0.01: the floor stays out of reach of the feet)
+    qpos = qpos.astype(np.float32).astype(np.float64)
+    sim = BatchSim(m, n, device=cuda_device)
+    sim.set_state(torch.tensor(qpos), torch.zeros(n, 18))
+    sim.friction[:] = 0.5
+    sim.forward()
+    con, ncon = sim.get(FIELD_CONTACTS).cpu().numpy(), sim.ncon.cpu().numpy()
+    for i, (x, y, fri) in enumerate(spots):
+        o = Oracle(m); o.set_state(qpos[i], np.zeros(18), np.zeros(18)); o.set_env(0.5, 0.5, [0, 0, 0, 0]); o.forward(np.zeros(12))
+        oc = o.get(F_CONTACTS); gc = con[i, :ncon[i]]
+        assert ncon[i] == len(oc) >= 4
+        gc, oc = gc[np.argsort(gc[:, 16], kind='stable')], oc[np.argsort(oc[:, 16], kind='stable')]
+        np.testing.assert_allclose(gc[:, 18], oc[:, 18], atol=1e-6)   # sliding friction of every contact
+        assert (gc[:, 19] == oc[:, 19]).all()                          # contact dimension
+        feet = np.isin(gc[:, 16], list(m.c.foot_geom))
+        if fri is not None:
+            assert np.allclose(gc[feet, 18], fri[0], atol=1e-6) and (gc[feet, 19] == 3).all()
+        else:
+            assert np.allclose(gc[feet, 18], 0.5, atol=1e-6) and (gc[feet, 19] == 6).all()

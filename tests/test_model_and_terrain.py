@@ -32,10 +32,10 @@ def test_flat_and_perlin_scene_tables():
     assert (img.min(), img.max()) == (64, 195) and list(img[0, :6]) == [127, 136, 129, 135, 143, 143]
     assert list(img[64, 60:66]) == [158, 152, 152, 159, 164, 177]
     with pytest.raises(ValueError):
-        generate_terrain('slippery', 0.3)
+        generate_terrain('lava', 0.3)
 
 
-@pytest.mark.parametrize('key,scene,hip', [('stairs', 'stairs', 0.35), ('ramp', 'ramp', 0.35), ('random_pyramids_mini_cheetah', 'random_pyramids', 0.225),
+@pytest.mark.parametrize('key,scene,hip', [('stairs', 'stairs', 0.35), ('ramp', 'ramp', 0.35), ('slippery', 'slippery', 0.35), ('random_pyramids_mini_cheetah', 'random_pyramids', 0.225),
                                            ('random_pyramids_aliengo', 'random_pyramids', 0.35), ('random_pyramids_go2', 'random_pyramids', 0.28),
                                            ('random_pyramids_hyqreal1', 'random_pyramids', 0.498)])
 def test_static_box_scenes_against_reference_generator(key, scene, hip):
@@ -47,6 +47,8 @@ def test_static_box_scenes_against_reference_generator(key, scene, hip):
     q = np.array(g['quat'])
     np.testing.assert_allclose(t['box_quat'], q / np.linalg.norm(q, axis=1, keepdims=True), atol=1e-15)
     assert tuple(float(x) for x in t['terrain_limits']) == tuple(g['terrain_limits'])
+    if 'friction' in g:  # scene_slippery.xml: per-surface friction triples and priority 2
+        assert np.array_equal(t['box_friction'], np.array(g['friction'])) and set(g['priority']) == {t['box_priority']} == {2}
 
 
 def test_model_constants_from_the_mjcf():
