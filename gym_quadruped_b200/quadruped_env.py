@@ -151,6 +151,8 @@ class QuadrupedEnv(Env):
         perm = [_MODEL_LEGS.index(leg) for leg in self.legs_order]
         self._leg_perm = None if perm == [0, 1, 2, 3] else torch.tensor(
             [3 * p + i for p in perm for i in range(3)], device=self.device, dtype=torch.long)
+        self._leg_perm_np = None if self._leg_perm is None else np.array([3 * p + i for p in perm for i in range(3)])
+        self._time_host = 0.0
 
         self.external_disturbances_kwargs = external_disturbances_kwargs
         self._ext_schedule = None
@@ -160,12 +162,21 @@ class QuadrupedEnv(Env):
         self.viewer = None
         self.step_num = 0
         self._last_obs_tensor = self.sim.obs
+        # single-env fast path: the step goes through qs_step_host with pinned one-row buffers (one launch, one synchronisation;
+        # the kernel reads ctrl and writes the observation row / flags straight through the mapped host memory)
+        self._host = None
+        if self.num_envs == 1:
+            pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
+            self._host = dict(ctrl=pin(1, 12), obs=pin(1, self.sim.obs_dim), rew=pin(1), term=pin(1, dtype=torch.uint8),
+                              trunc=pin(1, dtype=torch.uint8))
+            self._host['obs_np'] = self._host['obs'].numpy()
+            self._host['ctrl_np'] = self._host['ctrl'].numpy()
 
     # ------------------------------------------------------------------ gym API
     def step(self, action):
         """Apply joint torques, advance one sim step, return (obs, reward, terminated, truncated, info); :251-307."""
-        if self.num_envs == 1 and not isinstance(action, torch.Tensor):
-            action = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 12), device=self.device)
+        if self.num_envs == 1:
+            return self._step_single(action)
         obs_t, rew, term, trunc = self.sim.step(action)
         for s in self.sensors:
             s.step()
@@ -176,14 +187,36 @@ class QuadrupedEnv(Env):
         if self.external_disturbances_kwargs is not None and self.external_disturbances_kwargs.get('type') == 'reset':
             self._advance_disturbance_schedule()
         obs = self._obs_dict(obs_t)
-        if self.num_envs == 1:
-            mask = int(info_invalid[0, 0].item()) | (int(info_invalid[0, 1].item()) << 8)
-            names = self.model.tables['body_names']
-            invalid = {f'world:0_{names[b]}:{b}': None for b in range(1, 14) if mask >> b & 1}
-            info = {'time': float(self.sim.sim_time[0].item()), 'step_num': self.step_num - 1, 'invalid_contacts': invalid}
-            return obs, 0, bool(term[0].item()), False, info
         info = {'time': self.sim.sim_time, 'step_num': self.step_num - 1, 'invalid_contacts': info_invalid}
         return obs, rew, term.bool(), trunc.bool(), info
+
+    def _step_single(self, action):
+        """num_envs == 1: reference return types (dict of float64 arrays, Python flags) with one launch and one synchronisation."""
+        h = self._host
+        if isinstance(action, torch.Tensor):
+            h['ctrl'].copy_(action.detach().reshape(1, 12).to('cpu', torch.float32))
+        else:
+            h['ctrl_np'][0, :] = np.asarray(action, dtype=np.float32).reshape(12)
+        self.sim.step_host(h['ctrl'], h['obs'], h['rew'], h['term'], h['trunc'])  # returns after the stream is synchronised
+        self.sim.obs.copy_(h['obs'], non_blocking=True)  # keeps the device-side row (frame conversions of the accessors) current
+        for s in self.sensors:
+            s.step()
+        self.step_num += 1
+        if self._command_mode & backend.CMD_RESET:
+            self._advance_velocity_schedule()
+        if self.external_disturbances_kwargs is not None and self.external_disturbances_kwargs.get('type') == 'reset':
+            self._advance_disturbance_schedule()
+        obs = self._obs_dict(self.sim.obs, host_row=h['obs_np'][0])
+        terminated = bool(h['term'][0])
+        invalid = {}
+        if terminated:  # a contact can only be invalid if the episode terminated (quadruped_env.py:283-285)
+            m = self.sim.invalid_body_mask[0].tolist()
+            mask = int(m[0]) | (int(m[1]) << 8)
+            names = self.model.tables['body_names']
+            invalid = {f'world:0_{names[b]}:{b}': None for b in range(1, 14) if mask >> b & 1}
+        self._time_host += self.simulation_dt
+        info = {'time': self._time_host, 'step_num': self.step_num - 1, 'invalid_contacts': invalid}
+        return obs, 0, terminated, False, info
 
     def reset(self, qpos=None, qvel=None, seed: int | None = None, random: bool = True, options: dict[str, Any] | None = None,
               env_mask: torch.Tensor | None = None):
@@ -211,6 +244,7 @@ class QuadrupedEnv(Env):
             raise RuntimeError('Unable to initialize the robot without ground contact.')
         if self._command_mode & backend.CMD_RESET:
             self._vel_schedule = None
+        self._time_host = self.simulation_dt  # the reset ends with one step from time 0 (:333,:397)
         return self._obs_dict(obs_t)
 
     def auto_reset(self):
@@ -225,8 +259,16 @@ class QuadrupedEnv(Env):
             self.sim.close()
 
     # ------------------------------------------------------------------ observation plumbing
-    def _obs_dict(self, obs_t: torch.Tensor):
+    def _obs_dict(self, obs_t: torch.Tensor, host_row=None):
         self._last_obs_tensor = obs_t
+        if self.num_envs == 1:  # the reference's types: a dict of fresh float64 arrays (:1156-1204)
+            flat = (obs_t[0].detach().cpu().numpy() if host_row is None else host_row).astype(np.float64)
+            res = {}
+            for name in self.state_obs_names:
+                off, dim = self._layout[name]
+                a = flat[off:off + dim]
+                res[name] = a[self._leg_perm_np] if (self._leg_perm is not None and name in _PER_LEG_OBS) else a.copy()
+            return res
         out = {}
         for name in self.state_obs_names:
             off, dim = self._layout[name]
@@ -234,16 +276,6 @@ class QuadrupedEnv(Env):
             if self._leg_perm is not None and name in _PER_LEG_OBS:
                 v = v.index_select(1, self._leg_perm)
             out[name] = v
-        if self.num_envs == 1:
-            flat = obs_t[0].detach().cpu().numpy().astype(np.float64)
-            res = {}
-            for name in self.state_obs_names:
-                off, dim = self._layout[name]
-                a = flat[off:off + dim]
-                if self._leg_perm is not None and name in _PER_LEG_OBS:
-                    a = a[self._leg_perm.cpu().numpy()]
-                res[name] = a.copy()
-            return res
         return out
 
     def _sensor_obs(self, name):
