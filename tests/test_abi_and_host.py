@@ -133,3 +133,19 @@ def test_obs_gather_two_ranks_gloo(tmp_path):
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0, err[-2000:]
         assert 'ok' in out
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / 'bench.py'), '--impl', 'reference', '--steps', '3', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'env-steps/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['config']['workload'].startswith('mini_cheetah/flat') and line['n_gpus'] == 1 and line['steps'] == 3
