@@ -166,7 +166,7 @@ class ClockSampler:
         self.proc = None
         self.gpu = gpu_index
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '20',
                                           '-i', str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -181,6 +181,12 @@ class ClockSampler:
             self.proc.kill()
             out, _ = self.proc.communicate()
         sm, smax, reasons = [], [], set()
+        if not out.strip():  # the timed region was shorter than one sampling period: one query right after it
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-i', str(self.gpu)],
+                                     capture_output=True, text=True, timeout=10).stdout
+            except (OSError, subprocess.TimeoutExpired):
+                out = ''
         for line in out.splitlines():
             p = [x.strip() for x in line.split(',')]
             if len(p) < 9:

@@ -134,6 +134,14 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV static int tri_dof_leg(int t) { return (t >> 16) & 3; }
   QS_DEV static int tri_dof_k(int t) { return (t >> 18) & 3; }
 
+  // QS_FORCE_PYR (experiment / pyramidal-only builds): the cone type becomes a compile-time constant and the elliptic code disappears
+  QS_DEV bool cone_is_pyramidal() const {
+#ifdef QS_FORCE_PYR
+    return true;
+#else
+    return m.cone == 0;
+#endif
+  }
   bool terrain_on = true;  // false: the base is out of reach of everything but the floor plane (internal frame re-centred like 'flat')
   bool calf_only = false;  // collision stage restricted to the calf-body geoms (the reset lift loop looks at nothing else)
   QS_DEV bool geom_on(int g) const {
@@ -1022,7 +1030,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (dim == 1) {
         w.c_D[c][0] = 1 / N::max(N::minval, (1 - imp) * tran / imp);
         w.c_mu[c] = f0;
-      } else if (m.cone == 0) {
+      } else if (cone_is_pyramidal()) {
         const real Rn = N::max(N::minval, (1 - imp) * (tran + f0 * f0 * tran) / imp);
         const real mur = f0 * N::sqrt(1 / N::max(N::minval, m.impratio));
         const real Rpy = 2 * mur * mur * Rn;
@@ -1068,7 +1076,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (D0 == 0) return;
     if (dim == 1) { row_q(r[0], v[0], D0, cost, d1, d2); return; }
     const real mu = w.c_mu[c];
-    if (m.cone == 0) {
+    if (cone_is_pyramidal()) {
       for (int j = 1; j < 3; j++) {
         row_q(r[0] + mu * r[j], v[0] + mu * v[j], D0, cost, d1, d2);
         row_q(r[0] - mu * r[j], v[0] - mu * v[j], D0, cost, d1, d2);
@@ -1106,7 +1114,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       return cost;
     }
     const real mu = w.c_mu[c];
-    if (m.cone == 0) {
+    if (cone_is_pyramidal()) {
       real fe[4], de[4];
       for (int e = 0; e < 4; e++) {
         const real x = r[0] + ((e & 1) ? -mu : mu) * r[1 + e / 2];
@@ -1245,7 +1253,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const int leg = legc ? (body - 2) / 3 : 0;
       real h0 = 0, h1 = 0;
       const bool on0 = lane < 21 || legc, on1 = own1 && legc;
-      if (MAXDIM == 3 && m.cone == 0 && dim == 3) {
+      if (MAXDIM == 3 && cone_is_pyramidal() && dim == 3) {
         const real w00 = Wt[widx(0, 0)], w01 = Wt[widx(0, 1)], w02 = Wt[widx(0, 2)], w11 = Wt[widx(1, 1)], w22 = Wt[widx(2, 2)];
         if (on0) {
           const real p0 = w.Jc[c][0][i0], p1 = w.Jc[c][1][i0], p2 = w.Jc[c][2][i0], q0 = w.Jc[c][0][j0], q1 = w.Jc[c][1][j0], q2 = w.Jc[c][2][j0];

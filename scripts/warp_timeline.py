@@ -13,7 +13,8 @@ from gym_quadruped_b200.backend import BatchSim
 from gym_quadruped_b200.model import Model
 import bench
 
-model = Model('mini_cheetah', 'flat')
+import os
+model = Model(os.environ.get('QS_ROBOT', 'mini_cheetah'), os.environ.get('QS_SCENE', 'flat'))
 import os
 n = int(os.environ.get('QS_N', '4096'))
 sim = BatchSim(model, n, device=0)
