@@ -136,3 +136,35 @@ def test_cylinder_plane_collider_matches_oracle(roll):
     oc, ec = oc[key(oc)], ec[key(ec)]
     assert (oc[:, 16:18] == ec[:, 16:18]).all()
     np.testing.assert_allclose(ec[:, 0:13], oc[:, 0:13], atol=1e-9)   # dist, position, frame
+
+
+@pytest.mark.parametrize('robot,scene,xy,z0', [('aliengo', 'perlin', (3.0, 2.0), 0.95), ('go2', 'random_boxes', (2.0, -1.0), 0.45),
+                                               ('aliengo', 'stairs', (1.6, 0.0), 0.85), ('hyqreal2', 'random_pyramids', (3.0, 0.5), 1.32),
+                                               ('aliengo', 'slippery', (12.0, 0.1), 0.55), ('b2', 'ramp', (1.0, 0.1), 0.8)])
+def test_terrain_scenes_closed_loop(robot, scene, xy, z0):
+    """Terrain colliders of the kernel source (height field, static boxes incl. the priority-2 strips of `slippery`) against the
+    oracle, closed loop in fp64: the emulated step is re-seeded from the oracle's state every step while the robot drops onto the
+    terrain under a PD hold; contact count / flags identical, state to rounding."""
+    m = Model(robot, scene)
+    rng = np.random.RandomState(4)
+    key = np.array(m.c.key_qpos)
+    q = key.copy()
+    q[0:2] = np.array(xy) + rng.uniform(-0.3, 0.3, 2); q[2] = z0
+    q[7:] += rng.uniform(-0.15, 0.15, 12)
+    o = Oracle(m)
+    o.set_state(q, np.zeros(18), np.zeros(18)); assert o.lift() >= 0
+    o.set_env(0.8, 0.8, [0.5, 0, 0, 0])
+    kp = 40.0 if m.c.body_mass[1] < 20 else 400.0
+    max_ncon, worst = 0, 0.0
+    for k in range(120):
+        q0, v0, _, w0 = o.get_state()
+        ctrl = (kp * (key[7:] - q0[7:]) - 0.05 * kp * v0[6:] + rng.randn(12) * 2).astype(np.float32).astype(np.float64)
+        e = emu_step(m, q0, v0, w0, ctrl, 0.8, 0.8, [0.5, 0, 0, 0], precision=1, mode=1)
+        o.step(ctrl)
+        f = o.flags()
+        assert e['ncon'] == f['ncon'] and e['invalid_mask'] == f['invalid_body_mask'], f'step {k}'
+        assert e['contact_mask'] == sum(int(b) << i for i, b in enumerate(f['contact_state']))
+        qo, vo, _, _ = o.get_state()
+        worst = max(worst, np.abs(e['qpos'] - qo).max(), np.abs(e['qvel'] - vo).max())
+        max_ncon = max(max_ncon, f['ncon'])
+    assert max_ncon >= 2 and worst < 1e-8, (max_ncon, worst)
