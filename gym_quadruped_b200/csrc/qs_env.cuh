@@ -122,11 +122,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   QS_DEV Env(const DModel<real>& m_, W& w_, const Vert4<real>* v_, int lane_)
       : m(m_), w(w_), vert(v_), hf(nullptr), boxes(nullptr), lane(lane_), solver_iter(0), ls_evals(0), solver_maxed(false), bias_out(nullptr) {
-    int i0 = 0, j0 = lane_, i1 = 0, j1 = lane_ + 32;
-    while (j0 > i0) { j0 -= i0 + 1; i0++; }
-    while (j1 > i1) { j1 -= i1 + 1; i1++; }
-    const int dl = (lane_ >= 6 && lane_ < NV) ? (lane_ - 6) / 3 : 0, dk = (lane_ >= 6 && lane_ < NV) ? (lane_ - 6) % 3 : 0;
-    tri = i0 | (j0 << 4) | (i1 << 8) | (j1 << 12) | (dl << 16) | (dk << 18) | ((lane_ / 6) << 20) | ((lane_ % 6) << 23);
+    // per lane: i0 | j0<<4 | i1<<8 | j1<<12 | dof_leg<<16 | dof_k<<18 | (lane/6)<<20 | (lane%6)<<23, with (i, j) the row / column of
+    // entry e = lane (and e = lane + 32) of a row-major lower triangle -- tabulated (checked by tests/test_abi_and_host.py)
+    static constexpr int kLaneRoles[32] = {18176, 8410881, 16803601, 25196290, 33556498, 41949218, 1058819, 9713683, 18368547, 26302515, 34957316, 43612180, 2263076, 10881332, 19536196, 27470085, 36124949, 44779813, 3168565, 11561285, 19954005, 28346630, 36739350, 45091366, 4201014, 12593734, 20986454, 29379174, 37771783, 46164503, 5274151, 13666871};
+    tri = kLaneRoles[lane_ & 31];
   }
   // leg / joint-in-leg of dof lane 6..17 (0 elsewhere); lane / 6 and lane % 6
   QS_DEV int dof_leg() const { return (tri >> 16) & 3; }

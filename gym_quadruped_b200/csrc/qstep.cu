@@ -117,12 +117,20 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   using DM = DModel<real>;
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr size_t DM_BYTES = (sizeof(DM) + 127) & ~size_t(127);
-  DM* dm = reinterpret_cast<DM*>(smem);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + DM_BYTES);
   W* wsbase = reinterpret_cast<W*>(smem + DM_BYTES + 128);
   // canonical warp index broadcast from lane 0: lets the compiler prove it warp-uniform, so the per-warp workspace base lives
   // in a uniform register instead of being re-derived from threadIdx before every shared-memory access
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
+  // the lane id is read once through an opaque asm: left to itself the compiler re-materialises `threadIdx.x & 31` with an S2R (a
+  // ~25-cycle special-register read) at ~65 places per env-step to save one register
+  int lane_reg;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));
+  const int lane = lane_reg;
+  // The model sits at offset 0 of the dynamic shared memory.  Its base is tied to the (shuffle-produced, hence opaque) warp index so
+  // that it lives in a register like the workspace base: otherwise every indexed access to a model table re-derives the shared
+  // window base from the CgaCtaId special register (~50 S2R per env-step on address-critical paths).  warp < 32, so the term is 0.
+  DM* dm = reinterpret_cast<DM*>(smem + ((warp >> 10) << 4));
   if (MODE == MODE_STEP && p.sched_zero_cnt && blockIdx.x == 0 && threadIdx.x < 2) p.sched_zero_cnt[threadIdx.x] = 0;
   int env = blockIdx.x * nwarp + warp;
   if (MODE == MODE_STEP && p.sched_in) {

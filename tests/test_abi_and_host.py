@@ -149,3 +149,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert line['config']['workload'].startswith('mini_cheetah/flat') and line['n_gpus'] == 1 and line['steps'] == 3
+
+
+def test_lane_role_table_of_the_kernel_source():
+    """qs_env.cuh tabulates, per lane, the triangle coordinates of its Hessian entries and its dof role; recompute them here."""
+    src = (Path(__file__).resolve().parents[1] / 'gym_quadruped_b200' / 'csrc' / 'qs_env.cuh').read_text()
+    table = [int(x) for x in re.search(r'kLaneRoles\[32\] = \{([^}]*)\}', src).group(1).split(',')]
+    assert len(table) == 32
+    for lane, v in enumerate(table):
+        (i0, j0), (i1, j1) = [next((i, e - i * (i + 1) // 2) for i in range(12) if i * (i + 1) // 2 <= e < (i + 1) * (i + 2) // 2)
+                              for e in (lane, lane + 32)]
+        dl, dk = ((lane - 6) // 3, (lane - 6) % 3) if 6 <= lane < 18 else (0, 0)
+        assert v == i0 | (j0 << 4) | (i1 << 8) | (j1 << 12) | (dl << 16) | (dk << 18) | ((lane // 6) << 20) | ((lane % 6) << 23)
