@@ -152,6 +152,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV static int info_geom(int info) { return info & 0xff; }
   QS_DEV static int info_body(int info) { return (info >> 8) & 0xff; }
   QS_DEV static int info_dim(int info) { return (info >> 16) & 0xff; }
+  QS_DEV static int info_leg(int info) { return (info >> 24) & 7; }  // leg of the contact body, 7: base / world side only
   QS_DEV static bool info_terrain_wins(int info) { return (info >> 27) & 1; }  // parameters of a higher-priority terrain box apply
   QS_DEV static int widx(int a, int b) { return a <= b ? a * MAXDIM - (a * (a - 1)) / 2 + (b - a) : b * MAXDIM - (b * (b - 1)) / 2 + (a - b); }
 
@@ -559,7 +560,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, int wg) {
     w.c_dist[slot] = dist; w.c_sign[slot] = sign;
     const bool tw = wg >= 0 && m.terr_wins;
-    w.c_info[slot] = g | (m.geom_body[g] << 8) | ((tw ? m.terr_dim : m.geom_dim[g]) << 16) | (tw ? (1 << 27) : 0);
+    const int gb = m.geom_body[g], gleg = gb >= 2 ? (gb - 2) / 3 : 7;
+    w.c_info[slot] = g | (gb << 8) | ((tw ? m.terr_dim : m.geom_dim[g]) << 16) | (gleg << 24) | (tw ? (1 << 27) : 0);
     real f[6];
     for (int i = 0; i < 3; i++) { w.c_pos[slot][i] = pos[i]; f[i] = normal[i]; f[3 + i] = yhint ? yhint[i] : real(0); }
     // [MJ] mju_makeFrame (third axis = normal x second axis, rebuilt on demand)
@@ -1012,7 +1014,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         if (k < dim) {
           const real* J = w.Jc[c][k];
           s = J[0] * w.qvel[0] + J[1] * w.qvel[1] + J[2] * w.qvel[2] + J[3] * w.qvel[3] + J[4] * w.qvel[4] + J[5] * w.qvel[5];
-          if (body >= 2) { const real* xl = w.qvel + 6 + 3 * ((body - 2) / 3); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
+          if (body >= 2) { const real* xl = w.qvel + 6 + 3 * info_leg(info); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
         }
         velc[k] = s;
       }
@@ -1054,19 +1056,25 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV real fri_k(int c, int k) const { return k <= 2 ? w.c_fri[c][0] : (k == 3 ? w.c_fri[c][1] : w.c_fri[c][2]); }
 
   // ------------------------------------------------------------------ per-unit cost model  [MJ] mj_constraintUpdate
+  // branch-free (selects): these sit in the innermost loop of the line search, where every divergent region costs a re-convergence
   QS_DEV static void row_q(real x, real v, real D, real& cost, real& d1, real& d2) {
-    if (x < 0) { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
+    const bool on = x < 0;
+    const real c = real(0.5) * D * x * x, a = D * x * v, b = D * v * v;
+    cost += on ? c : real(0); d1 += on ? a : real(0); d2 += on ? b : real(0);
   }
   // scalar unit u at residual x with direction v
   QS_DEV void scalar_unit_eval(int u, real x, real v, real& cost, real& d1, real& d2) const {
     const real D = w.u_D[u];
-    if (D == 0) return;
-    if (u < NFL) {
-      const real f = m.dof_floss[6 + u], rf = N::div(f, D);
-      if (x <= -rf) { cost += -f * (real(0.5) * rf + x); d1 += -f * v; }
-      else if (x >= rf) { cost += -f * (real(0.5) * rf - x); d1 += f * v; }
-      else { cost += real(0.5) * D * x * x; d1 += D * x * v; d2 += D * v * v; }
-    } else row_q(x, v, D, cost, d1, d2);
+    const bool fric = u < NFL;
+    const real f = m.dof_floss[6 + (fric ? u : 0)], rf = N::div(f, D != 0 ? D : real(1));
+    const bool lo = fric && x <= -rf, hi = fric && !lo && x >= rf;       // linear zones of the friction-loss cost
+    const bool quad = D != 0 && (fric ? !(lo || hi) : x < 0);
+    const real cq = real(0.5) * D * x * x, aq = D * x * v, bq = D * v * v;
+    const real cl = -f * (real(0.5) * rf + x), ch = -f * (real(0.5) * rf - x);
+    const bool act = D != 0;
+    cost += quad ? cq : ((act && lo) ? cl : ((act && hi) ? ch : real(0)));
+    d1 += quad ? aq : ((act && lo) ? -f * v : ((act && hi) ? f * v : real(0)));
+    d2 += quad ? bq : real(0);
   }
   // contact unit c at contact-frame residual r[] with direction v[]
   QS_DEV void contact_unit_eval(int c, const real* r, const real* v, real& cost, real& d1, real& d2) const {
@@ -1169,7 +1177,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (k < info_dim(info)) {
         const real* J = w.Jc[c][k];
         s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
-        if (body >= 2) { const real* xl = x + 6 + 3 * ((body - 2) / 3); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
+        if (body >= 2) { const real* xl = x + 6 + 3 * info_leg(info); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
         if (minus_ar) s -= w.c_ar[c][k];
       }
       out_c[c][k] = s;
@@ -1183,7 +1191,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane], real(0), cost, d1, d2);
     real zero[MAXDIM];
     for (int k = 0; k < MAXDIM; k++) zero[k] = 0;
-    for (int c = lane; c < w.ncon; c += 32) contact_unit_eval(c, w.c_r[c], zero, cost, d1, d2);
+    static_assert(NCON <= 32, "one lane per contact");
+    if (lane < w.ncon) contact_unit_eval(lane, w.c_r[lane], zero, cost, d1, d2);
     cost = warp_sum(cost);
     syncwarp();  // residuals are overwritten by the next units_Jx
     return cost;
@@ -1207,7 +1216,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       w.u_F[u] = F; w.u_W[u] = Wt;
     }
     const int ncon = w.ncon;
-    for (int c = lane; c < ncon; c += 32) cost += contact_unit_update(c);
+    if (lane < ncon) cost += contact_unit_update(lane);
     syncwarp();
     return cost;  // per-lane partial: the caller reduces it together with its other sums
   }
@@ -1222,7 +1231,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const int ncon = w.ncon;
       for (int c = 0; c < ncon; c++) {
         const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
-        const bool mine = !isleg || (body >= 2 && (body - 2) / 3 == l);
+        const bool mine = !isleg || info_leg(info) == l;
         real t = 0;
 #pragma unroll
         for (int a = 0; a < MAXDIM; a++) t += (a < dim) ? w.Jc[c][a][col] * w.c_F[c][a] : real(0);
@@ -1249,7 +1258,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (Wt[0] == 0) continue;  // no active row in this contact (W00 sums the active regularisers)
       const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
       const bool legc = body >= 2;
-      const int leg = legc ? (body - 2) / 3 : 0;
+      const int leg = legc ? info_leg(info) : 0;
       real h0 = 0, h1 = 0;
       const bool on0 = lane < 21 || legc, on1 = own1 && legc;
       if (MAXDIM == 3 && cone_is_pyramidal() && dim == 3) {
@@ -1286,19 +1295,26 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
     // H = M + accumulated J^T W J (+ the scalar units' weights on the leg diagonals), written once by the owning lanes
     if (lane < 21) w.hes.Hbb[i0][j0] = w.Mbb[i0][j0] + ab;
+    // per-leg entries: the (row, column) of a lane is fixed, only the leg stride moves (Hlb / Mlb: 18 floats per leg, Hll / Mll: 9)
+    auto write_legs = [&](int i, int j, const real* acc) {
+      const int k = i - 6;
+      if (j < 6) {
+        real* H = &w.hes.Hlb[0][k][j];
+        const real* M = &w.Mlb[0][k][j];
 #pragma unroll
-    for (int l = 0; l < 4; l++) {
-      if (lane >= 21) {
-        const int k = i0 - 6;
-        if (j0 < 6) w.hes.Hlb[l][k][j0] = w.Mlb[l][k][j0] + a0[l];
-        else w.hes.Hll[l][k][j0 - 6] = w.Mll[l][k][j0 - 6] + a0[l] + ((j0 - 6 == k) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0));
+        for (int l = 0; l < 4; l++) H[18 * l] = M[18 * l] + acc[l];
+      } else {
+        const int jj = j - 6;
+        real* H = &w.hes.Hll[0][k][jj];
+        const real* M = &w.Mll[0][k][jj];
+        const bool diag = jj == k;
+        const real* uw = &w.u_W[k];
+#pragma unroll
+        for (int l = 0; l < 4; l++) H[9 * l] = M[9 * l] + acc[l] + (diag ? uw[3 * l] + uw[NFL + 3 * l] : real(0));
       }
-      if (own1) {
-        const int k = i1 - 6;
-        if (j1 < 6) w.hes.Hlb[l][k][j1] = w.Mlb[l][k][j1] + a1[l];
-        else w.hes.Hll[l][k][j1 - 6] = w.Mll[l][k][j1 - 6] + a1[l] + ((j1 - 6 == k) ? w.u_W[3 * l + k] + w.u_W[NFL + 3 * l + k] : real(0));
-      }
-    }
+    };
+    if (lane >= 21) write_legs(i0, j0, a0);
+    if (own1) write_legs(i1, j1, a1);
     syncwarp();
   }
 
@@ -1309,7 +1325,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     real cost = 0, d1 = 0, d2 = 0;
     if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane] + alpha * w.u_v[lane], w.u_v[lane], cost, d1, d2);
     const int ncon = w.ncon;
-    for (int c = lane; c < ncon; c += 32) {
+    if (lane < ncon) {
+      const int c = lane;
       real r[MAXDIM];
       for (int k = 0; k < MAXDIM; k++) r[k] = w.c_r[c][k] + alpha * w.c_v[c][k];
       contact_unit_eval(c, r, w.c_v[c], cost, d1, d2);
@@ -1567,9 +1584,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   struct Flags { unsigned contact_mask; unsigned invalid_mask; bool out_of_bounds; };
   QS_DEV Flags flags() const {
     unsigned cm = 0, im = 0;
-    for (int c = lane; c < w.ncon; c += 32) {
-      const int b = info_body(w.c_info[c]);
-      if (b >= 2 && (b - 2) % 3 == 2) cm |= 1u << ((b - 2) / 3); else im |= 1u << b;
+    if (lane < w.ncon) {
+      const int info = w.c_info[lane], b = info_body(info);
+      if (b >= 2 && (b - 2) % 3 == 2) cm |= 1u << info_leg(info); else im |= 1u << b;
     }
     for (int o = 16; o > 0; o >>= 1) { cm |= shfl_xor(cm, o); im |= shfl_xor(im, o); }
     Flags f;
