@@ -263,14 +263,20 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const int b = lane + 1;
       const int k = (lane >= 1 && isb) ? (lane - 1) % 3 : 3;
       real cr[10];
+      const real* ci = w.tmp.cinert[isb ? b : 1];
+#pragma unroll
       for (int i = 0; i < 10; i++) {
-        const real v = isb ? w.tmp.cinert[b][i] : real(0);
+        const real v = isb ? ci[i] : real(0);
         const real tot = warp_sum(v);
         const real t1 = shfl(v, (lane + 1) & 31), t2 = shfl(v, (lane + 2) & 31);
         cr[i] = (lane == 0) ? tot : v + (k <= 1 ? t1 : real(0)) + (k == 0 ? t2 : real(0));
       }
       syncwarp();
-      if (isb) for (int i = 0; i < 10; i++) w.tmp.cinert[b][i] = cr[i];
+      if (isb) {
+        real* co = w.tmp.cinert[b];
+#pragma unroll
+        for (int i = 0; i < 10; i++) co[i] = cr[i];
+      }
     }
     syncwarp();
     if (lane < NV) {
@@ -350,11 +356,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int i = 0; i < 6; i++) f[i] += t1[i];
     }
     const int kk = (lane >= 1 && isb) ? k : 3;
+    real s6[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
       real tot = warp_sum(f[i]);
       real t1 = shfl(f[i], (lane + 1) & 31), t2 = shfl(f[i], (lane + 2) & 31);
-      real s = (lane == 0) ? tot : f[i] + (kk <= 1 ? t1 : real(0)) + (kk == 0 ? t2 : real(0));
-      if (isb) w.tmp.cfrc[b][i] = s;
+      s6[i] = (lane == 0) ? tot : f[i] + (kk <= 1 ? t1 : real(0)) + (kk == 0 ? t2 : real(0));
+    }
+    if (isb) {
+      real* cf = w.tmp.cfrc[b];
+#pragma unroll
+      for (int i = 0; i < 6; i++) cf[i] = s6[i];
     }
     syncwarp();
     if (lane < NV) {
