@@ -1603,9 +1603,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     for (int o = 16; o > 0; o >>= 1) { cm |= shfl_xor(cm, o); im |= shfl_xor(im, o); }
     Flags f;
     f.contact_mask = cm; f.invalid_mask = im;
-    const double x = w.org[0] + double(w.qpos[0]), y = w.org[1] + double(w.qpos[1]);
-    f.out_of_bounds = x > double(m.terrain_limits[0]) || x < double(m.terrain_limits[1]) || y > double(m.terrain_limits[2]) || y < double(m.terrain_limits[3]);
+    f.out_of_bounds = out_of_bounds();
     return f;
+  }
+  // _check_out_of_terrain_bounds (quadruped_env.py:1250-1257) on the current base position
+  QS_DEV bool out_of_bounds() const {
+    const double x = w.org[0] + double(w.qpos[0]), y = w.org[1] + double(w.qpos[1]);
+    return x > double(m.terrain_limits[0]) || x < double(m.terrain_limits[1]) || y > double(m.terrain_limits[2]) || y < double(m.terrain_limits[3]);
   }
 
   // Packs the 227 ALL_OBS scalars into w.obs (layout: SURVEY.md section 8a). Mixed time levels as in the reference

@@ -350,11 +350,12 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     QS_MARK(1);
     e.forward_position();
     QS_MARK(2);
+    typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();  // contact masks depend on the collision stage only
     if (MODE == MODE_STEP && p.auto_reset && !resetting) {
       // Same-step auto-reset returns the post-reset state / observation of an env that terminates, so once the collision stage has
       // found a contact that terminates the episode (quadruped_env.py:1228-1248) the rest of this step cannot reach any output:
       // raise the flags, keep the IMU bias walk in step, and go straight to the reset pass.
-      if (e.flags().invalid_mask != 0) {
+      if (fl.invalid_mask != 0) {
         if (lane == 0) {
           if (p.reward) p.reward[env] = 0.f;
           if (p.terminated) p.terminated[env] = 1;
@@ -401,7 +402,6 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       e.forward_dynamics(p.max_iter, real(p.tol));
     }
 #endif
-    typename Env<real, NCON, MAXDIM>::Flags fl = e.flags();
 
     if (MODE == MODE_FORWARD) {
       if (lane < NV) B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     // ---- integrate, then env-side bookkeeping
     e.integrate(base64);
     QS_MARK(6);
-    fl.out_of_bounds = e.flags().out_of_bounds;  // bounds are tested on the post-step base position (:1252-1256)
+    fl.out_of_bounds = e.out_of_bounds();  // bounds are tested on the post-step base position (:1252-1256)
     const bool terminated = fl.invalid_mask != 0 || fl.out_of_bounds;
     sim_time += float(m.timestep);
     step_count = resetting ? 0 : step_count + 1;

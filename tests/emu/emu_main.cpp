@@ -51,7 +51,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       auto f = e.flags();
       if (mode == 1) {
         e.integrate(base64);
-        f.out_of_bounds = e.flags().out_of_bounds;
+        f.out_of_bounds = e.out_of_bounds();
         e.pack_obs(command, f.contact_mask);
       }
       if (mode == 2) {  // height map around the current base position / heading
