@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     // ---- write back
     {
       bool ok = true;
-      if (lane < NQ) ok = ok && isfinite(double(w.qpos[lane]));
-      if (lane < NV) ok = ok && isfinite(double(w.qvel[lane]));
+      if (lane < NQ) ok = ok && isfinite(w.qpos[lane]);
+      if (lane < NV) ok = ok && isfinite(w.qvel[lane]);
       if (qs::ballot(!ok) != 0) status |= 1u;
     }
     if (w.overflow) status |= 2u;
