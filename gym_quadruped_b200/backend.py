@@ -208,6 +208,8 @@ class BatchSim:
     def step_autoreset(self, ctrl: torch.Tensor, options: QsResetOptions | None = None):
         """`step` plus, in the same launch, a random reset of every env that just terminated (post-reset obs/state returned)."""
         o = options or self.reset_options
+        if ctrl.device != self.device or ctrl.dtype != torch.float32 or not ctrl.is_contiguous() or ctrl.shape != (self.N, 12):
+            ctrl = torch.as_tensor(ctrl, dtype=torch.float32, device=self.device).reshape(self.N, 12).contiguous()
         self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), self.obs.data_ptr(), self.reward.data_ptr(),
                                              self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated

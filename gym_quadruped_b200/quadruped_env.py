@@ -80,6 +80,7 @@ class QuadrupedEnv(Env):
         seed: int = 0,
         precision: str = 'fp32',
         env_id_offset: int = 0,
+        auto_reset: bool = False,
     ):
         self._init_args = dict(robot=robot, state_obs_names=state_obs_names, scene=scene, sim_dt=sim_dt,
                                base_vel_command_type=base_vel_command_type, ref_base_lin_vel=ref_base_lin_vel,
@@ -97,6 +98,9 @@ class QuadrupedEnv(Env):
         self.legs_order = tuple(legs_order)
         assert sorted(self.legs_order) == sorted(_MODEL_LEGS), f'legs_order must be a permutation of {_MODEL_LEGS}'
         self.is_paused = False
+        # batched extension: `step` resets, inside the same kernel launch, every env that terminates (same-step auto-reset: the
+        # returned observation of such an env is its post-reset one, `terminated` still flags the episode end)
+        self.auto_reset_on_step = bool(auto_reset)
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
 
@@ -177,7 +181,10 @@ class QuadrupedEnv(Env):
         """Apply joint torques, advance one sim step, return (obs, reward, terminated, truncated, info); :251-307."""
         if self.num_envs == 1:
             return self._step_single(action)
-        obs_t, rew, term, trunc = self.sim.step(action)
+        if self.auto_reset_on_step:
+            obs_t, rew, term, trunc = self.sim.step_autoreset(action)
+        else:
+            obs_t, rew, term, trunc = self.sim.step(action)
         for s in self.sensors:
             s.step()
         info_invalid = self.sim.invalid_body_mask

@@ -559,3 +559,20 @@ def test_slippery_strips_impose_their_own_contact_parameters(cuda_device):
             assert np.allclose(gc[feet, 18], fri[0], atol=1e-6) and (gc[feet, 19] == 3).all()
         else:
             assert np.allclose(gc[feet, 18], 0.5, atol=1e-6) and (gc[feet, 19] == 6).all()
+
+
+def test_quadruped_env_auto_reset_option(cuda_device):
+    """Batched extension: QuadrupedEnv(auto_reset=True) resets terminated envs inside the step launch (one kernel per step)."""
+    from gym_quadruped_b200.quadruped_env import QuadrupedEnv
+    env = QuadrupedEnv('mini_cheetah', state_obs_names=('qpos', 'qvel', 'contact_state'), ref_base_lin_vel=(0.5, 1.0),
+                       ground_friction_coeff=(0.2, 1.5), num_envs=512, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device='cpu').manual_seed(5)
+    n_term, launches0 = 0, env.sim.launch_count
+    for t in range(150):
+        obs, rew, term, trunc, info = env.step((torch.randn(512, 12, generator=g) * 50).to(cuda_device))
+        n_term += int(term.sum())
+        if term.any():  # an env that terminated has been reset in place: its step counter restarted, its state is finite and lifted
+            assert (env.sim.step_count[term] == 0).all() and torch.isfinite(obs['qpos'][term]).all()
+    assert n_term > 0 and env.sim.launch_count - launches0 == 150
+    env.close()
