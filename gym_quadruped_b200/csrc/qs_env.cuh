@@ -1111,8 +1111,8 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; cost += real(0.5) * Dk * r[k] * r[k]; d1 += Dk * r[k] * v[k]; d2 += Dk * v[k] * v[k]; }
       return;
     }
-    const real Dm = D0 / N::max(N::minval, mu * mu * (1 + mu * mu)), NmT = Nn - mu * T;
-    const real T1 = UV / T, T2d = VV / T - UV * UV / (T * T * T), e1 = N1 - mu * T1;
+    const real Dm = N::div(D0, N::max(N::minval, mu * mu * (1 + mu * mu))), NmT = Nn - mu * T;
+    const real T1 = N::div(UV, T), T2d = N::div(VV, T) - N::div(UV * UV, T * T * T), e1 = N1 - mu * T1;
     cost += real(0.5) * Dm * NmT * NmT;
     d1 += Dm * NmT * e1;
     d2 += Dm * (e1 * e1 - NmT * mu * T2d);
@@ -1160,17 +1160,17 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int k = 0; k < MAXDIM; k++) if (k < dim) { const real Dk = w.c_D[c][k]; F[k] = -Dk * r[k]; Wt[widx(k, k)] = Dk; cost += real(0.5) * Dk * r[k] * r[k]; }
       return cost;
     }
-    const real Dm = D0 / N::max(N::minval, mu * mu * (1 + mu * mu)), NmT = Nn - mu * T;
+    const real Dm = N::div(D0, N::max(N::minval, mu * mu * (1 + mu * mu))), NmT = Nn - mu * T;
     cost = real(0.5) * Dm * NmT * NmT;
     F[0] = -Dm * NmT * mu;
     real de[MAXDIM];
     de[0] = mu;
-    for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? -mu * fk[k] * U[k] / T : real(0); if (k < dim) F[k] = -F[0] / T * U[k] * fk[k]; }
+    for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? N::div(-mu * fk[k] * U[k], T) : real(0); if (k < dim) F[k] = N::div(-F[0], T) * U[k] * fk[k]; }
     for (int a = 0; a < MAXDIM; a++)
       for (int b = a; b < MAXDIM; b++) {
         if (a >= dim || b >= dim) continue;
         real h = Dm * de[a] * de[b];
-        if (a > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? 1 / T : real(0)) - U[a] * U[b] / (T * T * T));
+        if (a > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? N::div(real(1), T) : real(0)) - N::div(U[a] * U[b], T * T * T));
         Wt[widx(a, b)] = h;
       }
     return cost;
