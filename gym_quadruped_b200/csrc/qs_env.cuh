@@ -992,8 +992,9 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int k = 0; k < 3; k++) {
         real fr[3];
         frame_row(c, k, fr);
-        if (k < dim) w.Jc[c][k][col] = sg * dot3(fr, jp);
-        if (MAXDIM > 3 && 3 + k < dim) w.Jc[c][MAXDIM > 3 ? 3 + k : 0][col] = sg * dot3(fr, jr);
+        // rows beyond the contact's dimension are written as zeros so that the solver loop can run over all MAXDIM rows unguarded
+        w.Jc[c][k][col] = (k < dim) ? sg * dot3(fr, jp) : real(0);
+        if (MAXDIM > 3) w.Jc[c][MAXDIM > 3 ? 3 + k : 0][col] = (3 + k < dim) ? sg * dot3(fr, jr) : real(0);
       }
     }
     // scalar units
@@ -1185,13 +1186,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     const int ncon = w.ncon;
     for (int it = lane; it < ncon * MAXDIM; it += 32) {
       const int c = it / MAXDIM, k = it % MAXDIM, info = w.c_info[c], body = info_body(info);
-      real s = 0;
-      if (k < info_dim(info)) {
-        const real* J = w.Jc[c][k];
-        s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
-        if (body >= 2) { const real* xl = x + 6 + 3 * info_leg(info); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
-        if (minus_ar) s -= w.c_ar[c][k];
-      }
+      const real* J = w.Jc[c][k];  // rows >= dim hold zeros (and a zero reference acceleration)
+      real s = J[0] * x[0] + J[1] * x[1] + J[2] * x[2] + J[3] * x[3] + J[4] * x[4] + J[5] * x[5];
+      if (body >= 2) { const real* xl = x + 6 + 3 * info_leg(info); s += J[6] * xl[0] + J[7] * xl[1] + J[8] * xl[2]; }
+      if (minus_ar) s -= w.c_ar[c][k];
       out_c[c][k] = s;
     }
     syncwarp();
@@ -1246,7 +1244,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         const bool mine = !isleg || info_leg(info) == l;
         real t = 0;
 #pragma unroll
-        for (int a = 0; a < MAXDIM; a++) t += (a < dim) ? w.Jc[c][a][col] * w.c_F[c][a] : real(0);
+        for (int a = 0; a < MAXDIM; a++) t += w.Jc[c][a][col] * w.c_F[c][a];  // rows >= dim: zero Jacobian, zero force
         s += mine ? t : real(0);
       }
       w.fcon[d] = s;
