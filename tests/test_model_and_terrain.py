@@ -82,3 +82,37 @@ def test_qsmodel_struct_roundtrip():
     assert list(m.c.body_parent) == [0, 0, 1, 2, 3, 1, 5, 6, 1, 8, 9, 1, 11, 12]
     with pytest.raises(ValueError):
         Model('hyqreal', 'flat')  # the reference rejects this name too (robot_cfgs.py:49-58)
+
+
+def test_slippery_scene_and_new_robots_fill_the_model_struct():
+    m = Model('aliengo', 'slippery')
+    assert m.c.terrain_type == 2 and m.c.nbox == 2 and m.c.box_par.priority == 2 and m.c.box_par.condim == 3
+    assert list(m.c.box_friction[0]) == [0.03, 0.05, 0.07] and list(m.c.box_friction[1]) == [0.8, 0.2, 0.3]
+    assert tuple(m.c.terrain_limits) == FLAT_LIMITS
+    m = Model('aliengo', 'random_boxes')
+    assert m.c.box_par.priority == 0 and list(m.c.box_friction[5]) == [1.0, 0.005, 0.0001]
+    go1 = Model('go1', 'flat')
+    assert go1.c.ngeom == 42 and go1.c.cone == 1 and sorted(set(go1.c.geom_type[:42])) == [2, 3, 5, 6]  # sphere, capsule, cylinder, box
+    b2, spot, h2 = Model('b2', 'flat'), Model('spot', 'flat'), Model('hyqreal2', 'flat')
+    assert list(b2.c.geom_type[:b2.c.ngeom]).count(5) == 4 and spot.c.nvert > 1000 and spot.c.cone == 1
+    # hyqreal2.xml:36-51: joint-level actuatorfrcrange (150 / 250 / 350 N m) folded into the actuator force clamp
+    assert [h2.c.act_forcerange[a][1] for a in range(3)] == [150.0, 250.0, 350.0] and all(h2.c.act_forcelimited[a] for a in range(12))
+
+
+def test_fromto_capsules_of_go1_reproduce_their_end_points():
+    """go1.xml:47-59 gives its thigh / calf capsules as `fromto` segments; the compiler turns them into centre + half-length + a
+    frame whose z axis runs along from - to.  Rebuild the end points from the compiled tables."""
+    t = load_robot_tables('go1')
+    segs = {(-0.02, 0, 0, -0.02, 0, -0.16): 0.015, (0, 0, 0, -0.02, 0, -0.1): 0.015, (-0.02, 0, -0.16, 0, 0, -0.2): 0.015,
+            (0, 0, 0, 0.02, 0, -0.13): 0.01, (0.02, 0, -0.13, 0, 0, -0.2): 0.01}
+    found = 0
+    for g in t['geoms']:
+        if g['type'] != 3:
+            continue
+        q = np.array(g['quat']); w, x, y, z = q
+        zaxis = np.array([2 * (x * z + w * y), 2 * (y * z - w * x), w * w - x * x - y * y + z * z])
+        p1, p2 = np.array(g['pos']) + zaxis * g['size'][1], np.array(g['pos']) - zaxis * g['size'][1]
+        for seg, rad in segs.items():
+            if np.allclose(np.r_[p1, p2], seg, atol=1e-12) and abs(g['size'][0] - rad) < 1e-15:
+                found += 1
+    assert found == 20  # five segments on each of the four legs
