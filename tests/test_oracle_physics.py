@@ -236,3 +236,44 @@ def test_fk_known_answers_at_home_keyframes():
         np.testing.assert_allclose(fp[0], fl, atol=6e-4)
         np.testing.assert_allclose(fp[2], rl, atol=6e-4)
         np.testing.assert_allclose(fp[1], [fl[0], -fl[1], fl[2]], atol=6e-4)  # FR mirrors FL
+
+
+@pytest.mark.parametrize('roll,expect', [(0.0, 'side'), (np.pi / 2, 'cap')])
+def test_plane_cylinder_known_answers(roll, expect):
+    """Geometry of the plane-cylinder contacts (b2 hip cylinders, b2.xml:96: radius 0.07, half-length 0.025, axis along the hip's y):
+    lying on its side a cylinder touches along a line -> two contacts at the cap centres' projections, depth z_c - r; standing on a
+    cap -> three rim contacts 120 degrees apart, depth z_c - h."""
+    from oracle.oracle import F_XPOS
+    m = Model('b2', 'flat')
+    cyl = [g for g in range(m.c.ngeom) if m.c.geom_type[g] == 5]
+    g0 = cyl[0]
+    r, h = m.c.geom_size[g0][0], m.c.geom_size[g0][1]
+    gpos = np.array(m.c.geom_pos[g0]); body = m.c.geom_body[g0]
+    q = np.array(m.c.key_qpos); q[7:] = 0.0
+    q[3:7] = [np.cos(roll / 2), np.sin(roll / 2), 0, 0]
+    Rb = Rotation.from_quat(q[[4, 5, 6, 3]]).as_matrix()
+    o = Oracle(m)
+    # height at which the chosen cylinder penetrates the floor by 2 mm while (by symmetry) only hip cylinders can be lower
+    q[2] = 5.0
+    o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+    centre = o.get(F_XPOS)[body - 1] + Rb @ gpos
+    low = r if expect == 'side' else h
+    q[2] -= centre[2] - low + 0.002
+    o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+    centre = o.get(F_XPOS)[body - 1] + Rb @ gpos
+    c = o.get(F_CONTACTS)
+    mine = c[c[:, 16] == g0]
+    if expect == 'side':
+        assert len(mine) == 2
+        np.testing.assert_allclose(mine[:, 0], centre[2] - r, atol=1e-12)
+        axis = Rb @ np.array([0.0, 1.0, 0.0])  # geom quat (1,1,0,0)/sqrt2 turns the cylinder's z onto the body's -y / +y line
+        along = np.sort((mine[:, 1:4] - centre) @ axis)
+        np.testing.assert_allclose(along, [-h, h], atol=1e-12)
+    else:
+        assert len(mine) == 3
+        np.testing.assert_allclose(mine[:, 0], centre[2] - h, atol=1e-12)
+        rel = mine[:, 1:3] - centre[:2]
+        np.testing.assert_allclose(np.linalg.norm(rel, axis=1), r, atol=1e-12)
+        ang = np.sort(np.mod(np.arctan2(rel[:, 1], rel[:, 0]), 2 * np.pi))
+        np.testing.assert_allclose(np.diff(ang), [2 * np.pi / 3] * 2, atol=1e-9)
+    np.testing.assert_allclose(mine[:, 4:7], [[0, 0, 1]] * len(mine), atol=1e-15)  # contact normal = plane normal
