@@ -277,3 +277,43 @@ def test_plane_cylinder_known_answers(roll, expect):
         ang = np.sort(np.mod(np.arctan2(rel[:, 1], rel[:, 0]), 2 * np.pi))
         np.testing.assert_allclose(np.diff(ang), [2 * np.pi / 3] * 2, atol=1e-9)
     np.testing.assert_allclose(mine[:, 4:7], [[0, 0, 1]] * len(mine), atol=1e-15)  # contact normal = plane normal
+
+
+def _sliding_deceleration(x0, v0):
+    m = Model('aliengo', 'slippery')
+    o = Oracle(m)
+    key = np.array(m.c.key_qpos)
+    q = key.copy(); q[0] = x0; q[1] = 0.0
+    for z in np.arange(0.6, 0.2, -0.001):  # lower the robot until its feet touch the strip
+        q[2] = z
+        o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+        if o.flags()['contact_state'].all():
+            break
+    o.set_env(0.5, 0.5, [0, 0, 0, 0])  # friction override of feet / floor: must not matter on the strip
+    kp, kd = 400.0, 20.0
+    for _ in range(600):  # come to rest under a PD hold
+        qq, v, _, _ = o.get_state()
+        o.step(kp * (key[7:] - qq[7:]) - kd * v[6:])
+    qq, v, _, w = o.get_state()
+    v = v.copy(); v[0] = v0
+    o.set_state(qq, v, w)
+    vs = []
+    for _ in range(60):
+        qq, v, _, _ = o.get_state()
+        o.step(kp * (key[7:] - qq[7:]) - kd * v[6:])
+        vs.append(o.get_state()[1][0])
+    vs = np.array(vs)
+    moving = vs > 0.05
+    assert moving.sum() >= 15
+    t = 0.002 * np.arange(1, len(vs) + 1)
+    return -np.polyfit(t[moving], vs[moving], 1)[0]
+
+
+def test_sliding_on_the_slippery_strips_follows_each_strip_s_friction():
+    """scene_slippery.xml:39-40: a robot held by a PD controller and pushed along a priority-2 strip is decelerated by the strip's own
+    friction coefficient, whatever the feet's / floor's coefficient is set to: mu * g on the 0.03 strip (rigid sliding), and more than
+    ten times that on the 0.8 strip (where the legs give way before the feet slide, so only the order of magnitude is asserted)."""
+    slow = _sliding_deceleration(12.0, 0.3)
+    fast = _sliding_deceleration(2.0, 0.4)
+    assert slow == pytest.approx(0.03 * 9.81, rel=0.2), slow
+    assert fast > 10 * slow, (fast, slow)
