@@ -317,3 +317,58 @@ def test_sliding_on_the_slippery_strips_follows_each_strip_s_friction():
     fast = _sliding_deceleration(2.0, 0.4)
     assert slow == pytest.approx(0.03 * 9.81, rel=0.2), slow
     assert fast > 10 * slow, (fast, slow)
+
+
+def _fk_numpy(t, q):
+    """Independent forward kinematics from the compiled tables: world rotation / position of bodies 1..13."""
+    Rw = {0: np.eye(3)}; pw = {0: np.zeros(3)}
+    for b in range(1, 14):
+        if b == 1:
+            Rw[1] = Rotation.from_quat(np.array(q[3:7])[[1, 2, 3, 0]]).as_matrix(); pw[1] = np.array(q[:3])
+            continue
+        p = t['body_parent'][b]
+        R0 = Rw[p] @ Rotation.from_quat(np.array(t['body_quat'][b])[[1, 2, 3, 0]]).as_matrix()
+        j = b - 2
+        ang = q[7 + j] - t['qpos0'][7 + j]
+        Rw[b] = R0 @ Rotation.from_rotvec(ang * np.array(t['jnt_axis'][j])).as_matrix()
+        pw[b] = pw[p] + Rw[p] @ np.array(t['body_pos'][b])
+    return Rw, pw
+
+
+def test_plane_primitive_colliders_against_independent_geometry():
+    """Every floor contact of aliengo (spheres, capsules, boxes) in a tilted, half-sunk pose must be one of the analytic candidates --
+    sphere: z_c - r; capsule: end-sphere centres z - r; box: corner heights -- computed here with a separate numpy FK, and every
+    candidate within the margin must appear (boxes: at most four per geom)."""
+    m = Model('aliengo', 'flat')
+    t = m.tables
+    q = np.array(m.c.key_qpos); q[2] = 0.16
+    q[3:7] = Rotation.from_euler('xyz', [0.5, 0.3, 0.7]).as_quat()[[3, 0, 1, 2]]
+    q[7:] += np.random.RandomState(1).uniform(-0.3, 0.3, 12)
+    o = Oracle(m)
+    o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+    c = o.get(F_CONTACTS)
+    Rw, pw = _fk_numpy(t, q)
+    expected = {}
+    for g, geom in enumerate(t['geoms']):
+        b = geom['body']
+        Rg = Rw[b] @ Rotation.from_quat(np.array(geom['quat'])[[1, 2, 3, 0]]).as_matrix()
+        cg = pw[b] + Rw[b] @ np.array(geom['pos'])
+        sz, margin = geom['size'], geom['margin']
+        if geom['type'] == 2:
+            cand = [cg[2] - sz[0]]
+        elif geom['type'] == 3:
+            cand = [(cg + s * Rg[:, 2] * sz[1])[2] - sz[0] for s in (1, -1)]
+        elif geom['type'] == 6:
+            cand = [(cg + Rg @ (np.array(sz) * np.array([sx, sy, sz_])))[2] for sx in (-1, 1) for sy in (-1, 1) for sz_ in (-1, 1)]
+            cand = [d for d in cand if d - cg[2] <= 0]   # only corners below the box centre are tested by the engine's routine
+        else:
+            continue
+        expected[g] = sorted(d for d in cand if d <= margin)
+    assert len(c) >= 6
+    for g in set(c[:, 16].astype(int)) | {g for g, e in expected.items() if e}:
+        got = np.sort(c[c[:, 16] == g][:, 0])
+        exp = np.array(expected[g])
+        if t['geoms'][g]['type'] == 6:
+            assert len(got) == min(4, len(exp)) and all(np.abs(exp - d).min() < 1e-12 for d in got), g
+        else:
+            np.testing.assert_allclose(got, exp, atol=1e-12, err_msg=f'geom {g}')
