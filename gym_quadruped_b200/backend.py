@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from .model import (QS_CONTACT_STRIDE, QS_NOBS_BASE, QS_NOBS_IMU, Model, QsBuffers, QsConfig, QsModel, QsResetOptions)
+from .model import (QS_CONTACT_STRIDE, QS_NOBS_BASE, QS_NOBS_IMU, Model, QsBuffers, QsConfig, QsModel, QsResetOptions, QsSchedule)
 
 import os
 
@@ -53,6 +53,10 @@ def load_library() -> C.CDLL:
     L.qs_last_error.argtypes = [vp]
     L.qs_last_error.restype = C.c_char_p
     L.qs_bind.argtypes = [vp, C.POINTER(QsBuffers)]
+    L.qs_set_schedule.argtypes = [vp, C.POINTER(QsSchedule), vp]
+    L.qs_set_seed.argtypes = [vp, C.c_uint64, vp]
+    L.qs_step_variant.argtypes = [vp]
+    L.qs_step_variant.restype = C.c_char_p
     L.qs_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.qs_step_host.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
     L.qs_step_autoreset.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
@@ -95,7 +99,7 @@ class BatchSim:
 
     def __init__(self, model: Model, num_envs: int, device: int | str | torch.device = 0, precision: int = 0,
                  use_imu: bool = False, imu_noise=(0.01, 0.01, 0.01, 0.01), seed: int = 0, env_id_offset: int = 0,
-                 solver_max_iter: int = 0, heightmap: tuple | None = None):
+                 solver_max_iter: int = 0, heightmap: tuple | None = None, pipeline: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError('gym_quadruped_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
         self.L = load_library()
@@ -111,6 +115,8 @@ class BatchSim:
             raise ValueError(f'robot {model.robot} has no accelerometer/gyro pair in its model')
         cfg.imu_accel_noise, cfg.imu_gyro_noise, cfg.imu_accel_bias_rate, cfg.imu_gyro_bias_rate = [float(x) for x in imu_noise]
         cfg.seed, cfg.env_id_offset, cfg.solver_max_iter = int(seed), int(env_id_offset), int(solver_max_iter)
+        # pipeline=True: back-to-back step launches overlap on the device (see QsConfig.pipeline in include/qstep.h for the contract)
+        cfg.pipeline = int(bool(pipeline))
         if heightmap is not None:  # (rows, cols, dx, dy): appended to every observation row
             cfg.hm_rows, cfg.hm_cols, cfg.hm_dx, cfg.hm_dy = int(heightmap[0]), int(heightmap[1]), float(heightmap[2]), float(heightmap[3])
         self.cfg = cfg
@@ -138,9 +144,16 @@ class BatchSim:
         self.ncon = torch.zeros(N, dtype=torch.int32, device=dev)
         self.solver_iter = torch.zeros(N, dtype=torch.int32, device=dev)
         self.invalid_body_mask = torch.zeros(N, 2, dtype=torch.uint8, device=dev)
+        # in-episode schedules (quadruped_env.py:293-305), advanced inside the step kernel
+        self.cmd_count = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.cmd_limit = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.ext_count = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.ext_limit = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.ext_wrench = torch.zeros(N, 6, **f32)
         b = QsBuffers()
         for name in ('qpos', 'qvel', 'qacc', 'qacc_warmstart', 'base_pos64', 'qfrc_applied', 'command', 'friction', 'sim_time',
-                     'step_count', 'imu_bias', 'status', 'ncon', 'solver_iter', 'invalid_body_mask'):
+                     'step_count', 'imu_bias', 'status', 'ncon', 'solver_iter', 'invalid_body_mask', 'cmd_count', 'cmd_limit',
+                     'ext_count', 'ext_limit', 'ext_wrench'):
             setattr(b, name, getattr(self, name).data_ptr())
         self._buffers = b
         self._check(self.L.qs_bind(self.h, C.byref(b)))
@@ -175,6 +188,29 @@ class BatchSim:
     def launch_count(self) -> int:
         return int(self.L.qs_launch_count(self.h))
 
+    @property
+    def step_variant(self) -> str:
+        """Name of the compiled kernel variant that `step` launches (csrc/qs_variants.h)."""
+        return self.L.qs_step_variant(self.h).decode()
+
+    def set_seed(self, seed: int):
+        """`np.random.seed(seed)` equivalent: new key, per-env draw counters restarted; no buffer is touched."""
+        self._check(self.L.qs_set_seed(self.h, C.c_uint64(int(seed)), self._stream()))
+
+    def set_schedule(self, command_mode: int = 0, lin_vel_range=(0.0, 0.0), ang_vel_range=(0.0, 0.0), ext_ranges: dict | None = None,
+                     ext_enabled: bool = False):
+        """Install the in-kernel schedules: '+reset' command resampling (quadruped_env.py:293-296) and the external base wrench
+        (external_disturbances_kwargs, :299-305).  `ext_ranges` maps 'x','y','z','roll','pitch','yaw' to a 1- or 2-element range."""
+        sc = QsSchedule()
+        sc.command_mode, sc.ext_enabled = int(command_mode), int(bool(ext_enabled))
+        sc.lin_vel_range[:] = [float(x) for x in lin_vel_range]
+        sc.ang_vel_range[:] = [float(x) for x in ang_vel_range]
+        for k, key in enumerate(('x', 'y', 'z', 'roll', 'pitch', 'yaw')):
+            r = (ext_ranges or {}).get(key)
+            lo, hi = (0.0, 0.0) if r is None else ((float(r[0]), float(r[0])) if len(r) == 1 else (float(r[0]), float(r[1])))
+            sc.ext_lo[k], sc.ext_hi[k] = lo, hi
+        self._check(self.L.qs_set_schedule(self.h, C.byref(sc), self._stream()))
+
     def make_reset_options(self, randomize=True, angle_sweep=20 * math.pi / 180, roll_sweep=10 * math.pi / 180,
                            pitch_sweep=10 * math.pi / 180, lin_vel_range=(0.5, 0.5), ang_vel_range=(0.0, 0.0),
                            friction_range=(1.0, 1.0), command_mode=CMD_FORWARD) -> QsResetOptions:
@@ -197,10 +233,15 @@ class BatchSim:
         self.qvel[idx] = torch.as_tensor(qvel, device=self.device).to(torch.float32)
 
     # ------------------------------------------------------------------ hot path
+    def _as_ctrl(self, ctrl) -> torch.Tensor:
+        if (not isinstance(ctrl, torch.Tensor) or ctrl.device != self.device or ctrl.dtype != torch.float32 or not ctrl.is_contiguous()
+                or ctrl.shape != (self.N, 12)):
+            ctrl = torch.as_tensor(ctrl, dtype=torch.float32, device=self.device).reshape(self.N, 12).contiguous()
+        return ctrl
+
     def step(self, ctrl: torch.Tensor):
         """One fused kernel launch: ctrl [N,12] (cuda fp32, contiguous) -> obs [N,D], reward, terminated, truncated."""
-        if ctrl.device != self.device or ctrl.dtype != torch.float32 or not ctrl.is_contiguous() or ctrl.shape != (self.N, 12):
-            ctrl = torch.as_tensor(ctrl, dtype=torch.float32, device=self.device).reshape(self.N, 12).contiguous()
+        ctrl = self._as_ctrl(ctrl)
         self._check(self.L.qs_step(self.h, ctrl.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
                                    self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated
@@ -208,8 +249,7 @@ class BatchSim:
     def step_autoreset(self, ctrl: torch.Tensor, options: QsResetOptions | None = None):
         """`step` plus, in the same launch, a random reset of every env that just terminated (post-reset obs/state returned)."""
         o = options or self.reset_options
-        if ctrl.device != self.device or ctrl.dtype != torch.float32 or not ctrl.is_contiguous() or ctrl.shape != (self.N, 12):
-            ctrl = torch.as_tensor(ctrl, dtype=torch.float32, device=self.device).reshape(self.N, 12).contiguous()
+        ctrl = self._as_ctrl(ctrl)
         self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), self.obs.data_ptr(), self.reward.data_ptr(),
                                              self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated

@@ -95,10 +95,31 @@ template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
   real sens[8], sens_tmp[24];
 };
 
-template <typename real, int NCON, int MAXDIM> struct Env {
+// Compile-time feature switches of a kernel variant.  A set bit asserts a property of the robot / scene / configuration that the host
+// has checked (qstep.cu: model_features), so the code for everything else is not generated at all: the cfg2 step kernel
+// (mini_cheetah / flat) carries no elliptic-cone, terrain, capsule / box / cylinder, joint-limit, IMU or ray-cast code.  FEAT = 0 is
+// the generic variant that decides everything at run time; every variant produces bit-identical results on a model it admits.
+enum : int {
+  FEAT_PYR = 1, FEAT_ELL = 2,                       // friction cone known (neither: read from the model)
+  FEAT_FLAT = 4, FEAT_HFIELD = 8, FEAT_BOXES = 16,  // scene known: floor plane only / + height field / + static boxes
+  FEAT_NO_IMU = 32,                                 // no accelerometer / gyro columns requested: the sensor stage is dropped
+  FEAT_NO_MESH = 64, FEAT_NO_CAPSULE = 128, FEAT_NO_BOX = 256, FEAT_NO_CYL = 512,  // robot geom types that do not occur
+  FEAT_NGEOM32 = 1024,                              // at most 32 robot collision geoms: a single lane round
+  FEAT_NO_LIMITS = 2048,                            // no limited joint
+  FEAT_NO_HM = 4096,                                // no fused height-map columns
+};
+// the specialised step kernels that are compiled (qs_variants.h): one per BASELINE configuration
+constexpr int FEAT_CFG2 = FEAT_PYR | FEAT_FLAT | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_CAPSULE | FEAT_NO_BOX | FEAT_NO_CYL | FEAT_NGEOM32 | FEAT_NO_LIMITS;  // mini_cheetah / flat
+constexpr int FEAT_CFG3 = FEAT_PYR | FEAT_HFIELD | FEAT_NO_IMU | FEAT_NO_MESH | FEAT_NO_CYL | FEAT_NGEOM32;                                              // aliengo / perlin (+ height map)
+constexpr int FEAT_CFG4 = FEAT_ELL | FEAT_BOXES | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_MESH | FEAT_NO_CYL | FEAT_NGEOM32;                                 // go2 / random_boxes
+constexpr int FEAT_CFG5 = FEAT_ELL | FEAT_FLAT | FEAT_NO_HM | FEAT_NO_CAPSULE | FEAT_NO_BOX | FEAT_NO_CYL | FEAT_NGEOM32;                               // hyqreal1 / flat (+ IMU)
+
+template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   using N = Num<real>;
   using W = WS<real, NCON, MAXDIM>;
   static constexpr int NW = W::NW;
+  static constexpr bool kLimits = !(FEAT & FEAT_NO_LIMITS);
+  static constexpr int NSC = kLimits ? NFL + NLIM : NFL;  // scalar constraint units in use
   const DModel<real>& m;
   W& w;
   const Vert4<real>* vert;
@@ -133,13 +154,19 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV static int tri_dof_leg(int t) { return (t >> 16) & 3; }
   QS_DEV static int tri_dof_k(int t) { return (t >> 18) & 3; }
 
-  // QS_FORCE_PYR (experiment / pyramidal-only builds): the cone type becomes a compile-time constant and the elliptic code disappears
-  QS_DEV bool cone_is_pyramidal() const {
-#ifdef QS_FORCE_PYR
-    return true;
-#else
-    return m.cone == 0;
-#endif
+  QS_DEV bool cone_is_pyramidal() const { return (FEAT & FEAT_PYR) ? true : ((FEAT & FEAT_ELL) ? false : m.cone == 0); }
+  QS_DEV int ttype() const { return (FEAT & FEAT_FLAT) ? 0 : ((FEAT & FEAT_HFIELD) ? 1 : ((FEAT & FEAT_BOXES) ? 2 : m.terrain_type)); }
+  QS_DEV bool has_imu() const { return (FEAT & FEAT_NO_IMU) ? false : m.has_imu != 0; }
+  // robot geom type t can occur in this variant
+  QS_DEV static constexpr bool type_on(int t) {
+    return t == GEOM_MESH ? !(FEAT & FEAT_NO_MESH) : (t == GEOM_CAPSULE ? !(FEAT & FEAT_NO_CAPSULE) : (t == GEOM_BOX ? !(FEAT & FEAT_NO_BOX)
+         : (t == GEOM_CYLINDER ? !(FEAT & FEAT_NO_CYL) : true)));
+  }
+  unsigned cm_acc = 0, im_acc = 0;  // per-lane share of the contact / invalid-contact body masks, collected when a contact is DETECTED
+                                    // (before the NCON cap), so that termination stays exact even if the contact buffer overflows
+  QS_DEV void note_contact(int g) {
+    const int b = m.geom_body[g];
+    if (b >= 2 && (b - 2) % 3 == 2) cm_acc |= 1u << ((b - 2) / 3); else im_acc |= 1u << b;
   }
   bool terrain_on = true;  // false: the base is out of reach of everything but the floor plane (internal frame re-centred like 'flat')
   bool calf_only = false;  // collision stage restricted to the calf-body geoms (the reset lift loop looks at nothing else)
@@ -339,7 +366,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       real ca[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
       for (int d = 3; d < 6; d++) for (int i = 0; i < 6; i++) ca[i] += w.tmp.cdofdot[d][i] * w.qvel[d];
       for (int t = 0; t <= k; t++) { const int d = 6 + 3 * l + t; for (int i = 0; i < 6; i++) ca[i] += w.tmp.cdofdot[d][i] * w.qvel[d]; }
-      if (lane == 0 && m.has_imu) {
+      if (lane == 0 && has_imu()) {
         // IMU pre-computation (everything except the cdof*qacc term), kept because kin/tmp storage is recycled by the solver
         real* st = w.sens_tmp;
         for (int i = 0; i < 6; i++) { st[i] = cv[i]; st[6 + i] = ca[i]; }
@@ -554,7 +581,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // ------------------------------------------------------------------ collision with the terrain
   // wg: world geom of the contact (WG_FLOOR, WG_HFIELD, or the index of a static box)
   enum { WG_FLOOR = -1, WG_HFIELD = -2 };
-  QS_DEV void contact_friction(int g, int wg, real* fri) const {
+  QS_DEV static void contact_friction(const W& w, const DModel<real>& m, const DBox<real>* boxes, int g, int wg, real* fri) {
     const bool world_is_floor = wg == WG_FLOOR;
     real gf[3] = {m.geom_fri[g][0], m.geom_fri[g][1], m.geom_fri[g][2]};
     if (m.geom_leg[g] >= 0 && w.mu_feet >= 0) { gf[0] = w.mu_feet; gf[1] = real(0.005); gf[2] = 0; }   // quadruped_env.py:1290-1296
@@ -568,14 +595,21 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     }
   }
 
-  // store one contact (called by a single lane); normal given, yhint optional second-axis guess
+  // store one contact (called by a single lane); normal given, yhint optional second-axis guess.  One shared out-of-line body
+  // (scalar arguments, no `this`): the three collider stages that call it would otherwise each inline ~1.1 k instructions that
+  // run a handful of times per env-step.
   QS_DEV void store_contact(int slot, int g, real sign, real dist, const real* pos, const real* normal, const real* yhint, int wg) {
+    store_contact_impl(w, m, boxes, slot, g, sign, dist, pos[0], pos[1], pos[2], normal[0], normal[1], normal[2], yhint ? yhint[0] : real(0),
+                       yhint ? yhint[1] : real(0), yhint ? yhint[2] : real(0), wg);
+  }
+  QS_NOINLINE static void store_contact_impl(W& w, const DModel<real>& m, const DBox<real>* boxes, int slot, int g, real sign, real dist, real px,
+                                             real py, real pz, real nx, real ny, real nz, real yx, real yy, real yz, int wg) {
     w.c_dist[slot] = dist; w.c_sign[slot] = sign;
     const bool tw = wg >= 0 && m.terr_wins;
     const int gb = m.geom_body[g], gleg = gb >= 2 ? (gb - 2) / 3 : 7;
     w.c_info[slot] = g | (gb << 8) | ((tw ? m.terr_dim : m.geom_dim[g]) << 16) | (gleg << 24) | (tw ? (1 << 27) : 0);
-    real f[6];
-    for (int i = 0; i < 3; i++) { w.c_pos[slot][i] = pos[i]; f[i] = normal[i]; f[3 + i] = yhint ? yhint[i] : real(0); }
+    real f[6] = {nx, ny, nz, yx, yy, yz};
+    w.c_pos[slot][0] = px; w.c_pos[slot][1] = py; w.c_pos[slot][2] = pz;
     // [MJ] mju_makeFrame (third axis = normal x second axis, rebuilt on demand)
     if (dot3(f + 3, f + 3) < real(0.25)) { f[3] = f[4] = f[5] = 0; if (f[1] < real(0.5) && f[1] > real(-0.5)) f[4] = 1; else f[5] = 1; }
     real dd = dot3(f, f + 3);
@@ -584,7 +618,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     for (int i = 0; i < 3; i++) f[3 + i] *= inv;
     for (int i = 0; i < 6; i++) w.c_frame[slot][i] = f[i];
     real fri[3];
-    contact_friction(g, wg, fri);
+    contact_friction(w, m, boxes, g, wg, fri);
     for (int i = 0; i < 3; i++) w.c_fri[slot][i] = fri[i];
   }
   // row k (0 normal, 1, 2 tangents) of the contact frame
@@ -630,7 +664,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // point feature (centre p, radius r) against the height field or the candidate boxes; robot_first: sphere / capsule sort
   // before box in the engine's geom ordering, so the robot geom is geom1 and the normal points from it into the box
   QS_DEV void point_vs_terrain(const real* p, real r, real margin, bool robot_first, const unsigned* boxmask, Cand* list, int& n) const {
-    if (m.terrain_type == 1) {
+    if (ttype() == 1) {
       real z, nn[3];
       if (!hfield_height(p[0], p[1], z, nn)) return;
       const real dist = (p[2] - z) * nn[2] - r;
@@ -639,7 +673,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       c.dist = dist; c.sign = 1; c.wg = WG_HFIELD;
       for (int i = 0; i < 3; i++) { c.nrm[i] = nn[i]; c.pos[i] = p[i] - nn[i] * (r + real(0.5) * dist); }
       cand_insert(list, n, c);
-    } else if (m.terrain_type == 2) {
+    } else if (ttype() == 2) {
       for (int wd = 0; wd < 4; wd++) {
         unsigned mask = boxmask[wd];
         while (mask) {
@@ -681,7 +715,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // box-box and prism-based hfield routines otherwise (documented in DESIGN.md).  Appends after the floor contacts.
   QS_DEV void collide_terrain(int& ncon, const int gbase) {
     unsigned boxmask[4] = {0, 0, 0, 0};
-    if (m.terrain_type == 2) {
+    if (ttype() == 2) {
       for (int wd = 0; wd < 4; wd++) {
         const int b = 32 * wd + lane;
         bool near = false;
@@ -705,7 +739,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       for (int i = 0; i < 3; i++) gx[i] = w.kin.xpos[b][i] + tmp[i];
       const real margin = N::max(m.geom_margin[g], m.terr_margin);
       const real* sz = m.geom_size[g];
-      if (m.terrain_type == 2) {
+      if (ttype() == 2) {
         // per-geom cull of the warp-wide candidate set: bounding sphere of the geom against the bounding sphere of each box
         // (a superset of what the per-feature test below accepts, so the contact set is unchanged)
         const real rb = m.geom_rbound[g] + margin + real(0.01);
@@ -724,7 +758,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       }
       if (type == GEOM_SPHERE) {
         point_vs_terrain(gx, sz[0], margin, true, boxmask, list, n);
-      } else if (type == GEOM_CAPSULE) {
+      } else if (type_on(GEOM_CAPSULE) && type == GEOM_CAPSULE) {
         real gz[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]}, axis[3];
         mul_mv(axis, w.kin.xmat[b], gz);
         for (int i = 0; i < 3; i++) yh[i] = axis[i];
@@ -733,7 +767,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           const real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
           point_vs_terrain(p, sz[0], margin, true, boxmask, list, n);
         }
-      } else if (type == GEOM_BOX || type == GEOM_CYLINDER) {
+      } else if ((type_on(GEOM_BOX) && type == GEOM_BOX) || (type_on(GEOM_CYLINDER) && type == GEOM_CYLINDER)) {
         // box corners / eight cylinder rim points (four per cap) as point features
         real gm[9];
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.kin.xmat[b][3 * r] * m.geom_mat[g][c] + w.kin.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.kin.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
@@ -753,6 +787,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const unsigned mask = ballot(has);
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
+      if (has) note_contact(g);
       if (has && slot < NCON) store_contact(slot, g, list[r].sign, list[r].dist, list[r].pos, list[r].nrm, is_caps ? yh : nullptr, list[r].wg);
       ncon += popc(mask);
     }
@@ -762,10 +797,10 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   QS_DEV real ray_down(const real* org) const {
     real best = org[2] >= 0 ? org[2] : real(-1);  // floor plane z = 0
     if (!terrain_on) return best;
-    if (m.terrain_type == 1) {
+    if (ttype() == 1) {
       real z, nn[3];
       if (hfield_height(org[0], org[1], z, nn) && org[2] >= z) { const real t = org[2] - z; if (best < 0 || t < best) best = t; }
-    } else if (m.terrain_type == 2) {
+    } else if (ttype() == 2) {
       for (int b = 0; b < m.nbox; b++) {
         const DBox<real>& bx = boxes[b];
         const real rel[3] = {org[0] - bx.pos[0], org[1] - bx.pos[1], org[2] - bx.pos[2]};
@@ -808,9 +843,13 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
   QS_DEV void collide_floor() {
     int ncon = 0;
+    cm_acc = im_acc = 0;
     // one lane per geom; robots with more than 32 collision geoms (go1: 42) take a second round
+    if (FEAT & FEAT_NGEOM32) collide_round(0, ncon);
+    else {
 #pragma unroll 1
-    for (int gbase = 0; gbase < m.ngeom; gbase += 32) collide_round(gbase, ncon);
+      for (int gbase = 0; gbase < m.ngeom; gbase += 32) collide_round(gbase, ncon);
+    }
     if (lane == 0) { w.overflow = ncon > NCON; w.ncon = ncon > NCON ? NCON : ncon; }
     syncwarp();
   }
@@ -831,7 +870,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (type == GEOM_SPHERE) {
         real dist = gx[2] - sz[0];
         if (!(dist > margin)) { cd[0] = dist; cp[0][0] = gx[0]; cp[0][1] = gx[1]; cp[0][2] = gx[2] - (sz[0] + real(0.5) * dist); nc = 1; }
-      } else if (type == GEOM_CAPSULE) {
+      } else if (type_on(GEOM_CAPSULE) && type == GEOM_CAPSULE) {
         // capsule axis = third column of (R_body * R_geom)
         real gz[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]}, axis[3];
         mul_mv(axis, w.kin.xmat[b], gz);
@@ -842,7 +881,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
           if (dist > margin) continue;
           cd[nc] = dist; cp[nc][0] = p[0]; cp[nc][1] = p[1]; cp[nc][2] = p[2] - (sz[0] + real(0.5) * dist); nc++;
         }
-      } else if (type == GEOM_CYLINDER) {
+      } else if (type_on(GEOM_CYLINDER) && type == GEOM_CYLINDER) {
         // [MJ] mjc_PlaneCylinder: nearest rim point of the lower cap, its twin on the other cap, two more lower-rim points at +-120 deg
         real gxa[3] = {m.geom_mat[g][0], m.geom_mat[g][3], m.geom_mat[g][6]}, gza[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]};
         real xax[3], axis[3], vec[3];
@@ -876,7 +915,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
             }
           }
         }
-      } else if (type == GEOM_BOX) {
+      } else if (type_on(GEOM_BOX) && type == GEOM_BOX) {
         real gm[9];
         for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gm[3 * r + c] = w.kin.xmat[b][3 * r] * m.geom_mat[g][c] + w.kin.xmat[b][3 * r + 1] * m.geom_mat[g][3 + c] + w.kin.xmat[b][3 * r + 2] * m.geom_mat[g][6 + c];
         for (int i = 0; i < 8; i++) {
@@ -897,17 +936,18 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
       if (has) {
+        note_contact(g);
         if (slot < NCON) store_contact(slot, g, real(1), cd[r], cp[r], nrm, (m.geom_type[g] == GEOM_CAPSULE) ? yh : nullptr, WG_FLOOR);
       }
       ncon += popc(mask);
     }
-    if (m.terrain_type != 0 && terrain_on) collide_terrain(ncon, gbase);
+    if (ttype() != 0 && terrain_on) collide_terrain(ncon, gbase);
     // convex meshes. Broad phase: lanes test the body-frame bounding box of every mesh against the plane (a lower bound of the
     // hull's lowest point, tight for long thin links); only the survivors are scanned, by the whole warp, for their support vertex.
-    unsigned cand;
-    {
+    unsigned cand = 0;
+    if (type_on(GEOM_MESH)) {
       bool near = false;
-      if (geom_on(g) && m.geom_type[g] == GEOM_MESH) {
+      if (type_on(GEOM_MESH) && geom_on(g) && m.geom_type[g] == GEOM_MESH) {
         const int b = m.geom_body[g];
         const real* R = w.kin.xmat[b];
         const real cz = w.kin.xpos[b][2] + R[6] * m.geom_bcenter[g][0] + R[7] * m.geom_bcenter[g][1] + R[8] * m.geom_bcenter[g][2];
@@ -942,6 +982,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
                           w.kin.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};
       const real dist = pw[2];
       if (dist > margin) continue;
+      note_contact(gm_);
       if (lane == 0 && ncon < NCON) {
         const real pos[3] = {pw[0], pw[1], pw[2] - real(0.5) * dist};
         store_contact(ncon, gm_, real(1), dist, pos, nrm, nullptr, WG_FLOOR);
@@ -1003,7 +1044,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       w.u_D[lane] = m.dof_floss[d] > 0 ? m.dof_D[d] : real(0);
       w.u_sign[lane] = 1;
       w.u_ar[lane] = -m.dof_B[d] * w.qvel[d];
-    } else if (lane < NFL + NLIM) {
+    } else if (kLimits && lane < NFL + NLIM) {
       const int j = lane - NFL;
       real D = 0, ar = 0, sign = 0;
       if (m.jnt_limited[j]) {
@@ -1179,7 +1220,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
 
   // J x for every unit: out_u[] (scalar units) and out_c[][] (contacts). x in shared memory. minus_ar: subtract reference.
   QS_DEV void units_Jx(const real* x, real* out_u, real (*out_c)[MAXDIM], bool minus_ar) {
-    if (lane < NFL + NLIM) {
+    if (lane < NSC) {
       const int d = 6 + (lane < NFL ? lane : lane - NFL);
       out_u[lane] = w.u_sign[lane] * x[d] - (minus_ar ? w.u_ar[lane] : real(0));
     }
@@ -1198,7 +1239,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // constraint cost at the current residuals (no side effects); warp-uniform result
   QS_DEV real units_cost() {
     real cost = 0, d1 = 0, d2 = 0;
-    if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane], real(0), cost, d1, d2);
+    if (lane < NSC) scalar_unit_eval(lane, w.u_r[lane], real(0), cost, d1, d2);
     real zero[MAXDIM];
     for (int k = 0; k < MAXDIM; k++) zero[k] = 0;
     static_assert(NCON <= 32, "one lane per contact");
@@ -1211,7 +1252,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // states / forces / weights at the current residuals (w.u_r, w.c_r); returns this lane's share of the constraint cost
   QS_DEV real units_update() {
     real cost = 0;
-    if (lane < NFL + NLIM) {
+    if (lane < NSC) {
       const int u = lane;
       const real x = w.u_r[u], D = w.u_D[u];
       real F = 0, Wt = 0;
@@ -1237,7 +1278,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       const int d = lane;
       const bool isleg = d >= 6;
       const int l = dof_leg(), k = dof_k(), col = isleg ? 6 + k : d, j = isleg ? d - 6 : 0;
-      real s = isleg ? w.u_F[j] + w.u_sign[NFL + j] * w.u_F[NFL + j] : real(0);
+      real s = isleg ? w.u_F[j] + (kLimits ? w.u_sign[NFL + j] * w.u_F[NFL + j] : real(0)) : real(0);
       const int ncon = w.ncon;
       for (int c = 0; c < ncon; c++) {
         const int info = w.c_info[c], body = info_body(info), dim = info_dim(info);
@@ -1320,7 +1361,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
         const bool diag = jj == k;
         const real* uw = &w.u_W[k];
 #pragma unroll
-        for (int l = 0; l < 4; l++) H[9 * l] = M[9 * l] + acc[l] + (diag ? uw[3 * l] + uw[NFL + 3 * l] : real(0));
+        for (int l = 0; l < 4; l++) H[9 * l] = M[9 * l] + acc[l] + (diag ? uw[3 * l] + (kLimits ? uw[NFL + 3 * l] : real(0)) : real(0));
       }
     };
     if (lane >= 21) write_legs(i0, j0, a0);
@@ -1333,7 +1374,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // cost and derivatives along qacc + alpha*search (warp-uniform result)
   QS_DEV LsPoint ls_eval(real alpha, real qg0, real qg1, real qg2) {
     real cost = 0, d1 = 0, d2 = 0;
-    if (lane < NFL + NLIM) scalar_unit_eval(lane, w.u_r[lane] + alpha * w.u_v[lane], w.u_v[lane], cost, d1, d2);
+    if (lane < NSC) scalar_unit_eval(lane, w.u_r[lane] + alpha * w.u_v[lane], w.u_v[lane], cost, d1, d2);
     const int ncon = w.ncon;
     if (lane < ncon) {
       const int c = lane;
@@ -1504,7 +1545,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
       if (alpha == 0) break;
       // move
       if (lane < NV) { w.qacc[lane] += alpha * w.search[lane]; w.Ma[lane] += alpha * w.Mv[lane]; }
-      if (lane < NFL + NLIM) w.u_r[lane] += alpha * w.u_v[lane];
+      if (lane < NSC) w.u_r[lane] += alpha * w.u_v[lane];
       for (int it2 = lane; it2 < w.ncon * MAXDIM; it2 += 32) (&w.c_r[0][0])[it2] += alpha * (&w.c_v[0][0])[it2];
       syncwarp();
       iter++;
@@ -1549,7 +1590,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
     mass_matrix();
     make_constraints();
     solve(max_iter, tol);
-    if (m.has_imu) sensors();
+    if (has_imu()) sensors();
   }
   QS_DEV void forward(int max_iter, real tol) {
     forward_position();
@@ -1593,11 +1634,7 @@ template <typename real, int NCON, int MAXDIM> struct Env {
   // ------------------------------------------------------------------ env side: flags + ALL_OBS (quadruped_env.py:1146-1257)
   struct Flags { unsigned contact_mask; unsigned invalid_mask; bool out_of_bounds; };
   QS_DEV Flags flags() const {
-    unsigned cm = 0, im = 0;
-    if (lane < w.ncon) {
-      const int info = w.c_info[lane], b = info_body(info);
-      if (b >= 2 && (b - 2) % 3 == 2) cm |= 1u << info_leg(info); else im |= 1u << b;
-    }
+    unsigned cm = cm_acc, im = im_acc;
     for (int o = 16; o > 0; o >>= 1) { cm |= shfl_xor(cm, o); im |= shfl_xor(im, o); }
     Flags f;
     f.contact_mask = cm; f.invalid_mask = im;

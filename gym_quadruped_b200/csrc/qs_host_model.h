@@ -214,6 +214,28 @@ template <typename real> std::vector<real> build_hfield(const QsModel& s) {
   return out;
 }
 
+// Features a model / configuration admits (see FEAT_* in qs_env.cuh): a compiled variant may be used iff it asserts a subset.
+inline int model_features(const QsModel& m, bool use_imu, int hm_cells) {
+  int f = 0;
+  f |= m.cone == QS_CONE_PYRAMIDAL ? FEAT_PYR : FEAT_ELL;
+  f |= m.terrain_type == QS_TERRAIN_FLAT ? FEAT_FLAT : (m.terrain_type == QS_TERRAIN_HFIELD ? FEAT_HFIELD : FEAT_BOXES);
+  if (!use_imu) f |= FEAT_NO_IMU;
+  if (hm_cells == 0) f |= FEAT_NO_HM;
+  bool mesh = false, caps = false, box = false, cyl = false, lim = false;
+  for (int g = 0; g < m.ngeom; g++) {
+    mesh |= m.geom_type[g] == QS_GEOM_MESH; caps |= m.geom_type[g] == QS_GEOM_CAPSULE;
+    box |= m.geom_type[g] == QS_GEOM_BOX; cyl |= m.geom_type[g] == QS_GEOM_CYLINDER;
+  }
+  for (int j = 0; j < QS_NJNT; j++) lim |= m.jnt_limited[j] != 0;
+  if (!mesh) f |= FEAT_NO_MESH;
+  if (!caps) f |= FEAT_NO_CAPSULE;
+  if (!box) f |= FEAT_NO_BOX;
+  if (!cyl) f |= FEAT_NO_CYL;
+  if (m.ngeom <= 32) f |= FEAT_NGEOM32;
+  if (!lim) f |= FEAT_NO_LIMITS;
+  return f;
+}
+
 inline int model_max_dim(const QsModel& s) {
   int md = 1;
   for (int g = 0; g < s.ngeom; g++) {

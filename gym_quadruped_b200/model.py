@@ -17,7 +17,7 @@ from .terrain import generate_terrain
 
 ASSET_DIR = Path(__file__).resolve().parent / 'assets'
 
-QS_ABI_VERSION = 4
+QS_ABI_VERSION = 5
 QS_NBODY, QS_NJNT, QS_NQ, QS_NV, QS_NU, QS_NLEG = 14, 12, 19, 18, 12, 4
 QS_MAXGEOM, QS_MAXBOX = 48, 128
 QS_NOBS_BASE, QS_NOBS_IMU = 227, 18
@@ -71,14 +71,20 @@ class QsConfig(C.Structure):
         ('num_envs', i32), ('device', i32), ('precision', i32), ('use_imu', i32), ('hm_rows', i32), ('hm_cols', i32),
         ('hm_dx', d), ('hm_dy', d),
         ('imu_accel_noise', d), ('imu_gyro_noise', d), ('imu_accel_bias_rate', d), ('imu_gyro_bias_rate', d),
-        ('seed', C.c_uint64), ('env_id_offset', i32), ('solver_max_iter', i32),
+        ('seed', C.c_uint64), ('env_id_offset', i32), ('solver_max_iter', i32), ('pipeline', i32), ('pad0', i32),
     ]
 
 
 class QsBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         'qpos', 'qvel', 'qacc', 'qacc_warmstart', 'base_pos64', 'qfrc_applied', 'command', 'friction', 'sim_time',
-        'step_count', 'imu_bias', 'status', 'ncon', 'solver_iter', 'invalid_body_mask')]
+        'step_count', 'imu_bias', 'status', 'ncon', 'solver_iter', 'invalid_body_mask', 'cmd_count', 'cmd_limit', 'ext_count',
+        'ext_limit', 'ext_wrench')]
+
+
+class QsSchedule(C.Structure):
+    _fields_ = [('command_mode', i32), ('ext_enabled', i32), ('lin_vel_range', d * 2), ('ang_vel_range', d * 2),
+                ('ext_lo', d * 6), ('ext_hi', d * 6)]
 
 
 class QsResetOptions(C.Structure):

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define QS_ABI_VERSION 4
+#define QS_ABI_VERSION 5
 
 /* ---- fixed topology of every robot in robot_cfgs.py: ----
  * world -> base(free joint) -> 4 x {hip, thigh, calf} (one hinge each)           */
@@ -173,6 +173,11 @@ typedef struct QsConfig {
   uint64_t seed;
   int32_t env_id_offset;   /* global id of local env 0 (multi-GPU sharding; keys the counter RNG) */
   int32_t solver_max_iter; /* <=0: library default */
+  int32_t pipeline;        /* 1: consecutive qs_step / qs_step_autoreset launches may overlap on the device (programmatic dependent
+                              launch + per-env finish-order queues; results are bit-identical to the serialized order).  Contract: the
+                              buffers a step reads (ctrl, bound buffers edited by the caller) must be complete when the PREVIOUS step
+                              launch of this handle was enqueued, or be written by the host.  0 (default): plain stream order. */
+  int32_t pad0;
 } QsConfig;
 
 /* Device buffers owned by the caller (torch tensors), bound once after qs_create.
@@ -193,7 +198,24 @@ typedef struct QsBuffers {
   int32_t* ncon;        /* [N]     number of active contacts in the last forward pass         */
   int32_t* solver_iter; /* [N]                                                                 */
   uint8_t* invalid_body_mask; /* [N,2] bitmask (little endian u16) of robot bodies with a world contact that is not a foot/calf body */
+  /* in-episode schedules, quadruped_env.py:293-305 (see QsSchedule) */
+  int32_t* cmd_count;   /* [N]   steps since the velocity command was last drawn ('+reset' command types, :293-296)           */
+  int32_t* cmd_limit;   /* [N]   randint(1000, 3000) drawn together with the command (:1068-1070)                            */
+  int32_t* ext_count;   /* [N]   steps since the external wrench was last drawn (:299-302)                                   */
+  int32_t* ext_limit;   /* [N]                                                                                               */
+  float* ext_wrench;    /* [N,6] current disturbance (x, y, z, roll, pitch, yaw); copied to qfrc_applied after every step (:305) */
 } QsBuffers;
+
+/* In-episode schedules run inside the step kernel (no host round trip): resampling of the velocity command for '+reset' command
+ * types (quadruped_env.py:293-296, _sample_ref_vel :1046-1072) and of the external base wrench for
+ * external_disturbances_kwargs['type'] == 'reset' (:299-305, _sample_external_disturbances :1074-1139). */
+typedef struct QsSchedule {
+  int32_t command_mode;     /* as QsResetOptions.command_mode; bit3 enables the in-episode command resampling            */
+  int32_t ext_enabled;      /* 1: disturbance schedule on (kwargs given and type == 'reset')                             */
+  double lin_vel_range[2];
+  double ang_vel_range[2];
+  double ext_lo[6], ext_hi[6]; /* per component U(lo, hi); lo == hi: fixed value (a one-element range or an absent key = 0) */
+} QsSchedule;
 
 /* options of a random reset, quadruped_env.py:346-373 */
 typedef struct QsResetOptions {
@@ -223,6 +245,17 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out);
 void qs_destroy(QsHandle* h);
 const char* qs_last_error(QsHandle* h);
 int qs_bind(QsHandle* h, const QsBuffers* dev_buffers);
+
+/* Install the in-episode schedules and draw the initial wrench / limits of every env (the reference samples them in __init__,
+ * quadruped_env.py:240-242).  NULL switches both schedules off. */
+int qs_set_schedule(QsHandle* h, const QsSchedule* sched, void* cuda_stream);
+
+/* `np.random.seed(seed)` of reset(seed=...) (quadruped_env.py:337-338) for the counter-based generator: replaces the key and
+ * restarts the per-env draw counters (episode, IMU tick, schedule epochs); no buffer is touched. */
+int qs_set_seed(QsHandle* h, uint64_t seed, void* cuda_stream);
+
+/* name of the compiled kernel variant that qs_step launches for this handle (diagnostics / tests) */
+const char* qs_step_variant(QsHandle* h);
 
 /* mj_step + sensors + _get_obs + termination, quadruped_env.py:270-288.
  * ctrl [N,12]; obs [N,D]; reward [N]; terminated/truncated [N]. */

@@ -9,7 +9,7 @@
 #include "../../gym_quadruped_b200/csrc/qs_host_model.h"
 
 namespace {
-template <typename real, int MAXDIM>
+template <typename real, int MAXDIM, int FEAT>
 int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, const double* ctrl, const double* envp, double* obs,
              double* misc, int max_iter, double tol, int mode) {
   using namespace qs;
@@ -44,7 +44,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
     th.emplace_back([&, lane]() {
       g_ctx = &ctx;
       g_lane = lane;
-      Env<real, NCON, MAXDIM> e(*dm, *ws, verts.data(), lane);
+      Env<real, NCON, MAXDIM, FEAT> e(*dm, *ws, verts.data(), lane);
       e.bias_out = bias_buf.data();
       e.hf = hfv.data(); e.boxes = boxes.data();
       e.forward(max_iter, real(tol));
@@ -72,6 +72,7 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
   if (misc) {
     int k = 0;
     misc[k++] = iters; misc[k++] = maxed; misc[k++] = cmask; misc[k++] = imask; misc[k++] = oob; misc[k++] = ws->ncon; misc[k++] = ws->overflow;
+    misc[k++] = FEAT;
     k = 8;
     for (int i = 0; i < 18; i++) misc[k++] = double(ws->qacc[i]);      // 8
     for (int i = 0; i < 18; i++) misc[k++] = double(bias_buf[i]);      // 26
@@ -108,13 +109,33 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
 }
 }  // namespace
 
-// mode 0: forward only; mode 1: forward + integrate + obs. precision 0: fp32, 1: fp64.
+// mode 0: forward only; mode 1: forward + integrate + obs; mode 2: + height map. precision 0: fp32, 1: fp64.
 // envp = {mu_floor, mu_feet, command[4], applied[6]}; misc has room for 1024 doubles.
+// feat_sel 0: the generic variant (FEAT = 0); 1: the specialised variant the library would pick for this model (csrc/qs_variants.h:
+// the four BASELINE configurations, chosen by the same `model_features` rule as qstep.cu), generic if none applies.
 extern "C" int emu_step(const QsModel* model, int precision, double* qpos, double* qvel, double* warm, const double* ctrl,
-                        const double* envp, double* obs, double* misc, int max_iter, double tol, int mode) {
-  const int md = qs::model_max_dim(*model);
-  if (precision == 0) return md > 3 ? run_step<float, 6>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
-                                    : run_step<float, 3>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode);
-  return md > 3 ? run_step<double, 6>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
-                : run_step<double, 3>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode);
+                        const double* envp, double* obs, double* misc, int max_iter, double tol, int mode, int feat_sel) {
+  using namespace qs;
+  const int md = model_max_dim(*model);
+#define QS_EMU_RUN(real, MD, F) run_step<real, MD, F>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
+  if (feat_sel == 1) {
+    // IMU columns / height-map columns are not part of the emulated observation row: the sensor stage runs whenever the model has
+    // an IMU (FEAT_NO_IMU is never asserted here) and mode 2 asks for the height map
+    const int have = model_features(*model, model->has_imu != 0, mode == 2 ? 25 : 0);
+    auto ok = [&](int feat) { return (feat & ~have) == 0; };
+    if (precision == 0) {
+      if (md <= 3 && ok(FEAT_CFG2)) return QS_EMU_RUN(float, 3, FEAT_CFG2);
+      if (md <= 3 && ok(FEAT_CFG3)) return QS_EMU_RUN(float, 3, FEAT_CFG3);
+      if (md <= 3 && ok(FEAT_CFG5)) return QS_EMU_RUN(float, 3, FEAT_CFG5);
+      if (md > 3 && ok(FEAT_CFG4)) return QS_EMU_RUN(float, 6, FEAT_CFG4);
+    } else {
+      if (md <= 3 && ok(FEAT_CFG2)) return QS_EMU_RUN(double, 3, FEAT_CFG2);
+      if (md <= 3 && ok(FEAT_CFG3)) return QS_EMU_RUN(double, 3, FEAT_CFG3);
+      if (md <= 3 && ok(FEAT_CFG5)) return QS_EMU_RUN(double, 3, FEAT_CFG5);
+      if (md > 3 && ok(FEAT_CFG4)) return QS_EMU_RUN(double, 6, FEAT_CFG4);
+    }
+  }
+  if (precision == 0) return md > 3 ? QS_EMU_RUN(float, 6, 0) : QS_EMU_RUN(float, 3, 0);
+  return md > 3 ? QS_EMU_RUN(double, 6, 0) : QS_EMU_RUN(double, 3, 0);
+#undef QS_EMU_RUN
 }

@@ -36,7 +36,7 @@ def test_library_loads_and_struct_sizes_agree():
     from gym_quadruped_b200 import backend
     from gym_quadruped_b200.model import QsBuffers, QsConfig, QsModel
     L = backend.load_library()  # dlopen only: no CUDA call is made without a GPU
-    assert L.qs_abi_version() == 4
+    assert L.qs_abi_version() == 5
     assert L.qs_model_sizeof() == ctypes.sizeof(QsModel) and L.qs_config_sizeof() == ctypes.sizeof(QsConfig)
     assert L.qs_buffers_sizeof() == ctypes.sizeof(QsBuffers)
     cfg = QsConfig(); cfg.use_imu = 1
