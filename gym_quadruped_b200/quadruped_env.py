@@ -81,6 +81,7 @@ class QuadrupedEnv(Env):
         precision: str = 'fp32',
         env_id_offset: int = 0,
         auto_reset: bool = False,
+        pipeline: bool = False,
     ):
         self._init_args = dict(robot=robot, state_obs_names=state_obs_names, scene=scene, sim_dt=sim_dt,
                                base_vel_command_type=base_vel_command_type, ref_base_lin_vel=ref_base_lin_vel,
@@ -143,8 +144,11 @@ class QuadrupedEnv(Env):
             self.observation_space.spaces['heightmap'] = Box(low=-np.inf, high=np.inf, shape=(hm_dim,), dtype=np.float32)
         self.state_obs_names = state_obs_names
 
+        # pipeline=True lets back-to-back `step` launches overlap on the device (BatchSim / QsConfig.pipeline); only meaningful
+        # when the actions do not depend on the previous observation (open-loop rollouts, replay)
         self.sim = BatchSim(self.model, self.num_envs, device=self.device, precision=0 if precision == 'fp32' else 1,
-                            use_imu=use_imu, imu_noise=imu_noise, seed=seed, env_id_offset=env_id_offset, heightmap=hm_cfg)
+                            use_imu=use_imu, imu_noise=imu_noise, seed=seed, env_id_offset=env_id_offset, heightmap=hm_cfg,
+                            pipeline=pipeline)
         for cls, kw in deferred:  # host-side plug-ins following the Sensor protocol (base_sensor.py:4-41)
             self.sensors.append(cls(mj_model=self.model, mj_data=self, **kw))
         self._layout = dict(OBS_LAYOUT)
@@ -158,11 +162,16 @@ class QuadrupedEnv(Env):
         self._leg_perm_np = None if self._leg_perm is None else np.array([3 * p + i for p in perm for i in range(3)])
         self._time_host = 0.0
 
+        # In-episode schedules (:293-305): '+reset' command resampling and the external base wrench run inside the step kernel
+        # (per-env counters in sim.cmd_count / cmd_limit / ext_count / ext_limit, wrench in sim.ext_wrench): no host round trip.
+        # As in the reference the wrench is only ever applied for type == 'reset' (:299-305); it is drawn here, at construction (:240-242).
         self.external_disturbances_kwargs = external_disturbances_kwargs
-        self._ext_schedule = None
-        if external_disturbances_kwargs is not None:
-            self._sample_external_disturbances(torch.ones(self.num_envs, dtype=torch.bool, device=self.device))
-        self._vel_schedule = None
+        ext_on = external_disturbances_kwargs is not None and external_disturbances_kwargs.get('type') == 'reset'
+        self.sim.set_schedule(command_mode=self._command_mode, lin_vel_range=self.base_lin_vel_range, ang_vel_range=self.base_ang_vel_range,
+                              ext_ranges=external_disturbances_kwargs if external_disturbances_kwargs is not None else None,
+                              ext_enabled=ext_on)
+        self.sim.reset_options = self._reset_options(True, {})  # used by auto-reset before the first explicit reset()
+        self._warned_status = 0
         self.viewer = None
         self.step_num = 0
         self._last_obs_tensor = self.sim.obs
@@ -189,12 +198,9 @@ class QuadrupedEnv(Env):
             s.step()
         info_invalid = self.sim.invalid_body_mask
         self.step_num += 1
-        if self._command_mode & backend.CMD_RESET:
-            self._advance_velocity_schedule()
-        if self.external_disturbances_kwargs is not None and self.external_disturbances_kwargs.get('type') == 'reset':
-            self._advance_disturbance_schedule()
         obs = self._obs_dict(obs_t)
-        info = {'time': self.sim.sim_time, 'step_num': self.step_num - 1, 'invalid_contacts': info_invalid}
+        # `status` (per env): bit0 non-finite state, bit1 contact buffer overflow, bit2 solver iteration cap, bit3 reset could not clear contact
+        info = {'time': self.sim.sim_time, 'step_num': self.step_num - 1, 'invalid_contacts': info_invalid, 'status': self.sim.status}
         return obs, rew, term.bool(), trunc.bool(), info
 
     def _step_single(self, action):
@@ -204,15 +210,12 @@ class QuadrupedEnv(Env):
             h['ctrl'].copy_(action.detach().reshape(1, 12).to('cpu', torch.float32))
         else:
             h['ctrl_np'][0, :] = np.asarray(action, dtype=np.float32).reshape(12)
-        self.sim.step_host(h['ctrl'], h['obs'], h['rew'], h['term'], h['trunc'])  # returns after the stream is synchronised
+        self.sim.step_host(h['ctrl'], h['obs'], h['rew'], h['term'], h['trunc'],  # returns after the stream is synchronised
+                           auto_reset=self.sim.reset_options if self.auto_reset_on_step else None)
         self.sim.obs.copy_(h['obs'], non_blocking=True)  # keeps the device-side row (frame conversions of the accessors) current
         for s in self.sensors:
             s.step()
         self.step_num += 1
-        if self._command_mode & backend.CMD_RESET:
-            self._advance_velocity_schedule()
-        if self.external_disturbances_kwargs is not None and self.external_disturbances_kwargs.get('type') == 'reset':
-            self._advance_disturbance_schedule()
         obs = self._obs_dict(self.sim.obs, host_row=h['obs_np'][0])
         terminated = bool(h['term'][0])
         invalid = {}
@@ -222,7 +225,11 @@ class QuadrupedEnv(Env):
             names = self.model.tables['body_names']
             invalid = {f'world:0_{names[b]}:{b}': None for b in range(1, 14) if mask >> b & 1}
         self._time_host += self.simulation_dt
-        info = {'time': self._time_host, 'step_num': self.step_num - 1, 'invalid_contacts': invalid}
+        status = int(self.sim.status[0].item()) if terminated else 0  # read only when something happened: no extra sync per step
+        if status & ~self._warned_status & 7:
+            self._warned_status |= status
+            log.warning('libqstep status 0x%x (bit0 non-finite state, bit1 contact buffer overflow, bit2 solver iteration cap)', status)
+        info = {'time': self._time_host, 'step_num': self.step_num - 1, 'invalid_contacts': invalid, 'status': status}
         return obs, 0, terminated, False, info
 
     def reset(self, qpos=None, qvel=None, seed: int | None = None, random: bool = True, options: dict[str, Any] | None = None,
@@ -231,12 +238,8 @@ class QuadrupedEnv(Env):
         options = {} if options is None else options
         self.step_num = 0
         if seed is not None:
-            self._reseed(seed)
-        opt = self.sim.make_reset_options(
-            randomize=random, angle_sweep=options.get('angle_sweep', 20 * math.pi / 180),
-            roll_sweep=options.get('roll_sweep', 10 * math.pi / 180), pitch_sweep=options.get('pitch_sweep', 10 * math.pi / 180),
-            lin_vel_range=self.base_lin_vel_range, ang_vel_range=self.base_ang_vel_range,
-            friction_range=self.ground_friction_coeff_range, command_mode=self._command_mode)
+            self.sim.set_seed(seed)  # np.random.seed(seed) (:337-338): new key, draw counters restarted, no buffer touched
+        opt = self._reset_options(random, options)
         self.sim.reset_options = opt
         mask = None if env_mask is None else env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
         if qpos is not None or qvel is not None:
@@ -249,10 +252,15 @@ class QuadrupedEnv(Env):
             obs_t = self.sim.reset(mask, None, None, opt)
         if self.num_envs == 1 and (int(self.sim.status[0].item()) & 8):
             raise RuntimeError('Unable to initialize the robot without ground contact.')
-        if self._command_mode & backend.CMD_RESET:
-            self._vel_schedule = None
         self._time_host = self.simulation_dt  # the reset ends with one step from time 0 (:333,:397)
         return self._obs_dict(obs_t)
+
+    def _reset_options(self, random: bool, options: dict):
+        return self.sim.make_reset_options(
+            randomize=random, angle_sweep=options.get('angle_sweep', 20 * math.pi / 180),
+            roll_sweep=options.get('roll_sweep', 10 * math.pi / 180), pitch_sweep=options.get('pitch_sweep', 10 * math.pi / 180),
+            lin_vel_range=self.base_lin_vel_range, ang_vel_range=self.base_ang_vel_range,
+            friction_range=self.ground_friction_coeff_range, command_mode=self._command_mode)
 
     def auto_reset(self):
         """Batched convenience: reset every env whose last `terminated` flag is set (one masked kernel launch)."""
@@ -296,6 +304,9 @@ class QuadrupedEnv(Env):
     # ------------------------------------------------------------------ state tensors (write-then-step semantics of mjData)
     @property
     def qpos(self) -> torch.Tensor:
+        """[N, 19] fp32 view of the generalized positions.  Joint angles / orientation may be edited in place (write-then-step, like
+        `env.mjData.qpos[...] = ...`); the BASE POSITION is mastered in fp64 (`sim.base_pos64`, resets scatter envs over +-10 km) and
+        `qpos[:, :3]` is only its fp32 image, refreshed every step -- move the base with `set_state`."""
         return self.sim.qpos
 
     @property
@@ -486,62 +497,6 @@ class QuadrupedEnv(Env):
 
     def get_hyperparameters(self):
         return copy.copy(self._init_args)
-
-    # ------------------------------------------------------------------ schedules (:293-305, :1046-1139)
-    def _reseed(self, seed: int):
-        """`np.random.seed(seed)` equivalent for the counter-based generator: restart the reset stream under a new key."""
-        old = self.sim
-        state = (old.qpos.clone(), old.qvel.clone(), old.base_pos64.clone())
-        use_imu, noise = bool(old.cfg.use_imu), (old.cfg.imu_accel_noise, old.cfg.imu_gyro_noise, old.cfg.imu_accel_bias_rate, old.cfg.imu_gyro_bias_rate)
-        old.close()
-        self.sim = BatchSim(self.model, self.num_envs, device=self.device, precision=old.cfg.precision, use_imu=use_imu,
-                            imu_noise=noise, seed=seed, env_id_offset=old.cfg.env_id_offset)
-        self.sim.qpos.copy_(state[0]); self.sim.qvel.copy_(state[1]); self.sim.base_pos64.copy_(state[2])
-
-    def _advance_velocity_schedule(self):
-        n, dev = self.num_envs, self.device
-        if self._vel_schedule is None:
-            self._vel_schedule = [torch.zeros(n, dtype=torch.int32, device=dev), torch.randint(1000, 3000, (n,), dtype=torch.int32, device=dev)]
-        cnt, lim = self._vel_schedule
-        cnt += 1
-        due = cnt >= lim
-        if bool(due.any()):
-            lo, hi = self.base_lin_vel_range
-            norm = lo + (hi - lo) * torch.rand(n, device=dev)
-            if self._command_mode & backend.CMD_RANDOM:
-                ang = (torch.rand(n, device=dev) * 2 - 1) * math.pi
-                hx, hy = torch.cos(ang), torch.sin(ang)
-            else:
-                hx, hy = torch.ones(n, device=dev), torch.zeros(n, device=dev)
-            alo, ahi = self.base_ang_vel_range
-            yawrate = (alo + (ahi - alo) * torch.rand(n, device=dev)) if self._command_mode & backend.CMD_ROTATE else torch.zeros(n, device=dev)
-            new = torch.stack([norm * hx, norm * hy, torch.zeros(n, device=dev), yawrate], dim=1)
-            self.sim.command[due] = new[due]
-            cnt[due] = 0
-            lim[due] = torch.randint(1000, 3000, (int(due.sum().item()),), dtype=torch.int32, device=dev)
-
-    def _sample_external_disturbances(self, which: torch.Tensor):
-        kw, n, dev = self.external_disturbances_kwargs, self.num_envs, self.device
-        if self._ext_schedule is None:
-            self._ext_schedule = [torch.zeros(n, dtype=torch.int32, device=dev), torch.randint(1000, 3000, (n,), dtype=torch.int32, device=dev),
-                                  torch.zeros(n, 6, device=dev)]
-        cnt, lim, val = self._ext_schedule
-        cnt[which] = 0
-        lim[which] = torch.randint(1000, 3000, (int(which.sum().item()),), dtype=torch.int32, device=dev)
-        for k, key in enumerate(('x', 'y', 'z', 'roll', 'pitch', 'yaw')):
-            col = torch.zeros(n, device=dev)
-            if key in kw:
-                r = kw[key]
-                col = torch.full((n,), float(r[0]), device=dev) if len(r) == 1 else float(r[0]) + (float(r[1]) - float(r[0])) * torch.rand(n, device=dev)
-            val[which, k] = col[which]
-
-    def _advance_disturbance_schedule(self):
-        cnt, lim, val = self._ext_schedule
-        cnt += 1
-        due = cnt >= lim
-        if bool(due.any()):
-            self._sample_external_disturbances(due)
-        self.sim.qfrc_applied.copy_(val)  # acts on the next step, as in the reference (:305)
 
     def __str__(self):
         msg = f'robot={self._init_args["robot"]} terrain={self._init_args["scene"]} task={self.base_vel_command_type} num_envs={self.num_envs}'

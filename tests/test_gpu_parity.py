@@ -338,7 +338,7 @@ def test_quadruped_env_surface(cuda_device):
         for _ in range(10):
             action = env.action_space.sample() * 50
             obs, reward, term, trunc, info = env.step(action=action)
-            assert reward == 0 and isinstance(term, bool) and trunc is False and set(info) == {'time', 'step_num', 'invalid_contacts'}
+            assert reward == 0 and isinstance(term, bool) and trunc is False and {'time', 'step_num', 'invalid_contacts'} <= set(info)
             assert all(np.isfinite(v).all() for v in obs.values())
         assert abs(info['time'] - 11 * 0.002) < 1e-6 and info['step_num'] == 9
         assert env.feet_pos().FL.shape == (3,) and env.base_lin_vel('base').shape == (3,)
