@@ -5,14 +5,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (one process per GPU under torchrun)
     python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the fp64 oracle port on all host cores
 
-A "step" is one pass of the hot path over the whole batch: ONE launch of the fused step kernel, which also resets (in the
-same warp) the envs that just terminated.
-Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
+A "step" is one pass of the hot path over the whole batch: ONE launch of the fused step kernel through the single-step C-ABI
+call (qs_step_autoreset), which also resets (in the same warp) the envs that just terminated.  The timed region is exactly K such
+launches between a barrier + synchronize on both sides; it is repeated (at least 5 times, and until 0.25 s have been timed) and the
+MEDIAN region is reported, max over ranks.  Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every key.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -33,6 +35,7 @@ RESET_KW = dict(lin_vel_range=(0.5, 1.0), ang_vel_range=(0.0, 0.0), friction_ran
 METRIC = 'env-steps/sec (total batch) mini_cheetah/flat @4096 envs/GPU'
 UNIT = 'env-steps/s'
 USE_IMU, HEIGHTMAP = False, None
+PREROLL = 300  # untimed rollout steps before the warm-up: the timed steps see the steady-state mix of flight / contact / resets
 # BASELINE.json configs[1] is the bench workload; configs[2..4] are parity-test cases (tests/test_gpu_parity.py) that can also
 # be timed for information with --workload (per-GPU batch sizes of section 8(d))
 WORKLOADS = {
@@ -55,24 +58,37 @@ def select_workload(name):
 
 
 def workload_config(n_gpus, envs):
+    """Identical in both arms (the driver compares the two `config` objects)."""
+    ring = max(64, int(160e6 // (envs * 12 * 4)) + 1)
     return {
-        'workload': f'{ROBOT}/{SCENE}, ALL_OBS (D={OBS_DIM}), {envs} envs per GPU, ctrl = 50*N(0,1) per actuator, '
-                    f'random-reset initial states, auto-reset on termination',
+        'workload': f'{ROBOT}/{SCENE}, ALL_OBS (D={OBS_DIM}), {envs} envs per GPU, ctrl = 50*N(0,1) per actuator, random-reset initial states '
+                    f'advanced {PREROLL} untimed steps to the steady-state rollout, auto-reset on termination',
         'robot': ROBOT, 'scene': SCENE, 'envs_per_gpu': envs, 'global_envs': envs * n_gpus, 'obs_dim': OBS_DIM,
         'sim_dt': 0.002, 'algorithmic_bytes_per_env_step': BYTES_PER_ENV_STEP, 'parallelism': f'env-sharded x{n_gpus}',
+        'l2': f'inputs larger than L2: ctrl is streamed from a {ring}-entry action ring ({ring * envs * 48 / 1e6:.0f} MB per GPU, L2 = 126 MB); '
+              f'the env state ({envs * 220 / 1e6:.1f} MB) is carried in place from step to step, as in any rollout. An L2-flushed variant is '
+              f'reported as ms_per_step_l2_flushed',
     }
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm (oracle port)
-def _cpu_worker(args):
-    seed, n_envs, steps, duration = args
+_W = {}
+
+
+def _cpu_init(seed0, n_envs_total, cores):
+    """Pool initializer: every worker process builds its share of the envs once (not timed)."""
+    import multiprocessing as mp
+
     import numpy as np
 
     from gym_quadruped_b200.model import Model
     from oracle.oracle import Oracle
 
+    ident = mp.current_process()._identity
+    wid = (ident[0] - 1) % cores if ident else 0
+    share = n_envs_total // cores + (1 if wid < n_envs_total % cores else 0)
     model = Model(ROBOT, SCENE)
-    rng = np.random.RandomState(seed)
+    rng = np.random.RandomState(seed0 + wid)
     key = np.array(model.c.key_qpos)
     # a table of lifted random-reset start states (reset distribution of quadruped_env.py:346-373, near the origin)
     o = Oracle(model)
@@ -90,33 +106,29 @@ def _cpu_worker(args):
         table.append(np.concatenate([o.get_state()[0], v]))
     table = np.array(table)
     envs = []
-    for i in range(n_envs):
+    for i in range(share):
         e = Oracle(model)
         e.set_state(table[i % 32, :19], table[i % 32, 19:], np.zeros(18))
         e.set_env(rng.uniform(0.2, 1.5), -1.0, [rng.uniform(0.5, 1.0), 0, 0, 0])
         envs.append(e)
-    chunk = 64
-    ctrl = rng.randn(chunk, 12) * TORQUE_SCALE
-    done_steps, cursor = 0, 0
+    _W.update(envs=envs, table=table, cursor=0, rng=rng)
+
+
+def _cpu_block(k):
+    """Advance every env of this worker by k steps (random actions x50, auto-reset from the table); returns (env-steps, seconds)."""
+    rng, table = _W['rng'], _W['table']
+    ctrl = rng.randn(k, 12) * TORQUE_SCALE
     t0 = time.perf_counter()
-    if steps is not None:  # fixed number of steps for every env
-        for e in envs:
-            left = steps
-            while left > 0:
-                k = min(chunk, left)
-                _, cursor = e.rollout_autoreset(ctrl[:k], table, cursor)
-                left -= k
-            done_steps += steps
-    else:  # run for a fixed duration
-        while time.perf_counter() - t0 < duration:
-            for e in envs:
-                _, cursor = e.rollout_autoreset(ctrl, table, cursor)
-                done_steps += chunk
-    return done_steps, time.perf_counter() - t0
+    cur = _W['cursor']
+    for e in _W['envs']:
+        _, cur = e.rollout_autoreset(ctrl, table, cur)
+    _W['cursor'] = cur
+    return len(_W['envs']) * k, time.perf_counter() - t0
 
 
-def cpu_throughput(steps_per_env=None, n_envs_total=None, duration=3.0, warmup=0):
-    """Oracle env-steps/s on all host cores: one process per core, each advancing its share of the envs independently."""
+def cpu_throughput(steps, warmup, n_envs_total, min_seconds=1.0, preroll=PREROLL):
+    """Oracle env-steps/s on all host cores: one process per core, each owning a fixed share of the `n_envs_total` envs.
+    One block = every env advanced `steps` steps; blocks are repeated until `min_seconds` have been timed; the median block counts."""
     import multiprocessing as mp
 
     from oracle.oracle import build
@@ -124,35 +136,41 @@ def cpu_throughput(steps_per_env=None, n_envs_total=None, duration=3.0, warmup=0
     build()
     cores = os.cpu_count() or 1
     ctx = mp.get_context('spawn')
-    with ctx.Pool(cores) as pool:
-        if steps_per_env is None:
-            jobs = [(100 + i, 4, None, duration) for i in range(cores)]
-        else:
-            share = [n_envs_total // cores + (1 if i < n_envs_total % cores else 0) for i in range(cores)]
-            if warmup:
-                pool.map(_cpu_worker, [(900 + i, max(1, s), warmup, None) for i, s in enumerate(share)])
-            jobs = [(100 + i, s, steps_per_env, None) for i, s in enumerate(share) if s > 0]
-        res = pool.map(_cpu_worker, jobs)
-    total = sum(r[0] for r in res)
-    wall = max(r[1] for r in res)
-    return total / wall, cores, total, wall
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(100, n_envs_total, cores)) as pool:
+        def block(k):
+            res = pool.map(_cpu_block, [k] * cores, chunksize=1)
+            return sum(r[0] for r in res), max(r[1] for r in res)
+        if preroll:
+            block(preroll)
+        if warmup:
+            block(warmup)
+        walls, total_steps, total_wall = [], 0, 0.0
+        while len(walls) < 5 or total_wall < min_seconds:
+            n, w = block(steps)
+            walls.append(w); total_steps += n; total_wall += w
+            if len(walls) >= 400:
+                break
+    wall = statistics.median(walls)
+    return n_envs_total * steps / wall, cores, len(walls), wall, total_steps, total_wall
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return  # under torchrun only rank 0 measures the CPU arm
-    sample_envs = 512
-    value, cores, total, wall = cpu_throughput(steps_per_env=args.steps, n_envs_total=sample_envs, warmup=args.warmup)
-    sample = (f'{sample_envs} of {ENVS_PER_GPU} envs advanced {args.steps} steps each (after {args.warmup} warm-up steps) by the '
-              f'fp64 C oracle port, one process per host core, auto-reset on termination; {total} env-steps in {wall:.2f} s')
+    envs = args.envs
+    value, cores, blocks, wall, total, total_wall = cpu_throughput(args.steps, args.warmup, envs, min_seconds=1.0)
+    sample = (f'all {envs} envs of one GPU shard advanced by the fp64 C oracle port, one process per host core ({cores}), auto-reset on '
+              f'termination; {PREROLL} untimed pre-roll + {args.warmup} warm-up steps, then {blocks} blocks of {args.steps} steps '
+              f'({total} env-steps in {total_wall:.2f} s), median block')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * wall / max(1, args.steps), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': workload_config(args.gpus, ENVS_PER_GPU),
+        'data': 'synthetic', 'config': workload_config(args.gpus, envs),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'note': 'MuJoCo (the engine the reference calls) is not installable in this image; this is the from-scratch oracle port of its step',
+        'note': 'MuJoCo (the engine the reference calls) is not installable in this image; this is the from-scratch oracle port of its step. '
+                'The value is one shard of envs on the whole host; it does not scale with --gpus',
     }
     print(json.dumps(line), flush=True)
 
@@ -217,6 +235,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from gym_quadruped_b200.backend import BatchSim
+    from gym_quadruped_b200.distributed import ObsGather
     from gym_quadruped_b200.model import Model
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -234,111 +253,173 @@ def run_gpu(args):
     K, W = args.steps, max(3, args.warmup)
 
     model = Model(ROBOT, SCENE)
-    sim = BatchSim(model, envs, device=dev, seed=args.seed, env_id_offset=rank * envs, use_imu=USE_IMU, heightmap=HEIGHTMAP)
-    opt = sim.make_reset_options(**RESET_KW)
-    sim.reset(options=opt)
-
-    # action ring larger than L2 (126 MB): 768 x 4096 x 12 fp32 = 151 MB per GPU, so ctrl is streamed from HBM every step
+    sim_kw = dict(device=dev, seed=args.seed, env_id_offset=rank * envs, use_imu=USE_IMU, heightmap=HEIGHTMAP)
+    # action ring larger than L2 (126 MB): 814 x 4096 x 12 fp32 = 160 MB per GPU, so ctrl is streamed from HBM every step
     ring = max(64, int(160e6 // (envs * 12 * 4)) + 1) if not args.small_ring else 64
     gen = torch.Generator(device=dev).manual_seed(args.seed + rank)
     actions = torch.randn(ring, envs, 12, device=dev, generator=gen) * TORQUE_SCALE
-
-    def one_step(i):
-        sim.step_autoreset(actions[i % ring], opt)  # one launch: step + in-kernel reset of the envs that just terminated
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(W):
-        one_step(i)
-    barrier()
+    def make_sim(pipeline, precision=0):
+        s = BatchSim(model, envs, pipeline=pipeline, precision=precision, **sim_kw)
+        o = s.make_reset_options(**RESET_KW)
+        s.reset(options=o)
+        for i in range(PREROLL):
+            s.step_autoreset(actions[i % ring], o)
+        return s, o
 
-    # ---- timed region: exactly K steps, device-timed, max over ranks
+    def timed_regions(s, o, start, min_regions=5, min_seconds=0.25, max_regions=400):
+        """Regions of exactly K single-step launches, each between barrier + synchronize; returns per-region ms (max over ranks)."""
+        out, i, total = [], start, 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        while True:
+            barrier()
+            e0.record()
+            for _ in range(K):
+                s.step_autoreset(actions[i % ring], o)  # one launch: step + in-kernel reset of the envs that just terminated
+                i += 1
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            stop = len(out) + 1 >= min_regions and total + ms >= 1e3 * min_seconds
+            if world > 1:
+                t = torch.tensor([ms, 0.0 if stop else 1.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms, stop = float(t[0]), float(t[1]) == 0.0
+            out.append(ms); total += ms
+            if stop or len(out) >= max_regions:
+                return out, i
+
+    # ---- headline: pipelined single-step launches (QsConfig.pipeline: consecutive launches overlap on the device)
+    sim, opt = make_sim(pipeline=not args.no_pipeline)
+    for i in range(W):
+        sim.step_autoreset(actions[(PREROLL + i) % ring], opt)
+    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = sim.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        one_step(W + i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = sim.launch_count - launches0
+    regions, cursor = timed_regions(sim, opt, PREROLL + W)
+    launches = (sim.launch_count - launches0) // len(regions)
     clocks = sampler.stop() if sampler else None
-    terminated_frac = float(sim.terminated.float().mean().item())
+    ms = statistics.median(regions)
+    torch.cuda.synchronize(dev)
+    ncon = sim.ncon.cpu(); its = (sim.solver_iter.cpu() & 0xff)
+    stats = {
+        'mean_contacts_per_env': round(float(ncon.float().mean()), 3), 'envs_without_contact': round(float((ncon == 0).float().mean()), 3),
+        'newton_iterations_mean': round(float(its.float().mean()), 3), 'newton_iterations_max': int(its.max()),
+        'newton_iterations_hist': {str(k): round(float((its == k).float().mean()), 4) for k in range(0, 9)},
+        'terminated_fraction_last_step': round(float(sim.terminated.float().mean()), 5), 'status_or': int(sim.status.max()),
+    }
+    variant = sim.step_variant
 
-    # ---- dominant kernel alone: per-launch CUDA events on the launching stream (roofline.achieved)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for i in range(K):
-        a, b = evs[i]
+    # ---- the same launches in plain stream order (no overlap between consecutive launches), each launch timed on its own
+    ser, ser_opt = make_sim(pipeline=False)
+    for i in range(W):
+        ser.step_autoreset(actions[(PREROLL + i) % ring], ser_opt)
+    ser_regions, _ = timed_regions(ser, ser_opt, PREROLL + W, min_regions=5, min_seconds=0.1)
+    ser_ms = statistics.median(ser_regions)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(K, 50))]
+    for i, (a, b) in enumerate(evs):
         a.record()
-        one_step(W + K + i)
+        ser.step_autoreset(actions[i % ring], ser_opt)
         b.record()
     torch.cuda.synchronize(dev)
-    step_kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / K
-
-    # ---- same loop with the L2 flushed between iterations (256 MB write), each step timed on its own
+    launch_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    # L2 flushed between iterations (256 MB write), each step timed on its own
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    kf = min(K, 200)
-    cold = 0.0
-    for i in range(kf):
+    cold = []
+    for i in range(min(len(evs), 100)):
         flush.fill_(i & 0xff)
         a, b = evs[i]
         a.record()
-        one_step(i)
+        ser.step_autoreset(actions[i % ring], ser_opt)
         b.record()
         torch.cuda.synchronize(dev)
-        cold += a.elapsed_time(b)
-    cold_ms = cold / kf
+        cold.append(a.elapsed_time(b))
+    cold_ms = statistics.median(cold)
     del flush
 
-    # ---- end to end through the C-ABI with HOST buffers (pinned): H2D ctrl + kernels + D2H obs/reward/flags every step
+    # ---- end to end through the C-ABI with HOST buffers (pinned): H2D ctrl + kernel + D2H obs/reward/flags every step, synchronous
     host_ring = 8
     ctrl_h = [(torch.randn(envs, 12) * TORQUE_SCALE).pin_memory() for _ in range(host_ring)]
     obs_h = torch.empty(envs, sim.obs_dim).pin_memory(); rew_h = torch.empty(envs).pin_memory()
     term_h = torch.empty(envs, dtype=torch.uint8).pin_memory(); trunc_h = torch.empty(envs, dtype=torch.uint8).pin_memory()
-    ke = min(K, 500)
-    for i in range(3):
-        sim.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=opt)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(ke):
-        sim.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=opt)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    for i in range(5):
+        ser.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=ser_opt)
+    e2e_regions, total = [], 0.0
+    while len(e2e_regions) < 5 or total < 0.25:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            ser.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=ser_opt)
+        dt = time.perf_counter() - t0
+        e2e_regions.append(dt); total += dt
+        if len(e2e_regions) >= 400:
+            break
+    e2e_s = statistics.median(e2e_regions)
     h2d = envs * 12 * 4
     d2h = envs * (sim.obs_dim * 4 + 4 + 1 + 1)
 
-    # ---- optional: per-step NCCL all-gather of the observation tensor over NVLink (north_star's only collective)
-    gather_ms = None
-    if world > 1:
-        gathered = torch.empty(world * envs, sim.obs_dim, device=dev)
-        for i in range(3):
-            one_step(i); dist.all_gather_into_tensor(gathered, sim.obs)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+    # ---- fp64 arithmetic build of the same kernel (QsConfig.precision = 1), for reference next to the fp32 value
+    f64_ms = None
+    if n_gpus == 1 and not args.no_fp64:
+        s64, o64 = make_sim(pipeline=not args.no_pipeline, precision=1)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         for i in range(K):
-            one_step(i); dist.all_gather_into_tensor(gathered, sim.obs)
-        g1.record()
-        barrier()
-        gather_ms = g0.elapsed_time(g1)
+            s64.step_autoreset(actions[i % ring], o64)
+        b.record()
+        torch.cuda.synchronize(dev)
+        f64_ms = a.elapsed_time(b) / K
+        s64.close()
+
+    # ---- the one collective north_star names: every rank ends up with the observation rows of all ranks
+    gather = None
+    if world > 1:
+        gather = {}
+        for mode in ('p2p', 'nccl'):
+            try:
+                g = ObsGather(sim, mode=mode)
+            except Exception as e:  # noqa: BLE001
+                gather[mode] = {'unavailable': str(e)[:200]}
+                continue
+            for i in range(10):
+                g.step_autoreset(actions[i % ring], opt)
+            g.wait()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reg = []
+            for _ in range(5):
+                barrier()
+                g0.record()
+                for i in range(K):
+                    g.step_autoreset(actions[i % ring], opt)
+                g.wait()  # the gathered tensor of the last step is complete on this rank
+                g1.record()
+                barrier()
+                reg.append(g0.elapsed_time(g1))
+            t = torch.tensor(reg, dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gather[mode] = {'ms_per_step': float(t.median()) / K, 'value': n_gpus * envs * K / (float(t.median()) * 1e-3),
+                            'bytes_received_per_rank_per_step': (world - 1) * envs * sim.obs_dim * 4, 'how': g.describe()}
+            g.close()
 
     # ---- reduce over ranks (max time)
-    t = torch.tensor([ms, step_kernel_ms, cold_ms, e2e_s, gather_ms or 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ser_ms, launch_ms, cold_ms, e2e_s, f64_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, step_kernel_ms, cold_ms, e2e_s, gather_ms_max = [float(x) for x in t.tolist()]
+    ser_ms, launch_ms, cold_ms, e2e_s, f64_ms_r = [float(x) for x in t.tolist()]
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
     if rank == 0:
         value = n_gpus * envs * K / (ms * 1e-3)
         peak, peak_src = measured_hbm_peak()
-        achieved = envs * BYTES_PER_ENV_STEP / (step_kernel_ms * 1e-3) / 1e9
+        achieved = envs * BYTES_PER_ENV_STEP / (ms / K * 1e-3) / 1e9
         traffic = None
         tp = ROOT / 'profiles' / 'traffic.json'
         if tp.exists() and args.workload == 'cfg2':
@@ -348,27 +429,42 @@ def run_gpu(args):
                 traffic = None
         cpu = None
         if n_gpus == 1 and not args.no_cpu_baseline:
-            v, cores, total, wall = cpu_throughput(duration=3.0)
+            v, cores, blocks, wall, total, total_wall = cpu_throughput(20, 5, envs, min_seconds=1.2)
             cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': f'fp64 C oracle port of the same workload, 4 envs per process x {cores} processes for {wall:.1f} s ({total} env-steps)'}
-        cfg = workload_config(n_gpus, envs)
-        cfg['l2'] = (f'inputs larger than L2: ctrl streamed from a {ring}-entry action ring ({ring * envs * 48 / 1e6:.0f} MB/GPU); env state '
-                     f'({envs * 220 / 1e6:.1f} MB) is carried in place from step to step. L2-flushed variant reported as ms_per_step_l2_flushed')
+                   'sample': f'fp64 C oracle port, all {envs} envs on {cores} processes (one per host core), {blocks} blocks of 20 steps after '
+                             f'{PREROLL}+5 untimed steps ({total} env-steps in {total_wall:.1f} s), median block'}
+        e2e_ms = 1e3 * e2e_s / K
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(n_gpus, envs),
+            'timing': {'regions': len(regions), 'region_ms_median': ms, 'region_ms_min': min(regions), 'region_ms_max': max(regions),
+                       'launch_mode': 'serialized' if args.no_pipeline else
+                       'pipelined: QsConfig.pipeline=1, every step is its own qs_step_autoreset launch; consecutive launches overlap on the '
+                       'device (programmatic dependent launch + per-env finish-order queues), results bit-identical to the serialized order',
+                       'step_kernel_variant': variant},
+            'serialized': {'value': n_gpus * envs * K / (ser_ms * 1e-3), 'ms_per_step': ser_ms / K, 'ms_per_launch_events': launch_ms,
+                           'note': 'same launches without overlap (QsConfig.pipeline=0): what a caller gets whose next action depends on '
+                                   'the previous observation'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': peak_src, 'kernel': 'env_kernel<float,16,%d,MODE_STEP>' % (6 if ROBOT == 'go2' else 3), 'kernel_ms_per_launch': step_kernel_ms,
-                         'note': 'latency/issue-bound path (about 1.4 kB and 60 kFLOP of dependent fp32 work per env-step): a low HBM fraction is expected'},
+                         'peak_source': peak_src, 'kernel': f'env_kernel<float,16,{6 if ROBOT == "go2" else 3},MODE_STEP,{variant}>',
+                         'kernel_ms_per_launch': ms / K, 'kernel_ms_per_launch_serialized': launch_ms,
+                         'note': 'latency/issue-bound path (about 1.4 kB and 60 kFLOP of dependent fp32 work per env-step): a low HBM '
+                                 'fraction is expected; achieved = algorithmic bytes per launch / (timed region / K launches)'},
             'cpu_baseline': cpu,
-            'e2e': {'value': n_gpus * envs * ke / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ke,
-                    'api': 'qs_step_host (C-ABI, pinned host buffers, in-kernel auto-reset)'},
+            'e2e': {'value': n_gpus * envs * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': K,
+                    'regions': len(e2e_regions), 'ms_per_step': e2e_ms,
+                    'api': 'qs_step_host (C-ABI, pinned host buffers, in-kernel auto-reset), synchronous: returns when the results are in host memory',
+                    'exposed_transfer_ms_per_step': e2e_ms - ser_ms / K,
+                    'note': 'zero-copy: the kernel reads ctrl and writes obs rows through the mapped host buffers; exposed_transfer = e2e - '
+                            'serialized device time per step is what PCIe adds on top of the kernel'},
             'gpu_launches': int(lt.item()), 'clocks': clocks,
-            'ms_per_step_l2_flushed': cold_ms, 'terminated_fraction_last_step': terminated_frac,
+            'ms_per_step_l2_flushed': cold_ms, 'workload_stats': stats,
+            'fp64_arithmetic': None if f64_ms is None else {'value': envs * K / (f64_ms_r * K * 1e-3), 'ms_per_step': f64_ms_r,
+                                                            'note': 'QsConfig.precision=1: same kernel source in fp64 arithmetic (8 warps per CTA)'},
         }
-        if world > 1:
-            line['with_obs_all_gather'] = {'value': n_gpus * envs * K / (gather_ms_max * 1e-3), 'unit': UNIT,
-                                           'bytes_gathered_per_rank_per_step': world * envs * sim.obs_dim * 4}
+        if gather is not None:
+            line['with_obs_all_gather'] = gather
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -378,14 +474,16 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1000)
-    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=None, help='envs per GPU (default: the workload\'s)')
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS), help='cfg2 = BASELINE configs[1] (the bench line)')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--small-ring', action='store_true', help='64-entry action ring (profiling runs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fp64', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true', help='headline in plain stream order (QsConfig.pipeline=0)')
     args = ap.parse_args()
     select_workload(args.workload)
     if args.envs is None:

@@ -246,13 +246,15 @@ class BatchSim:
                                    self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated
 
-    def step_autoreset(self, ctrl: torch.Tensor, options: QsResetOptions | None = None):
-        """`step` plus, in the same launch, a random reset of every env that just terminated (post-reset obs/state returned)."""
+    def step_autoreset(self, ctrl: torch.Tensor, options: QsResetOptions | None = None, obs_out: torch.Tensor | None = None):
+        """`step` plus, in the same launch, a random reset of every env that just terminated (post-reset obs/state returned).
+        `obs_out`: write the observation rows there instead of `self.obs` (double-buffered consumers, see distributed.ObsGather)."""
         o = options or self.reset_options
         ctrl = self._as_ctrl(ctrl)
-        self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), self.obs.data_ptr(), self.reward.data_ptr(),
+        obs = self.obs if obs_out is None else obs_out
+        self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), obs.data_ptr(), self.reward.data_ptr(),
                                              self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
-        return self.obs, self.reward, self.terminated, self.truncated
+        return obs, self.reward, self.terminated, self.truncated
 
     def step_host(self, ctrl_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
                   terminated_host: torch.Tensor, truncated_host: torch.Tensor, auto_reset: QsResetOptions | None = None):

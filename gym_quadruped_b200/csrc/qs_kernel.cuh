@@ -54,6 +54,7 @@ struct KParams {
   unsigned* q_tail;        // monotonic publish counter of q_out
   unsigned q_tail_base;    // its value before this launch's first publish
   int q_contiguous;        // 1: CTA c takes slots [c*W, c*W + W); 0: slot = warp * gridDim + c
+  int q_sync;              // 1: launches of this handle may overlap -> acquire / release on the queue slots; 0: the grid boundary orders everything
   // in-episode schedules (quadruped_env.py:293-305): command resampling ('+reset' types) and external-wrench resampling
   int sch_command_mode, sch_ext_enabled;
   float sch_lin[2], sch_ang[2], sch_ext_lo[6], sch_ext_hi[6];
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     if (slot < p.num_envs) {
       int e_ = 0;
       if (lane == 0) {
-        while ((e_ = ld_acquire(p.q_in + slot)) < 0) __nanosleep(100);
+        if (p.q_sync) { while ((e_ = ld_acquire(p.q_in + slot)) < 0) __nanosleep(100); }
+        else e_ = p.q_in[slot];  // plain stream order: the previous launch has completed, every slot is filled
         p.q_in[slot] = -1;  // consumed: the launch after the next one refills this queue
       }
       env = __shfl_sync(0xffffffffu, e_, 0);
@@ -643,9 +645,8 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     // (all lanes' stores happen-before lane 0's fence) -- the consumer's acquire load pairs with it.
     __syncwarp();
     if (lane == 0) {
-      __threadfence();
       const unsigned pos = atomicAdd(p.q_tail, 1u) - p.q_tail_base;
-      st_release(p.q_out + pos, env);
+      if (p.q_sync) st_release(p.q_out + pos, env); else p.q_out[pos] = env;
     }
   }
 #ifdef QS_PROF

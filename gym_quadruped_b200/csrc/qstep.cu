@@ -143,9 +143,7 @@ template <typename real> static int setup_variant(QsHandle* h, const QsModel* mo
   QS_CUDA(h, cudaGetDevice(&dev));
   QS_CUDA(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   int warps = gen->max_warps;
-#ifdef QS_PROF
-  if (const char* ev = getenv("QS_WARPS_PER_CTA")) { const int v = atoi(ev); if (v >= 1 && v < warps) warps = v; }  // contention experiments
-#endif
+  if (const char* ev = getenv("QS_WARPS_PER_CTA")) { const int v = atoi(ev); if (v >= 1 && v < warps) warps = v; }  // occupancy experiments
   while (warps > 1 && gen->dm_bytes + 128 + warps * gen->ws_bytes > size_t(max_smem)) warps--;
   h->warps_per_cta = warps;
   h->smem_bytes = gen->dm_bytes + 128 + warps * gen->ws_bytes;
@@ -314,6 +312,7 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
     p.q_tail = h->d_queue_tail + out;
     p.q_tail_base = unsigned((s / 2) * n);  // launches s-2, s-4, ... published n entries each through this counter
     p.q_contiguous = h->cfg.pipeline ? 1 : 0;
+    p.q_sync = h->cfg.pipeline ? 1 : 0;
   }
   const bool chained = h->cfg.pipeline && h->last_was_step && h->last_stream == stream;
   const int rc = launch(h, h->k_step, p, static_cast<cudaStream_t>(stream), chained);

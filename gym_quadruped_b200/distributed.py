@@ -1,6 +1,16 @@
-"""Env sharding across GPUs: contiguous env-index ranges per rank, no data-path collective; the
-only optional collective is an all-gather of the per-rank observation rows (NCCL over NVLink on GPUs, gloo in CPU tests)."""
+"""Env sharding across GPUs: contiguous env-index ranges per rank, no data-path collective.  The only
+collective north_star names is the gather of the observation rows, `ObsGather`:
+
+* mode 'p2p'  -- fused into the step kernel: every warp stores its finished observation row straight into the gathered tensor of
+  EVERY rank through peer-mapped memory (CUDA IPC over NVLink / NVSwitch), the last warp of the launch raises a per-rank flag on
+  every peer; no separate collective kernel, the transfer overlaps the envs that are still being solved (csrc/qs_kernel.cuh).
+* mode 'nccl' -- `all_gather_into_tensor` on a side stream, double-buffered so that it overlaps the next step (the baseline).
+
+`gather_rows` is the plain blocking helper (gloo in the CPU tests).
+"""
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -21,3 +31,107 @@ def gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous(), group=group)
     return out
+
+
+class _DevArray:
+    """Wraps a raw device pointer owned by libqstep so that torch can view it (`__cuda_array_interface__`)."""
+
+    def __init__(self, ptr: int, shape, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+class ObsGather:
+    """Steps a `BatchSim` shard and keeps, on every rank, the observation rows of ALL ranks: `gathered[k]` is a
+    [world * N, D] tensor in global env order, k = step parity (double buffer: the rows of step t stay valid until step t + 2 is
+    enqueued).  Usage per step:  `g.step_autoreset(ctrl, opt)`; ...; `rows = g.wait()` (stream-ordered: kernels enqueued on the
+    current stream after `wait()` see the complete tensor of the last step)."""
+
+    def __init__(self, sim, mode: str = 'p2p', group=None):
+        if not dist.is_initialized():
+            raise RuntimeError('ObsGather needs an initialised torch.distributed process group')
+        self.sim, self.mode, self.group = sim, mode, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.N, self.D, self.dev = sim.N, sim.obs_dim, sim.device
+        self.t = 0
+        self.side = torch.cuda.Stream(device=self.dev)
+        self._ev_step = [torch.cuda.Event() for _ in range(2)]
+        self._ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._pending = [False, False]
+        if mode == 'nccl':
+            self.local = [torch.zeros(self.N, self.D, device=self.dev) for _ in range(2)]
+            self.gathered = [torch.zeros(self.world * self.N, self.D, device=self.dev) for _ in range(2)]
+        elif mode == 'p2p':
+            self._open_p2p()
+        else:
+            raise ValueError(f'unknown gather mode {mode}')
+
+    # ------------------------------------------------------------------ p2p plumbing (CUDA IPC handles exchanged through the process group)
+    def _open_p2p(self):
+        L, sim = self.sim.L, self.sim
+        if not hasattr(L, 'qs_gather_create'):
+            raise RuntimeError('libqstep was built without the peer-to-peer gather')
+        L.qs_gather_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.qs_gather_connect.argtypes = [C.c_void_p, C.c_void_p]
+        L.qs_gather_buffer.argtypes = [C.c_void_p, C.c_int]
+        L.qs_gather_buffer.restype = C.c_void_p
+        L.qs_gather_wait.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.qs_gather_steps.argtypes = [C.c_void_p]
+        L.qs_gather_steps.restype = C.c_uint64
+        L.qs_gather_close.argtypes = [C.c_void_p]
+        handle = (C.c_ubyte * 64)()
+        sim._check(L.qs_gather_create(sim.h, self.world, self.rank, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        buf = (C.c_ubyte * (64 * self.world))(*allh.cpu().tolist())
+        sim._check(L.qs_gather_connect(sim.h, buf))
+        dist.barrier(group=self.group)
+        self.gathered = [torch.as_tensor(_DevArray(L.qs_gather_buffer(sim.h, k), (self.world * self.N, self.D)), device=self.dev)
+                         for k in range(2)]
+
+    def describe(self) -> str:
+        if self.mode == 'p2p':
+            return ('fused: each warp of the step kernel stores its observation row into the gathered tensor of every rank through '
+                    'peer-mapped memory (CUDA IPC over NVLink), per-rank completion flags raised by the last warp; wait() is a flag-poll kernel on a side stream')
+        return 'NCCL all_gather_into_tensor on a side stream, double-buffered observation rows (overlaps the next step)'
+
+    # ------------------------------------------------------------------ stepping
+    def step_autoreset(self, ctrl, opt):
+        k = self.t & 1
+        main = torch.cuda.current_stream(self.dev)
+        if self._pending[k]:
+            main.wait_event(self._ev_done[k])  # the consumer / collective of step t - 2 has released this buffer
+            self._pending[k] = False
+        if self.mode == 'nccl':
+            self.sim.step_autoreset(ctrl, opt, obs_out=self.local[k])
+            self._ev_step[k].record(main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self._ev_step[k])
+                dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+                self._ev_done[k].record(self.side)
+            self._pending[k] = True
+        else:
+            self.sim.step_autoreset(ctrl, opt)  # rows go to every rank's gathered[k] from inside the kernel
+            self._ev_step[k].record(main)
+        self.t += 1
+
+    def wait(self) -> torch.Tensor:
+        """Make the current stream wait until the gathered tensor of the last step is complete on this rank; returns it."""
+        k = (self.t - 1) & 1
+        main = torch.cuda.current_stream(self.dev)
+        if self.mode == 'nccl':
+            main.wait_event(self._ev_done[k])
+        else:
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self._ev_step[k])
+                self.sim._check(self.sim.L.qs_gather_wait(self.sim.h, C.c_uint64(self.sim.L.qs_gather_steps(self.sim.h)),
+                                                          C.c_void_p(self.side.cuda_stream)))
+                self._ev_done[k].record(self.side)
+            main.wait_event(self._ev_done[k])
+        return self.gathered[k]
+
+    def close(self):
+        torch.cuda.synchronize(self.dev)
+        if self.mode == 'p2p':
+            dist.barrier(group=self.group)
+            self.sim.L.qs_gather_close(self.sim.h)

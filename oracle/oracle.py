@@ -17,7 +17,8 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / 'build' / 'liboracle.so'
 
 F_M, F_BIAS, F_PASSIVE, F_FEET_JACP, F_FEET_POS, F_COM, F_CONTACTS, F_SMOOTH, F_CONSTRAINT, F_XPOS, F_IMU, \
-    F_QACC_SMOOTH, F_EFC, F_FLAGS, F_FEET_JACR, F_FEET_JACP_DOT, F_FEET_JACR_DOT = range(17)
+    F_QACC_SMOOTH, F_EFC, F_FLAGS, F_FEET_JACR, F_FEET_JACP_DOT, F_FEET_JACR_DOT, F_EFC_FULL = range(18)
+EFC_FULL_STRIDE = 34
 
 
 def build(force: bool = False) -> Path:
@@ -126,8 +127,10 @@ class Oracle:
         return self.L.orc_lift(self.h)
 
     def get(self, field):
-        buf = np.zeros(4096)
+        buf = np.zeros(65536)
         n = self.L.orc_get(self.h, field, _p(buf))
+        if field == F_EFC_FULL:
+            return buf[:EFC_FULL_STRIDE * n].reshape(n, EFC_FULL_STRIDE).copy()
         if field == F_M:
             return buf[:324].reshape(18, 18).copy()
         if field in (F_FEET_JACP, F_FEET_JACR, F_FEET_JACP_DOT, F_FEET_JACR_DOT):

@@ -1334,7 +1334,9 @@ int orc_lift(void* h) {
 }
 
 enum { F_M = 0, F_BIAS = 1, F_PASSIVE = 2, F_FEET_JACP = 3, F_FEET_POS = 4, F_COM = 5, F_CONTACTS = 6, F_SMOOTH = 7, F_CONSTRAINT = 8,
-       F_XPOS = 9, F_IMU = 10, F_QACC_SMOOTH = 11, F_EFC = 12, F_FLAGS = 13, F_FEET_JACR = 14, F_FEET_JACP_DOT = 15, F_FEET_JACR_DOT = 16 };
+       F_XPOS = 9, F_IMU = 10, F_QACC_SMOOTH = 11, F_EFC = 12, F_FLAGS = 13, F_FEET_JACR = 14, F_FEET_JACP_DOT = 15, F_FEET_JACR_DOT = 16,
+       F_EFC_FULL = 17 };
+#define EFC_FULL_STRIDE 34
 int orc_get(void* h, int field, double* dst) {
   OData* d = (OData*)h;
   switch (field) {
@@ -1369,6 +1371,18 @@ int orc_get(void* h, int field, double* dst) {
     case F_QACC_SMOOTH: memcpy(dst, d->qacc_smooth, sizeof(d->qacc_smooth)); return NV;
     case F_EFC: /* per row: type, D, R, aref, force, state */
       for (int r = 0; r < d->nefc; r++) { double* o = dst + 6 * r; o[0] = d->efc_type[r]; o[1] = d->efc_D[r]; o[2] = d->efc_R[r]; o[3] = d->efc_aref[r]; o[4] = d->efc_force[r]; o[5] = d->efc_state[r]; }
+      return d->nefc;
+    case F_EFC_FULL: /* the constraint problem handed to the solver, one row each: type, id, D, R, aref, force, state, floss, contact mu,
+                        friction[5], contact dim, pad, J[18] -- for the independent-optimiser pin in tests/test_solver_pin.py */
+      for (int r = 0; r < d->nefc; r++) {
+        double* o = dst + EFC_FULL_STRIDE * r;
+        int type = d->efc_type[r], id = d->efc_id[r];
+        memset(o, 0, EFC_FULL_STRIDE * sizeof(double));
+        o[0] = type; o[1] = id; o[2] = d->efc_D[r]; o[3] = d->efc_R[r]; o[4] = d->efc_aref[r]; o[5] = d->efc_force[r]; o[6] = d->efc_state[r];
+        o[7] = d->efc_floss[r];
+        if (type >= T_CONTACT_FRICTIONLESS) { const OContact* c = &d->con[id]; o[8] = c->mu; memcpy(o + 9, c->friction, 5 * sizeof(double)); o[14] = c->dim; }
+        memcpy(o + 16, d->efc_J[r], NV * sizeof(double));
+      }
       return d->nefc;
     case F_FLAGS:
       for (int l = 0; l < 4; l++) dst[l] = d->contact_state[l];

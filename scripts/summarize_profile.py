@@ -24,7 +24,7 @@ tag, label = sys.argv[1], sys.argv[2]
 rep = ROOT / 'gpurun_out' / f'prof_{tag}.ncu-rep'
 out = ROOT / 'profiles'
 out.mkdir(exist_ok=True)
-KERNEL = 'env_kernelIfLi16ELi3ELi0E'
+KERNEL = sys.argv[3] if len(sys.argv) > 3 else 'env_kernelIfLi16ELi3ELi0ELi8101E'
 
 raw = subprocess.run(['ncu', '-i', str(rep), '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -57,9 +57,14 @@ traffic = to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
 # ---- SASS -> source attribution
 tmp = Path(tempfile.mkdtemp())
 subprocess.run(['cuobjdump', '-xelf', 'all', str(ROOT / 'gym_quadruped_b200' / 'csrc' / 'libqstep.so')], cwd=tmp, capture_output=True)
-cubin = next(tmp.glob('*.cubin'))
-dis = subprocess.run(['nvdisasm', '-g', '-c', str(cubin)], capture_output=True, text=True).stdout.split('\n')
-start = [i for i, l in enumerate(dis) if l.startswith('.text.') and KERNEL in l and l.rstrip().endswith(':')][0]
+dis, start = None, None
+for cubin in sorted(tmp.glob('*.cubin')):  # one cubin per translation unit (qs_inst_*.cu): find the one that holds the kernel
+    d_ = subprocess.run(['nvdisasm', '-g', '-c', str(cubin)], capture_output=True, text=True).stdout.split('\n')
+    hit = [i for i, l in enumerate(d_) if l.startswith('.text.') and KERNEL in l and l.rstrip().endswith(':')]
+    if hit:
+        dis, start = d_, hit[0]
+        break
+assert dis is not None, f'{KERNEL} not found in libqstep.so'
 insts, cur = [], ('?', 0)
 for l in dis[start + 1:]:
     if l.startswith('//---------------------'):
