@@ -466,3 +466,32 @@ def test_contact_buffer_overflow_keeps_termination_exact(cuda_device):
     inv = sim.invalid_body_mask.cpu().numpy().astype(np.int64)
     assert (inv[0, 0] | (inv[0, 1] << 8)) == f['invalid_body_mask'] and bool(term[0].item()) == ref_term
     assert ((sim.obs[0, 199:203].cpu().numpy() > 0.5) == f['contact_state']).all()
+
+
+def test_rollout_recorder_from_gpu_rollout(tmp_path, cuda_device):
+    """f3: a batched GPU rollout written in the reference's recording layout (utils/data/h5py.py:90-172): N envs x T steps become N
+    trajectories [traj, time, dim] float64 with `action`, `time` and the env hyper-parameters."""
+    from gym_quadruped_b200.quadruped_env import QuadrupedEnv
+    from gym_quadruped_b200.utils.data.recorder import RolloutReader, RolloutRecorder
+    names = ('qpos', 'qvel', 'base_ori_SO3', 'contact_state', 'feet_pos:base')
+    env = QuadrupedEnv('aliengo', state_obs_names=names, ref_base_lin_vel=(0.5, 1.0), num_envs=8)
+    env.reset(seed=1)
+    rec = RolloutRecorder(env, tmp_path / 'rollout.npz', with_terminated=True)
+    g = torch.Generator(device='cpu').manual_seed(0)
+    kept = []
+    for t in range(6):
+        a = (torch.randn(8, 12, generator=g) * 5).to(cuda_device)
+        obs, rew, term, trunc, info = env.step(a)
+        rec.record(obs, a, term)
+        kept.append((obs['qpos'].clone(), a.clone(), env.sim.sim_time.clone()))
+    rec.flush()
+    r = RolloutReader(tmp_path / 'rollout.npz')
+    assert r.len() == 8 and r.env_hparams['robot'] == 'aliengo' and r.env_hparams['state_obs_names'] == list(names)
+    time, data = r.get_trajectory(3)
+    assert time.shape == (6, 1) and data['qpos'].shape == (6, 19) and data['base_ori_SO3'].shape == (6, 9) and data['action'].shape == (6, 12)
+    for t, (q, a, st) in enumerate(kept):
+        assert np.array_equal(data['qpos'][t], q[3].cpu().numpy().astype(np.float64))
+        assert np.array_equal(data['action'][t], a[3].cpu().numpy().astype(np.float64))
+        assert time[t, 0] == float(st[3])
+    assert data['terminated'].shape == (6, 1) and data['qpos'].dtype == np.float64
+    env.close()
