@@ -36,7 +36,7 @@ template <typename real> struct alignas(16) DModel {
   real floor_fri[4];
   real imu_pos[4];
   real imu_mat[12];
-  real mass_total, robot_radius, pad_r[2];
+  real mass_total, robot_radius, hf_lip, pad_r;  // hf_lip: largest slope of any height-field triangle (broad phase of the mesh collider)
   real hf_size[4], hf_pos[4];          // height field: half-x, half-y, z-scale, base; position
   real terr_fri[4], terr_margin, terr_K, terr_B, terr_pad;  // hfield: default parameters; boxes: friction per box (DBox), the rest per scene
   real terr_solimp[8];                         // contact parameters when the scene's boxes out-rank every robot geom (terr_wins)
@@ -713,20 +713,21 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   // Primitive robot geoms against the perlin height field / the static boxes, as feature points (sphere centre + radius, capsule
   // end spheres, box corners) -- exact for sphere-box and plane-like cases, an approximation of the engine's capsule-box,
   // box-box and prism-based hfield routines otherwise (documented in DESIGN.md).  Appends after the floor contacts.
-  QS_DEV void collide_terrain(int& ncon, const int gbase) {
-    unsigned boxmask[4] = {0, 0, 0, 0};
-    if (ttype() == 2) {
-      for (int wd = 0; wd < 4; wd++) {
-        const int b = 32 * wd + lane;
-        bool near = false;
-        if (b < m.nbox) {
-          const real rel[3] = {boxes[b].pos[0] - w.kin.xpos[1][0], boxes[b].pos[1] - w.kin.xpos[1][1], boxes[b].pos[2] - w.kin.xpos[1][2]};
-          const real reach = boxes[b].rad + m.robot_radius;
-          near = dot3(rel, rel) < reach * reach;
-        }
-        boxmask[wd] = ballot(near);
+  unsigned boxnear[4] = {0, 0, 0, 0};  // static boxes within reach of the robot (warp-uniform), refreshed by every collision pass
+  QS_DEV void find_near_boxes() {
+    for (int wd = 0; wd < 4; wd++) {
+      const int b = 32 * wd + lane;
+      bool near = false;
+      if (b < m.nbox) {
+        const real rel[3] = {boxes[b].pos[0] - w.kin.xpos[1][0], boxes[b].pos[1] - w.kin.xpos[1][1], boxes[b].pos[2] - w.kin.xpos[1][2]};
+        const real reach = boxes[b].rad + m.robot_radius;
+        near = dot3(rel, rel) < reach * reach;
       }
+      boxnear[wd] = ballot(near);
     }
+  }
+  QS_DEV void collide_terrain(int& ncon, const int gbase) {
+    unsigned boxmask[4] = {boxnear[0], boxnear[1], boxnear[2], boxnear[3]};
     Cand list[4];
     int n = 0;
     const int g = gbase + lane;
@@ -793,6 +794,150 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
     }
   }
 
+  // signed distance of point p to static box bx (negative inside) and the outward box normal there (world frame)
+  QS_DEV static real point_box_distance(const DBox<real>& bx, const real* p, real* nw) {
+    const real rel[3] = {p[0] - bx.pos[0], p[1] - bx.pos[1], p[2] - bx.pos[2]};
+    real q[3], dl[3], nl[3] = {0, 0, 0}, dist;
+    mul_mtv(q, bx.mat, rel);
+    bool inside = true;
+    for (int i = 0; i < 3; i++) { const real cl = q[i] < -bx.half[i] ? -bx.half[i] : (q[i] > bx.half[i] ? bx.half[i] : q[i]); dl[i] = q[i] - cl; if (dl[i] != 0) inside = false; }
+    if (!inside) {
+      const real len = N::sqrt(dot3(dl, dl));
+      dist = len;
+      for (int i = 0; i < 3; i++) nl[i] = dl[i] / len;
+    } else {
+      int best = 0;
+      real depth = N::big;
+      for (int i = 0; i < 3; i++) { const real e = bx.half[i] - N::abs(q[i]); if (e < depth) { depth = e; best = i; } }
+      dist = -depth;
+      nl[best] = q[best] >= 0 ? real(1) : real(-1);
+    }
+    mul_mv(nw, bx.mat, nl);
+    return dist;
+  }
+
+  // Convex meshes against the height field / the static boxes, hull vertices as feature points (the terrain counterpart of the
+  // support-vertex rule used on the floor plane): the deepest vertex per mesh on the height field, the deepest vertex per
+  // (mesh, box) pair on boxes, at most 4 per mesh, deepest first.  Broad phase on the lanes (bounding sphere of the hull's box
+  // against a Lipschitz bound of the field around it / against the robot-near boxes), the vertex scans by the whole warp.
+  QS_DEV void collide_mesh_terrain(const int gbase, int& ncon) {
+    const int g = gbase + lane;
+    const int tt = ttype();
+    bool near = false;
+    if (geom_on(g) && m.geom_type[g] == GEOM_MESH) {
+      const int b = m.geom_body[g];
+      real c[3], tmp[3];
+      mul_mv(tmp, w.kin.xmat[b], m.geom_bcenter[g]);
+      for (int i = 0; i < 3; i++) c[i] = w.kin.xpos[b][i] + tmp[i];
+      const real* bh = m.geom_bhalf[g];
+      const real rb = N::sqrt(bh[0] * bh[0] + bh[1] * bh[1] + bh[2] * bh[2]);
+      if (tt == 1) {
+        // the field under the hull's footprint is at most lip * rb above its height at the centre (anywhere: below the global top)
+        real z, nn[3];
+        const real top = m.hf_pos[2] + m.hf_size[2];
+        const real bound = hfield_height(c[0], c[1], z, nn) ? N::min(top, z + m.hf_lip * rb) : top;
+        const bool over = !(c[0] + rb < m.hf_pos[0] - m.hf_size[0] || c[0] - rb > m.hf_pos[0] + m.hf_size[0] ||
+                            c[1] + rb < m.hf_pos[1] - m.hf_size[1] || c[1] - rb > m.hf_pos[1] + m.hf_size[1]);
+        near = over && !(c[2] - rb > bound + N::max(m.geom_margin[g], m.terr_margin) + real(1e-4));
+      } else {
+        near = (boxnear[0] | boxnear[1] | boxnear[2] | boxnear[3]) != 0;
+      }
+    }
+    unsigned cand = ballot(near);
+    while (cand) {
+      const int gm_ = gbase + ctz(cand);
+      cand &= cand - 1;
+      const int b = m.geom_body[gm_];
+      const real margin = N::max(m.geom_margin[gm_], m.terr_margin);
+      const real* R = w.kin.xmat[b];
+      const real* X = w.kin.xpos[b];
+      const Vert4<real>* v = vert + m.geom_vertadr[gm_];
+      const int nv = m.geom_vertnum[gm_];
+      if (tt == 1) {
+        real best = N::big;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < nv; i += 32) {
+          const Vert4<real> q = v[i];
+          const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
+          real z, nn[3];
+          if (!hfield_height(p[0], p[1], z, nn)) continue;
+          const real dist = (p[2] - z) * nn[2];
+          if (dist < best) { best = dist; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const real ob = shfl_xor(best, o);
+          const int oi = shfl_xor(bi, o);
+          if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi == 0x7fffffff || best > margin) continue;
+        note_contact(gm_);
+        if (lane == 0 && ncon < NCON) {
+          const Vert4<real> q = v[bi];
+          const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
+          real z, nn[3];
+          hfield_height(p[0], p[1], z, nn);
+          const real pos[3] = {p[0] - nn[0] * real(0.5) * best, p[1] - nn[1] * real(0.5) * best, p[2] - nn[2] * real(0.5) * best};
+          store_contact(ncon, gm_, real(1), best, pos, nn, nullptr, WG_HFIELD);
+        }
+        ncon++;
+      } else {
+        // every lane keeps the same (warp-uniform) list of the 4 deepest (box, vertex) pairs of this mesh
+        real ld[4];
+        int lb[4], lv[4], n = 0;
+        real c[3], tmp[3];
+        mul_mv(tmp, R, m.geom_bcenter[gm_]);
+        for (int i = 0; i < 3; i++) c[i] = X[i] + tmp[i];
+        const real* bh = m.geom_bhalf[gm_];
+        const real rb = N::sqrt(bh[0] * bh[0] + bh[1] * bh[1] + bh[2] * bh[2]) + margin + real(0.01);
+        for (int wd = 0; wd < 4; wd++) {
+          unsigned mask = boxnear[wd];
+          while (mask) {
+            const int bx = 32 * wd + ctz(mask);
+            mask &= mask - 1;
+            const DBox<real>& B = boxes[bx];
+            const real rel[3] = {c[0] - B.pos[0], c[1] - B.pos[1], c[2] - B.pos[2]};
+            const real reach = B.rad + rb;
+            if (dot3(rel, rel) > reach * reach) continue;
+            real best = N::big;
+            int bi = 0x7fffffff;
+            for (int i = lane; i < nv; i += 32) {
+              const Vert4<real> q = v[i];
+              const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
+              real nw[3];
+              const real dist = point_box_distance(B, p, nw);
+              if (dist < best) { best = dist; bi = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+              const real ob = shfl_xor(best, o);
+              const int oi = shfl_xor(bi, o);
+              if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (best > margin) continue;
+            // insertion by depth; among equals the earlier box stays first (the order of a stable sort over the box index)
+            int k = n < 4 ? n : 4;
+            if (n >= 4 && !(best < ld[3])) continue;
+            if (k == 4) k = 3;
+            while (k > 0 && best < ld[k - 1]) { ld[k] = ld[k - 1]; lb[k] = lb[k - 1]; lv[k] = lv[k - 1]; k--; }
+            ld[k] = best; lb[k] = bx; lv[k] = bi;
+            if (n < 4) n++;
+          }
+        }
+        for (int r = 0; r < n; r++) {
+          note_contact(gm_);
+          if (lane == 0 && ncon < NCON) {
+            const Vert4<real> q = v[lv[r]];
+            const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
+            real nw[3];
+            point_box_distance(boxes[lb[r]], p, nw);
+            const real pos[3] = {p[0] - nw[0] * real(0.5) * ld[r], p[1] - nw[1] * real(0.5) * ld[r], p[2] - nw[2] * real(0.5) * ld[r]};
+            store_contact(ncon, gm_, real(1), ld[r], pos, nw, nullptr, lb[r]);
+          }
+          ncon++;
+        }
+      }
+    }
+  }
+
   // downward ray from `org` against the static terrain: distance to the nearest hit or -1 ([MJ] mj_ray, heightmap.py:77-99)
   QS_DEV real ray_down(const real* org) const {
     real best = org[2] >= 0 ? org[2] : real(-1);  // floor plane z = 0
@@ -844,6 +989,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   QS_DEV void collide_floor() {
     int ncon = 0;
     cm_acc = im_acc = 0;
+    if (ttype() == 2 && terrain_on) find_near_boxes();
     // one lane per geom; robots with more than 32 collision geoms (go1: 42) take a second round
     if (FEAT & FEAT_NGEOM32) collide_round(0, ncon);
     else {
@@ -989,6 +1135,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       }
       ncon++;
     }
+    if (type_on(GEOM_MESH) && ttype() != 0 && terrain_on) collide_mesh_terrain(gbase, ncon);
   }
 
   // ------------------------------------------------------------------ constraint construction

@@ -100,6 +100,18 @@ std::string build_dmodel(const QsModel& s, DModel<real>& d, std::vector<Vert4<re
   }
   d.hf_nrow = s.hf_nrow; d.hf_ncol = s.hf_ncol;
   if (s.terrain_type == QS_TERRAIN_HFIELD && (s.hf_nrow < 2 || s.hf_ncol < 2 || !s.hf_data)) return "height field data missing";
+  if (s.terrain_type == QS_TERRAIN_HFIELD) {  // largest gradient magnitude over both triangles of every cell (+ a rounding cushion)
+    const int nc = s.hf_ncol, nr = s.hf_nrow;
+    const double dx = 2 * s.hf_size[0] / (nc - 1), dy = 2 * s.hf_size[1] / (nr - 1), sz = s.hf_size[2];
+    double lip2 = 0;
+    for (int r = 0; r + 1 < nr; r++)
+      for (int c = 0; c + 1 < nc; c++) {
+        const double z00 = sz * s.hf_data[r * nc + c], z10 = sz * s.hf_data[r * nc + c + 1], z01 = sz * s.hf_data[(r + 1) * nc + c], z11 = sz * s.hf_data[(r + 1) * nc + c + 1];
+        const double g1x = (z10 - z00) / dx, g1y = (z11 - z10) / dy, g2x = (z11 - z01) / dx, g2y = (z01 - z00) / dy;
+        lip2 = std::max(lip2, std::max(g1x * g1x + g1y * g1y, g2x * g2x + g2y * g2y));
+      }
+    d.hf_lip = real(std::sqrt(lip2) * 1.001 + 1e-6);
+  }
   if (s.terrain_type == QS_TERRAIN_BOXES && (s.nbox < 0 || s.nbox > QS_MAXBOX)) return "nbox out of range";
   for (int j = 0; j < QS_NJNT; j++) {
     for (int i = 0; i < 3; i++) {

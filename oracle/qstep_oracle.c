@@ -502,7 +502,9 @@ static void collideFloor(OData* d) {
  * Robot geoms are reduced to "feature points" (sphere centre + radius; capsule end spheres; box corners), each tested against
  * the surface below / around it.  This is the engine's exact rule for sphere-box and plane-like cases and an approximation of
  * its capsule-box / box-box / prism-based hfield routines (no edge-edge contacts) -- [MJ-approx], documented in DESIGN.md.
- * Mesh geoms collide with the floor plane only. */
+ * Convex meshes use the same idea with their hull vertices as the feature points: against the height field the deepest vertex
+ * (signed distance to the triangle plane under it) gives one contact per mesh; against a box the deepest vertex per (mesh, box)
+ * pair, at most 4 per mesh (deepest first), the box being geom1 (box < mesh in the engine's type order). */
 static int hfieldHeight(const OData* d, double x, double y, double* z, double* n) {
   const QsModel* m = &d->m;
   double sx = m->hf_size[0], sy = m->hf_size[1], sz = m->hf_size[2];
@@ -568,6 +570,73 @@ static void collidePointTerrain(OData* d, int g, const double* p, double r, int 
   }
 }
 
+/* signed distance of point p to box b (negative inside) and the outward box normal there (world frame) */
+static double pointBoxDistance(const QsModel* m, int b, const double* p, double* nw) {
+  double R[9], q[3], rel[3] = {p[0] - m->box_pos[b][0], p[1] - m->box_pos[b][1], p[2] - m->box_pos[b][2]};
+  const double* h = m->box_half[b];
+  quat2Mat(R, m->box_quat[b]);
+  mulMatTVec3(q, R, rel);
+  double cl[3], dl[3], nl[3] = {0, 0, 0}, dist;
+  int inside = 1;
+  for (int i = 0; i < 3; i++) { cl[i] = q[i] < -h[i] ? -h[i] : (q[i] > h[i] ? h[i] : q[i]); dl[i] = q[i] - cl[i]; if (dl[i] != 0) inside = 0; }
+  if (!inside) {
+    double len = norm3(dl);
+    dist = len;
+    for (int i = 0; i < 3; i++) nl[i] = dl[i] / len;
+  } else {
+    int best = 0; double depth = 1e300;
+    for (int i = 0; i < 3; i++) { double e = h[i] - fabs(q[i]); if (e < depth) { depth = e; best = i; } }
+    dist = -depth;
+    nl[best] = q[best] >= 0 ? 1 : -1;
+  }
+  mulMatVec3(nw, R, nl);
+  return dist;
+}
+
+/* convex mesh g (hull vertices in the body frame) against the height field / the static boxes */
+static void collideMeshTerrain(OData* d, int g) {
+  const QsModel* m = &d->m;
+  const QsGeomParams* gp = &m->geom_par[g];
+  const int b = m->geom_body[g], nv = m->geom_vertnum[g];
+  const double* v = d->vert + 3 * m->geom_vertadr[g];
+  if (m->terrain_type == QS_TERRAIN_HFIELD) {
+    double margin = gp->margin > m->hf_par.margin ? gp->margin : m->hf_par.margin;
+    double best = 1e300, bp[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
+    for (int i = 0; i < nv; i++) {
+      double p[3], z, n[3];
+      mulMatVec3(p, d->xmat[b], v + 3 * i);
+      for (int k = 0; k < 3; k++) p[k] += d->xpos[b][k];
+      if (!hfieldHeight(d, p[0], p[1], &z, n)) continue;
+      double dist = (p[2] - z) * n[2];
+      if (dist < best) { best = dist; memcpy(bp, p, sizeof(bp)); memcpy(bn, n, sizeof(bn)); }
+    }
+    if (best > margin) return;
+    double pos[3] = {bp[0] - bn[0] * 0.5 * best, bp[1] - bn[1] * 0.5 * best, bp[2] - bn[2] * 0.5 * best};
+    addContact(d, g, 1, 1, best, pos, bn, NULL, &m->hf_par, m->hf_par.friction);
+  } else if (m->terrain_type == QS_TERRAIN_BOXES) {
+    double margin = gp->margin > m->box_par.margin ? gp->margin : m->box_par.margin;
+    double c[3], tmp[3];
+    mulMatVec3(tmp, d->xmat[b], m->geom_bcenter[g]);
+    for (int k = 0; k < 3; k++) c[k] = d->xpos[b][k] + tmp[k];
+    for (int bx = 0; bx < m->nbox; bx++) {
+      double rel[3] = {c[0] - m->box_pos[bx][0], c[1] - m->box_pos[bx][1], c[2] - m->box_pos[bx][2]};
+      double reach = norm3(m->box_half[bx]) + m->geom_rbound[g] + margin + 0.01;
+      if (dot3(rel, rel) > reach * reach) continue; /* bounding spheres: conservative */
+      double best = 1e300, bp[3] = {0, 0, 0}, bn[3] = {0, 0, 1};
+      for (int i = 0; i < nv; i++) {
+        double p[3], nw[3];
+        mulMatVec3(p, d->xmat[b], v + 3 * i);
+        for (int k = 0; k < 3; k++) p[k] += d->xpos[b][k];
+        double dist = pointBoxDistance(m, bx, p, nw);
+        if (dist < best) { best = dist; memcpy(bp, p, sizeof(bp)); memcpy(bn, nw, sizeof(bn)); }
+      }
+      if (best > margin) continue;
+      double pos[3] = {bp[0] - bn[0] * 0.5 * best, bp[1] - bn[1] * 0.5 * best, bp[2] - bn[2] * 0.5 * best};
+      addContact(d, g, 1 + bx, 1, best, pos, bn, NULL, &m->box_par, m->box_friction[bx]);
+    }
+  }
+}
+
 static void collideTerrain(OData* d) {
   const QsModel* m = &d->m;
   if (m->terrain_type == QS_TERRAIN_FLAT) return;
@@ -600,6 +669,7 @@ static void collideTerrain(OData* d) {
           collidePointTerrain(d, g, p, 0.0, QS_GEOM_CYLINDER, NULL);
         }
         break;
+      case QS_GEOM_MESH: collideMeshTerrain(d, g); break;
       default: break;
     }
     /* at most 4 terrain contacts per geom, deepest first (the engine caps its multi-contact routines similarly) */

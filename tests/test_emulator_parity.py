@@ -168,3 +168,52 @@ def test_terrain_scenes_closed_loop(robot, scene, xy, z0):
         worst = max(worst, np.abs(e['qpos'] - qo).max(), np.abs(e['qvel'] - vo).max())
         max_ncon = max(max_ncon, f['ncon'])
     assert max_ncon >= 2 and worst < 1e-8, (max_ncon, worst)
+
+
+@pytest.mark.parametrize('robot,scene,xy', [('mini_cheetah', 'perlin', (3.0, 2.0)), ('hyqreal1', 'perlin', (-4.0, 6.0)), ('mini_cheetah', 'random_boxes', (2.0, -1.0)),
+                                            ('hyqreal1', 'random_boxes', (1.0, 2.5)), ('spot', 'perlin', (5.0, -3.0))])
+def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
+    """Convex-mesh links against the height field / static boxes (reference test matrix: mini_cheetah, hyqreal1, hyqreal2 x perlin,
+    tests/env_test.py:14-16): the robot is dropped limp onto the terrain so that thighs, calves and the trunk end up lying on it;
+    the kernel source (fp64, emulated warp) must produce the oracle's contact set -- including the mesh geoms -- at every step."""
+    m = Model(robot, scene)
+    rng = np.random.RandomState(11)
+    key = np.array(m.c.key_qpos)
+    q = key.copy()
+    q[0:2] = np.array(xy) + rng.uniform(-0.3, 0.3, 2)
+    q[2] = 1.2 if robot != 'hyqreal1' else 1.6
+    o = Oracle(m)
+    o.set_state(q, np.zeros(18), np.zeros(18)); assert o.lift() >= 0
+    o.set_env(0.8, 0.8, [0, 0, 0, 0])
+    mesh = np.array([m.c.geom_type[g] == 7 for g in range(m.c.ngeom)])
+    assert mesh.any()
+    mesh_terrain_contacts, worst, steps = 0, 0.0, 0
+    for k in range(400):
+        q0, v0, _, w0 = o.get_state()
+        ctrl = np.zeros(12)
+        o.step(ctrl)
+        f = o.flags()
+        if f['ncon'] == 0 or k % 3:
+            continue  # emulate only every third contact step (32 host threads per emulated step are slow)
+        e = emu_step(m, q0, v0, w0, ctrl, 0.8, 0.8, [0, 0, 0, 0], precision=1, mode=1)
+        steps += 1
+        if f['ncon'] > 16:
+            assert e['overflow']
+            continue
+        assert e['ncon'] == f['ncon'] and e['invalid_mask'] == f['invalid_body_mask'], f'step {k}'
+        assert e['contact_mask'] == sum(int(b) << i for i, b in enumerate(f['contact_state']))
+        oc = o.get(F_CONTACTS) if False else None
+        qo, vo, _, _ = o.get_state()
+        worst = max(worst, np.abs(e['qpos'] - qo).max(), np.abs(e['qvel'] - vo).max())
+        # contacts of the forward pass the step started from
+        o2 = Oracle(m); o2.set_state(q0, v0, w0); o2.set_env(0.8, 0.8, [0, 0, 0, 0]); o2.forward(ctrl)
+        oc = o2.get(F_CONTACTS); ec = e['contacts']
+        key_ = lambda c: np.lexsort((np.round(c[:, 0], 9), c[:, 16]))
+        oc, ec = oc[key_(oc)], ec[key_(ec)]
+        assert (oc[:, 16:18] == ec[:, 16:18]).all()
+        np.testing.assert_allclose(ec[:, 0:13], oc[:, 0:13], atol=1e-9)
+        on_terrain = np.abs(oc[:, 3]) > 1e-3 if scene == 'random_boxes' else np.ones(len(oc), dtype=bool)  # contact point above the floor plane
+        mesh_terrain_contacts += int((mesh[oc[:, 16].astype(int)] & on_terrain & (oc[:, 3] - 0.5 * oc[:, 0] > 0.01)).sum())
+        if steps >= 45:
+            break
+    assert mesh_terrain_contacts >= 5 and worst < 1e-8, (mesh_terrain_contacts, worst)

@@ -495,3 +495,57 @@ def test_rollout_recorder_from_gpu_rollout(tmp_path, cuda_device):
         assert time[t, 0] == float(st[3])
     assert data['terminated'].shape == (6, 1) and data['qpos'].dtype == np.float64
     env.close()
+
+
+@pytest.mark.parametrize('robot,scene,xy', [('mini_cheetah', 'perlin', (3.0, 2.0)), ('hyqreal1', 'perlin', (-4.0, 6.0)), ('mini_cheetah', 'random_boxes', (2.0, -1.0))])
+def test_mesh_links_collide_with_the_terrain(robot, scene, xy, cuda_device):
+    """Mesh robots on non-flat terrain (the reference's own test matrix runs mini_cheetah / hyqreal1 / hyqreal2 x perlin,
+    tests/env_test.py:14-16): convex-mesh links against the height field / static boxes.  The robots are dropped limp so that
+    thighs, calves and trunk come to rest on the terrain; closed loop against the oracle (re-seeded from the GPU state each step):
+    contact count, contact_state, invalid-contact mask and termination identical, state to single-step fp32 accuracy."""
+    m = Model(robot, scene)
+    n, T = 6, 330
+    rng = np.random.RandomState(11)
+    key = np.array(m.c.key_qpos)
+    qpos = np.tile(key, (n, 1)); qvel = np.zeros((n, 18))
+    for i in range(n):
+        qpos[i, 0:2] = np.array(xy) + rng.uniform(-0.8, 0.8, 2)
+        qpos[i, 2] = 1.2 if robot != 'hyqreal1' else 1.6
+        qpos[i, 7:] += rng.uniform(-0.2, 0.2, 12)
+    qpos = qpos.astype(np.float32).astype(np.float64)
+    sim = BatchSim(m, n, device=cuda_device)
+    assert sim.step_variant in ('f3', 'f6')  # mesh x terrain runs on the generic kernel
+    sim.set_state(torch.tensor(qpos), torch.tensor(qvel))
+    sim.friction[:] = 0.8
+    orc = [Oracle(m) for _ in range(n)]
+    for o in orc:
+        o.set_env(0.8, 0.8, [0, 0, 0, 0])
+    mesh = np.array([m.c.geom_type[g] == 7 for g in range(m.c.ngeom)])
+    ctrl = torch.zeros(n, 12, device=cuda_device)
+    worst, mesh_contacts, ties = 0.0, 0, 0
+    for t in range(T):
+        q0, v0 = _state(sim)
+        w0 = sim.qacc_warmstart.cpu().numpy().astype(np.float64)
+        obs, _, term, _ = sim.step(ctrl)
+        q1, v1 = _state(sim)
+        inv = sim.invalid_body_mask.cpu().numpy().astype(np.int64)
+        for i, o in enumerate(orc):
+            o.set_state(q0[i], v0[i], w0[i])
+            _, ref_term = o.step(np.zeros(12))
+            f = o.flags()
+            if f['ncon'] > 16:
+                continue  # the 16-slot contact buffer is full (status bit 1): flags stay exact (own test), forces do not
+            same = (bool(term[i].item()) == ref_term and int(sim.ncon[i].item()) == f['ncon'] and (inv[i, 0] | (inv[i, 1] << 8)) == f['invalid_body_mask']
+                    and ((obs[i, 199:203].cpu().numpy() > 0.5) == f['contact_state']).all())
+            oc = o.get(F_CONTACTS)
+            if not same:  # a contact within fp32 rounding of its activation distance (same rule as test_terrain_scenes_match_oracle)
+                assert len(oc) and np.abs(oc[:, 0]).min() < 3e-6, f'step {t} env {i}: contact set differs'
+                ties += 1
+                continue
+            if len(oc):
+                mesh_contacts += int((mesh[oc[:, 16].astype(int)] & (oc[:, 3] > 0.02)).sum())
+            qo, vo, _, _ = o.get_state()
+            if f['ncon'] <= 6:  # many redundant contacts of a body lying on the terrain: ill-conditioned, held to the flags only
+                worst = max(worst, np.abs(q1[i] - qo).max(), 0.1 * np.abs(v1[i] - vo).max())
+    # single-step bound: several contacts on one lying link are a redundant, stiff problem (cf. test_terrain_scenes_match_oracle)
+    assert mesh_contacts >= 50 and ties <= 6 and worst < 3e-4, (mesh_contacts, ties, worst)
