@@ -238,6 +238,8 @@ def run_gpu(args):
     from gym_quadruped_b200.distributed import ObsGather
     from gym_quadruped_b200.model import Model
 
+    import faulthandler
+    faulthandler.dump_traceback_later(420, exit=True)  # watchdog: a stuck collective must not hold the GPUs (stack traces, then exit)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -350,14 +352,19 @@ def run_gpu(args):
     for i in range(5):
         ser.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=ser_opt)
     e2e_regions, total = [], 0.0
-    while len(e2e_regions) < 5 or total < 0.25:
+    while True:
         barrier()
         t0 = time.perf_counter()
         for i in range(K):
             ser.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=ser_opt)
         dt = time.perf_counter() - t0
         e2e_regions.append(dt); total += dt
-        if len(e2e_regions) >= 400:
+        more = (len(e2e_regions) < 5 or total < 0.25) and len(e2e_regions) < 400
+        if world > 1:  # every rank must take the same number of trips through the barrier
+            flag = torch.tensor([1.0 if more else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            more = bool(flag.item() > 0)
+        if not more:
             break
     e2e_s = statistics.median(e2e_regions)
     h2d = envs * 12 * 4
@@ -381,15 +388,24 @@ def run_gpu(args):
     gather = None
     if world > 1:
         gather = {}
-        for mode in ('p2p', 'nccl'):
+        check = {}
+        for mode in ('nccl', 'p2p'):
+            gsim, gopt = make_sim(pipeline=not args.no_pipeline)  # same seed: both modes replay the same rollout
             try:
-                g = ObsGather(sim, mode=mode)
+                g = ObsGather(gsim, mode=mode)
             except Exception as e:  # noqa: BLE001
                 gather[mode] = {'unavailable': str(e)[:200]}
                 continue
+
+            def gstep(i):
+                g.step_autoreset(actions[i % ring], gopt)
+                with torch.cuda.stream(g.side):  # the consumer of the gathered rows lives on its own stream
+                    rows = g.wait()
+                    if not os.environ.get('QS_BENCH_NO_RELEASE'):
+                        g.release()
+                return rows
             for i in range(10):
-                g.step_autoreset(actions[i % ring], opt)
-            g.wait()
+                rows = gstep(i)
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reg = []
@@ -397,16 +413,22 @@ def run_gpu(args):
                 barrier()
                 g0.record()
                 for i in range(K):
-                    g.step_autoreset(actions[i % ring], opt)
-                g.wait()  # the gathered tensor of the last step is complete on this rank
+                    rows = gstep(10 + i)
+                torch.cuda.current_stream(dev).wait_stream(g.side)  # the region ends when the last gathered tensor is complete
                 g1.record()
                 barrier()
                 reg.append(g0.elapsed_time(g1))
+            check[mode] = rows.clone()
             t = torch.tensor(reg, dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             gather[mode] = {'ms_per_step': float(t.median()) / K, 'value': n_gpus * envs * K / (float(t.median()) * 1e-3),
-                            'bytes_received_per_rank_per_step': (world - 1) * envs * sim.obs_dim * 4, 'how': g.describe()}
+                            'bytes_received_per_rank_per_step': (world - 1) * envs * gsim.obs_dim * 4, 'how': g.describe()}
             g.close()
+            gsim.close()
+        if len(check) == 2:  # both modes ran the same rollout: the gathered tensors must be bit-identical, on every rank
+            same = torch.tensor([float(torch.equal(check['nccl'], check['p2p']))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            gather['p2p_equals_nccl_bitwise'] = bool(same.item() == 1.0)
 
     # ---- reduce over ranks (max time)
     t = torch.tensor([ser_ms, launch_ms, cold_ms, e2e_s, f64_ms or 0.0], dtype=torch.float64, device=dev)

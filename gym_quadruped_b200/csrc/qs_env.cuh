@@ -64,6 +64,10 @@ template <typename real> struct alignas(16) DModel {
 //                                                                      | obs (staged observation row)  : after Euler
 template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
   static constexpr int NW = MAXDIM * (MAXDIM + 1) / 2;  // packed symmetric contact weight
+  // staged terrain boxes (collision stage): they overlay everything behind tmp.cinert, which is written later in the step
+  static constexpr int kStgPad = NV * 6 + NB * 10;
+  static constexpr int kUnionWords = (NCON * MAXDIM * 9 > NV * 6 + NB * 22) ? NCON * MAXDIM * 9 : NV * 6 + NB * 22;
+  static constexpr int KST = int((kUnionWords - kStgPad) * sizeof(real) / sizeof(DBox<real>));
   // state (internal frame: base xy relative to the per-env origin `org`)
   real qpos[20], qvel[NV], ctrl[NU], warm[NV], applied[6];
   real mu_floor, mu_feet;
@@ -79,7 +83,9 @@ template <typename real, int NCON, int MAXDIM> struct alignas(16) WS {
     struct { real cdofdot[NV][6], cinert[NB][10], cvel[NB][6], cfrc[NB][6]; } tmp;
     real Jc[NCON][MAXDIM][9];
     real obs[NOBS_BASE + 5];
+    struct { real pad_[kStgPad]; DBox<real> box[KST]; } stg;
   };
+  unsigned char near_id[32];  // global index of the k-th static box within reach of the robot (k < nnear)
   // block mass matrix: base-base, leg-base, leg-leg
   real Mbb[6][6], Mlb[4][3][6], Mll[4][3][3];
   // dof vectors
@@ -663,7 +669,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   }
   // point feature (centre p, radius r) against the height field or the candidate boxes; robot_first: sphere / capsule sort
   // before box in the engine's geom ordering, so the robot geom is geom1 and the normal points from it into the box
-  QS_DEV void point_vs_terrain(const real* p, real r, real margin, bool robot_first, const unsigned* boxmask, Cand* list, int& n) const {
+  QS_DEV void point_vs_terrain(const real* p, real r, real margin, bool robot_first, unsigned boxmask, Cand* list, int& n) const {
     if (ttype() == 1) {
       real z, nn[3];
       if (!hfield_height(p[0], p[1], z, nn)) return;
@@ -674,12 +680,13 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       for (int i = 0; i < 3; i++) { c.nrm[i] = nn[i]; c.pos[i] = p[i] - nn[i] * (r + real(0.5) * dist); }
       cand_insert(list, n, c);
     } else if (ttype() == 2) {
-      for (int wd = 0; wd < 4; wd++) {
-        unsigned mask = boxmask[wd];
+      {
+        unsigned mask = boxmask;
         while (mask) {
-          const int b = 32 * wd + ctz(mask);
+          const int k = ctz(mask);
           mask &= mask - 1;
-          const DBox<real>& bx = boxes[b];
+          const DBox<real>& bx = near_box(k);
+          const int b = w.near_id[k];
           const real rel[3] = {p[0] - bx.pos[0], p[1] - bx.pos[1], p[2] - bx.pos[2]};
           const real reach = bx.rad + r + real(0.01);
           if (dot3(rel, rel) > reach * reach) continue;
@@ -713,8 +720,15 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   // Primitive robot geoms against the perlin height field / the static boxes, as feature points (sphere centre + radius, capsule
   // end spheres, box corners) -- exact for sphere-box and plane-like cases, an approximation of the engine's capsule-box,
   // box-box and prism-based hfield routines otherwise (documented in DESIGN.md).  Appends after the floor contacts.
-  unsigned boxnear[4] = {0, 0, 0, 0};  // static boxes within reach of the robot (warp-uniform), refreshed by every collision pass
+  // Static boxes within reach of the robot, found once per collision pass and renumbered 0 .. nnear-1 (at most 32; more would raise
+  // the overflow flag).  The first KST of them are staged in shared memory -- a contact-rich pass reads every near box dozens of
+  // times (per geom, per feature point), and the lift loop of a reset repeats the pass up to 100 times -- the rest stay in global.
+  int nnear = 0;
+  bool near_overflow = false;
+  static constexpr int KST = W::KST;
+  QS_DEV const DBox<real>& near_box(int k) const { return k < KST ? w.stg.box[k] : boxes[w.near_id[k]]; }
   QS_DEV void find_near_boxes() {
+    int n = 0;
     for (int wd = 0; wd < 4; wd++) {
       const int b = 32 * wd + lane;
       bool near = false;
@@ -723,11 +737,26 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
         const real reach = boxes[b].rad + m.robot_radius;
         near = dot3(rel, rel) < reach * reach;
       }
-      boxnear[wd] = ballot(near);
+      const unsigned mask = ballot(near);
+      const int pos = n + popc(mask & ((1u << lane) - 1u));
+      if (near && pos < 32) w.near_id[pos] = (unsigned char)b;
+      n += popc(mask);
     }
+    near_overflow = n > 32;
+    nnear = n > 32 ? 32 : n;
+    syncwarp();
+    // cooperative copy in 16-byte chunks (DBox is a multiple of 16 bytes)
+    constexpr int CH = int(sizeof(DBox<real>) / 16);
+    static_assert(sizeof(DBox<real>) % 16 == 0, "DBox must be a multiple of 16 bytes");
+    struct alignas(16) Chunk { unsigned v[4]; };
+    const int nst = nnear < KST ? nnear : KST;
+    Chunk* dst = reinterpret_cast<Chunk*>(&w.stg.box[0]);
+    const Chunk* src = reinterpret_cast<const Chunk*>(boxes);
+    for (int i = lane; i < nst * CH; i += 32) dst[i] = src[int(w.near_id[i / CH]) * CH + i % CH];
+    syncwarp();
   }
   QS_DEV void collide_terrain(int& ncon, const int gbase) {
-    unsigned boxmask[4] = {boxnear[0], boxnear[1], boxnear[2], boxnear[3]};
+    unsigned boxmask = nnear >= 32 ? 0xffffffffu : ((1u << nnear) - 1u);
     Cand list[4];
     int n = 0;
     const int g = gbase + lane;
@@ -744,17 +773,17 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
         // per-geom cull of the warp-wide candidate set: bounding sphere of the geom against the bounding sphere of each box
         // (a superset of what the per-feature test below accepts, so the contact set is unchanged)
         const real rb = m.geom_rbound[g] + margin + real(0.01);
-        for (int wd = 0; wd < 4; wd++) {
-          unsigned mask = boxmask[wd], keep = 0;
+        {
+          unsigned mask = boxmask, keep = 0;
           while (mask) {
             const int bit = ctz(mask);
             mask &= mask - 1;
-            const DBox<real>& bx = boxes[32 * wd + bit];
+            const DBox<real>& bx = near_box(bit);
             const real rel[3] = {gx[0] - bx.pos[0], gx[1] - bx.pos[1], gx[2] - bx.pos[2]};
             const real reach = bx.rad + rb;
             if (dot3(rel, rel) <= reach * reach) keep |= 1u << bit;
           }
-          boxmask[wd] = keep;
+          boxmask = keep;
         }
       }
       if (type == GEOM_SPHERE) {
@@ -840,7 +869,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
                             c[1] + rb < m.hf_pos[1] - m.hf_size[1] || c[1] - rb > m.hf_pos[1] + m.hf_size[1]);
         near = over && !(c[2] - rb > bound + N::max(m.geom_margin[g], m.terr_margin) + real(1e-4));
       } else {
-        near = (boxnear[0] | boxnear[1] | boxnear[2] | boxnear[3]) != 0;
+        near = nnear > 0;
       }
     }
     unsigned cand = ballot(near);
@@ -889,12 +918,10 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
         for (int i = 0; i < 3; i++) c[i] = X[i] + tmp[i];
         const real* bh = m.geom_bhalf[gm_];
         const real rb = N::sqrt(bh[0] * bh[0] + bh[1] * bh[1] + bh[2] * bh[2]) + margin + real(0.01);
-        for (int wd = 0; wd < 4; wd++) {
-          unsigned mask = boxnear[wd];
-          while (mask) {
-            const int bx = 32 * wd + ctz(mask);
-            mask &= mask - 1;
-            const DBox<real>& B = boxes[bx];
+        {
+          for (int kb = 0; kb < nnear; kb++) {
+            const int bx = w.near_id[kb];
+            const DBox<real>& B = near_box(kb);
             const real rel[3] = {c[0] - B.pos[0], c[1] - B.pos[1], c[2] - B.pos[2]};
             const real reach = B.rad + rb;
             if (dot3(rel, rel) > reach * reach) continue;
@@ -996,7 +1023,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
 #pragma unroll 1
       for (int gbase = 0; gbase < m.ngeom; gbase += 32) collide_round(gbase, ncon);
     }
-    if (lane == 0) { w.overflow = ncon > NCON; w.ncon = ncon > NCON ? NCON : ncon; }
+    if (lane == 0) { w.overflow = ncon > NCON || near_overflow; w.ncon = ncon > NCON ? NCON : ncon; }
     syncwarp();
   }
   QS_DEV void collide_round(const int gbase, int& ncon) {

@@ -22,6 +22,7 @@
 namespace qs {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
+constexpr int QS_QUEUE_DEPTH = 8;
 constexpr int NCON_MAX = 16;
 constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6 + 3 * 216;  // 1640
 constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_JACP = 360, AUX_OFF_FEETPOS = 576, AUX_OFF_COM = 588,
@@ -50,11 +51,20 @@ struct KParams {
   // (programmatic dependent launch, QsConfig.pipeline) without any grid-wide dependency: the tail of step t, set by its slowest env,
   // runs next to the head of step t+1.  Envs that finish together are also the ones of similar cost, so a CTA that takes 28
   // consecutive slots gets a homogeneous group (pipelined mode); the serialized mode deals the slots round-robin over the CTAs instead.
+  // The queues form a ring of QS_QUEUE_DEPTH entries (launch s reads entry s % DEPTH and fills (s + 1) % DEPTH), so fast envs can run
+  // up to DEPTH - 1 launches ahead of a straggler (e.g. an env whose reset lifts it 100 times out of a box) before they wait for it.
   int* q_in; int* q_out;
   unsigned* q_tail;        // monotonic publish counter of q_out
   unsigned q_tail_base;    // its value before this launch's first publish
   int q_contiguous;        // 1: CTA c takes slots [c*W, c*W + W); 0: slot = warp * gridDim + c
   int q_sync;              // 1: launches of this handle may overlap -> acquire / release on the queue slots; 0: the grid boundary orders everything
+  // Peer-to-peer observation gather fused into the step (north_star's one collective): with gather_world > 1
+  // every warp also stores its finished observation row into the [world * N, D] tensor of EVERY rank (peer-mapped memory, NVLink),
+  // and the warp that completes the launch raises this rank's flag on every peer.  `obs` then points into this rank's own tensor.
+  float* gather_peers[8];      // base of the parity-selected gathered tensor on rank q (own rank: local memory)
+  unsigned* gather_flags[8];   // [world] flags on rank q for this parity; rank r writes entry r
+  int gather_world, gather_rank;
+  unsigned gather_seq;         // value written to the flags: number of gather steps of this parity so far
   // in-episode schedules (quadruped_env.py:293-305): command resampling ('+reset' types) and external-wrench resampling
   int sch_command_mode, sch_ext_enabled;
   float sch_lin[2], sch_ang[2], sch_ext_lo[6], sch_ext_hi[6];
@@ -150,25 +160,34 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   const long long t_entry = clock64();
 #endif
   if (threadIdx.x == 0) mbar_init(mbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_bulk_load(dm, p.dm, static_cast<uint32_t>(sizeof(DM)), mbar);
   if (MODE == MODE_STEP) {
-    // take this warp's env from the finish-order queue of the previous step launch (results do not depend on the placement)
+    // The next step launch may be scheduled as soon as every CTA of this one is resident (or done): whatever env one of its warps
+    // waits for is then held by a running warp, so the waits below always end.  Without the pipeline attribute on the next launch
+    // this is a no-op.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // take this warp's env from the finish-order queue filled by the previous step launch (results do not depend on the
+    // placement)
     const int slot = p.q_contiguous ? blockIdx.x * nwarp + warp : warp * int(gridDim.x) + int(blockIdx.x);
     env = p.num_envs;
     if (slot < p.num_envs) {
       int e_ = 0;
       if (lane == 0) {
-        if (p.q_sync) { while ((e_ = ld_acquire(p.q_in + slot)) < 0) __nanosleep(100); }
-        else e_ = p.q_in[slot];  // plain stream order: the previous launch has completed, every slot is filled
-        p.q_in[slot] = -1;  // consumed: the launch after the next one refills this queue
+        if (p.q_sync) {
+          while ((e_ = ld_acquire(p.q_in + slot)) < 0) __nanosleep(200);
+          st_release(p.q_in + slot, -1);  // consumed: free for the launch that reuses this ring entry (QS_QUEUE_DEPTH launches later)
+        } else {
+          e_ = p.q_in[slot];  // plain stream order: the previous launch has completed, every slot is filled
+          p.q_in[slot] = -1;
+        }
       }
       env = __shfl_sync(0xffffffffu, e_, 0);
     }
+    // The warps of a CTA start their envs together: a convoy that runs through the same code shares its instruction-cache fills
+    // (measured: letting every warp start as soon as its own slot is filled costs 45 % throughput on mini_cheetah / flat).
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) tma_bulk_load(dm, p.dm, static_cast<uint32_t>(sizeof(DM)), mbar);
-  // Every slot of this CTA has been read: a dependent launch may start (it overwrites q_in only after all CTAs got here).
-  // Without the pipeline attribute on the next launch this is a no-op.
-  if (MODE == MODE_STEP) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   bool active = env < p.num_envs;
   if (MODE == MODE_RESET && active && p.mask) active = p.mask[env] != 0;
@@ -618,6 +637,26 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
                   obs + NOBS_BASE + (p.use_imu ? QS_NOBS_IMU : 0));
     }
     if (!(FEAT & FEAT_NO_IMU) && p.use_imu) imu_step(obs, !resetting);
+    if (MODE == MODE_STEP && p.gather_world > 1 && obs && !(p.auto_reset && !resetting && terminated)) {
+      // final observation row of this env (a terminated env under auto-reset sends its post-reset row from the second pass):
+      // straight to the gathered tensor of every peer, 16-B stores where the destination allows
+      syncwarp();
+      const size_t row = (size_t(p.gather_rank) * p.num_envs + env) * p.obs_dim;
+      auto val = [&](int i) { return i < NOBS_BASE ? float(w.obs[i]) : __ldcg(obs + i); };
+      for (int q = 0; q < p.gather_world; q++) {
+        if (q == p.gather_rank) continue;
+        float* dst = p.gather_peers[q] + row;
+        const int head = (4 - int((reinterpret_cast<size_t>(dst) >> 2) & 3)) & 3;
+        if (lane < head) dst[lane] = val(lane);
+        const int nvec = (p.obs_dim - head) >> 2;
+        for (int v = lane; v < nvec; v += 32) {
+          const int i = head + 4 * v;
+          *reinterpret_cast<float4*>(dst + i) = make_float4(val(i), val(i + 1), val(i + 2), val(i + 3));
+        }
+        const int done = head + 4 * nvec;
+        if (lane < p.obs_dim - done) dst[done + lane] = val(done + lane);
+      }
+    }
     if (MODE == MODE_STEP && !resetting) schedule_update();
     if (lane == 0) {
       B.sim_time[env] = sim_time;
@@ -645,8 +684,21 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     // (all lanes' stores happen-before lane 0's fence) -- the consumer's acquire load pairs with it.
     __syncwarp();
     if (lane == 0) {
+      if (p.gather_world > 1) __threadfence_system();  // this warp's peer stores are performed before it counts as finished
       const unsigned pos = atomicAdd(p.q_tail, 1u) - p.q_tail_base;
-      if (p.q_sync) st_release(p.q_out + pos, env); else p.q_out[pos] = env;
+      if (p.q_sync) {
+        while (ld_acquire(p.q_out + pos) >= 0) __nanosleep(200);  // the consumer of this ring entry's previous use is far behind: wait
+        st_release(p.q_out + pos, env);
+      } else {
+        p.q_out[pos] = env;
+      }
+      if (p.gather_world > 1 && pos == unsigned(p.num_envs) - 1u) {
+        // last env of the launch: every other warp fenced before its increment, so all rows of this rank are on their way before
+        // the flag; release at system scope, the peers' wait kernel acquires it
+        __threadfence_system();
+        for (int q = 0; q < p.gather_world; q++)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.gather_flags[q] + p.gather_rank), "r"(p.gather_seq) : "memory");
+      }
     }
   }
 #ifdef QS_PROF

@@ -57,10 +57,24 @@ __global__ void schedule_init_kernel(const KParams p) {
   p.ext_epoch[env] = ee + 1;
 }
 
-__global__ void queue_init_kernel(int* q0, int* q1, unsigned* tails, int n) {
+// qs_gather_wait: one thread per rank polls this rank's flag slots until every rank has published step `seq` of this parity
+__global__ void gather_wait_kernel(const unsigned* flags, int world, unsigned seq) {
+  if (int(threadIdx.x) < world) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+      if (int(v - seq) < 0) __nanosleep(200);
+    } while (int(v - seq) < 0);
+  }
+}
+
+__global__ void queue_init_kernel(int* q, unsigned* tails, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { q0[i] = i; q1[i] = -1; }
-  if (i < 2) tails[i] = 0;
+  if (i < n) {
+    q[i] = i;  // ring entry 0: identity placement for the first launch
+    for (int r = 1; r < QS_QUEUE_DEPTH; r++) q[size_t(r) * n + i] = -1;
+  }
+  if (i < QS_QUEUE_DEPTH) tails[i] = 0;
 }
 
 }  // namespace
@@ -74,12 +88,21 @@ struct QsHandle_ {
   void* d_hf = nullptr;
   void* d_boxes = nullptr;
   KernelFn k_raycast = nullptr;
-  int* d_queue = nullptr;          // 2 x [N] finish-order queues (see KParams)
-  unsigned* d_queue_tail = nullptr; // 2 monotonic publish counters
-  uint64_t step_seq = 0;           // number of step launches so far: launch s reads queue s % 2 and fills queue (s + 1) % 2
+  int* d_queue = nullptr;          // QS_QUEUE_DEPTH x [N] finish-order queues (see KParams)
+  unsigned* d_queue_tail = nullptr; // one monotonic publish counter per ring entry
+  uint64_t step_seq = 0;           // number of step launches so far: launch s reads ring entry s % DEPTH and fills (s + 1) % DEPTH
   bool last_was_step = false;      // the previous launch of this handle was a step kernel (nothing of ours in between)
   void* last_stream = nullptr;
   const char* step_variant = "";
+  // peer-to-peer observation gather (qs_gather_*)
+  struct {
+    int world = 0, rank = 0;
+    unsigned char* block = nullptr;     // this rank's allocation: 2 gathered tensors + 2 x 8 flags
+    unsigned char* peer[8] = {};        // the same block on every rank (peer[rank] == block)
+    size_t tensor_bytes = 0;
+    uint64_t steps = 0;                 // gather steps launched so far
+    bool connected = false;
+  } gather;
   QsSchedule sched{};
   unsigned* d_episode = nullptr;
   unsigned* d_tick = nullptr;
@@ -195,13 +218,13 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
   if (rc == 0) {
     const size_t n = size_t(cfg->num_envs);
     unsigned* ctr = nullptr;  // episode | tick | cmd_epoch | ext_epoch
-    cudaError_t e1 = cudaMalloc(&ctr, 4 * n * sizeof(unsigned)), e2 = cudaMalloc(&h->d_queue, 2 * n * sizeof(int)),
-                e3 = cudaMalloc(&h->d_queue_tail, 2 * sizeof(unsigned));
+    cudaError_t e1 = cudaMalloc(&ctr, 4 * n * sizeof(unsigned)), e2 = cudaMalloc(&h->d_queue, QS_QUEUE_DEPTH * n * sizeof(int)),
+                e3 = cudaMalloc(&h->d_queue_tail, QS_QUEUE_DEPTH * sizeof(unsigned));
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) rc = fail(h, 5, "cudaMalloc failed");
     else {
       h->d_episode = ctr; h->d_tick = ctr + n; h->d_cmd_epoch = ctr + 2 * n; h->d_ext_epoch = ctr + 3 * n;
       cudaMemset(ctr, 0, 4 * n * sizeof(unsigned));
-      queue_init_kernel<<<unsigned((n + 255) / 256), 256>>>(h->d_queue, h->d_queue + n, h->d_queue_tail, int(n));
+      queue_init_kernel<<<unsigned((n + 255) / 256), 256>>>(h->d_queue, h->d_queue_tail, int(n));
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(h, 5, "queue initialisation failed");
     }
   }
@@ -212,6 +235,7 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
 
 void qs_destroy(QsHandle* h) {
   if (!h) return;
+  if (h->gather.block) qs_gather_close(h);
   cudaFree(h->d_queue); cudaFree(h->d_queue_tail);
   cudaFree(h->d_dm); cudaFree(h->d_vert); cudaFree(h->d_hf); cudaFree(h->d_boxes); cudaFree(h->d_episode); cudaFree(h->d_aux);
   cudaFree(h->d_ctrl); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
@@ -253,6 +277,69 @@ int qs_set_seed(QsHandle* h, uint64_t seed, void* stream) {
 }
 
 const char* qs_step_variant(QsHandle* h) { return h ? h->step_variant : ""; }
+
+int qs_gather_create(QsHandle* h, int world, int rank, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(h, 1, "qs_gather_create: null argument");
+  if (world < 2 || world > 8 || rank < 0 || rank >= world) return fail(h, 1, "qs_gather_create: world must be 2..8");
+  if (h->gather.block) return fail(h, 1, "qs_gather_create: already created");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  auto& g = h->gather;
+  g.world = world; g.rank = rank;
+  g.tensor_bytes = (size_t(world) * h->cfg.num_envs * h->obs_dim * sizeof(float) + 255) & ~size_t(255);
+  const size_t total = 2 * g.tensor_bytes + 256;
+  QS_CUDA(h, cudaMalloc(&g.block, total));
+  QS_CUDA(h, cudaMemset(g.block, 0, total));
+  cudaIpcMemHandle_t hd;
+  QS_CUDA(h, cudaIpcGetMemHandle(&hd, g.block));
+  std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+  return 0;
+}
+
+int qs_gather_connect(QsHandle* h, const void* ipc_handles) {
+  if (!h || !h->gather.block || !ipc_handles) return fail(h, 1, "qs_gather_connect: call qs_gather_create first");
+  auto& g = h->gather;
+  for (int q = 0; q < g.world; q++) {
+    if (q == g.rank) { g.peer[q] = g.block; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const unsigned char*>(ipc_handles) + 64 * q, sizeof(hd));
+    void* ptr = nullptr;
+    QS_CUDA(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    g.peer[q] = static_cast<unsigned char*>(ptr);
+  }
+  g.connected = true;
+  h->last_was_step = false;
+  return 0;
+}
+
+void* qs_gather_buffer(QsHandle* h, int parity) {
+  return (h && h->gather.block) ? h->gather.block + size_t(parity & 1) * h->gather.tensor_bytes : nullptr;
+}
+
+uint64_t qs_gather_steps(QsHandle* h) { return h ? h->gather.steps : 0; }
+
+int qs_gather_wait(QsHandle* h, uint64_t step_index, void* stream) {
+  if (!h || !h->gather.connected) return fail(h, 1, "qs_gather_wait: gather not connected");
+  if (step_index == 0) return 0;
+  auto& g = h->gather;
+  const int k = int((step_index - 1) & 1);
+  const unsigned seq = unsigned((step_index + 1) / 2);
+  const unsigned* flags = reinterpret_cast<const unsigned*>(g.block + 2 * g.tensor_bytes) + 8 * k;
+  gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, g.world, seq);
+  h->launches++;
+  QS_CUDA(h, cudaGetLastError());
+  return 0;
+}
+
+int qs_gather_close(QsHandle* h) {
+  if (!h) return 1;
+  auto& g = h->gather;
+  for (int q = 0; q < g.world; q++)
+    if (q != g.rank && g.peer[q]) cudaIpcCloseMemHandle(g.peer[q]);
+  if (g.block) cudaFree(g.block);
+  g = {};
+  h->last_was_step = false;
+  return 0;
+}
 
 static KParams base_params(QsHandle* h) {
   KParams p{};
@@ -307,12 +394,24 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
   {
     const size_t n = size_t(h->cfg.num_envs);
     const uint64_t s = h->step_seq++;
-    const int in = int(s & 1), out = in ^ 1;
+    const int in = int(s % QS_QUEUE_DEPTH), out = int((s + 1) % QS_QUEUE_DEPTH);
     p.q_in = h->d_queue + size_t(in) * n; p.q_out = h->d_queue + size_t(out) * n;
     p.q_tail = h->d_queue_tail + out;
-    p.q_tail_base = unsigned((s / 2) * n);  // launches s-2, s-4, ... published n entries each through this counter
+    p.q_tail_base = unsigned((s / QS_QUEUE_DEPTH) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
     p.q_contiguous = h->cfg.pipeline ? 1 : 0;
     p.q_sync = h->cfg.pipeline ? 1 : 0;
+  }
+  if (h->gather.connected) {
+    auto& g = h->gather;
+    const int k = int(g.steps & 1);
+    g.steps++;
+    p.gather_world = g.world; p.gather_rank = g.rank;
+    p.gather_seq = unsigned((g.steps + 1) / 2);  // 1, 1, 2, 2, ...: the count of steps of this parity
+    for (int q = 0; q < g.world; q++) {
+      p.gather_peers[q] = reinterpret_cast<float*>(g.peer[q] + size_t(k) * g.tensor_bytes);
+      p.gather_flags[q] = reinterpret_cast<unsigned*>(g.peer[q] + 2 * g.tensor_bytes) + 8 * k;
+    }
+    p.obs = p.gather_peers[g.rank] + size_t(g.rank) * h->cfg.num_envs * h->obs_dim;  // own rows live in the gathered tensor itself
   }
   const bool chained = h->cfg.pipeline && h->last_was_step && h->last_stream == stream;
   const int rc = launch(h, h->k_step, p, static_cast<cudaStream_t>(stream), chained);

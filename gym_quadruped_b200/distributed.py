@@ -43,8 +43,14 @@ class _DevArray:
 class ObsGather:
     """Steps a `BatchSim` shard and keeps, on every rank, the observation rows of ALL ranks: `gathered[k]` is a
     [world * N, D] tensor in global env order, k = step parity (double buffer: the rows of step t stay valid until step t + 2 is
-    enqueued).  Usage per step:  `g.step_autoreset(ctrl, opt)`; ...; `rows = g.wait()` (stream-ordered: kernels enqueued on the
-    current stream after `wait()` see the complete tensor of the last step)."""
+    enqueued).  Per step:
+
+        g.step_autoreset(ctrl, opt)              # on the current stream; in 'p2p' mode the rows travel from inside the kernel
+        with torch.cuda.stream(g.side):          # the consumer lives on its own stream, so the next step is not held back
+            rows = g.wait()                      # stream-ordered: work enqueued after it sees the complete tensor of the last step
+            ... consume rows ...
+            g.release()                          # step t + 2 may overwrite this buffer
+    """
 
     def __init__(self, sim, mode: str = 'p2p', group=None):
         if not dist.is_initialized():
@@ -54,9 +60,11 @@ class ObsGather:
         self.N, self.D, self.dev = sim.N, sim.obs_dim, sim.device
         self.t = 0
         self.side = torch.cuda.Stream(device=self.dev)
+        self._coll = torch.cuda.Stream(device=self.dev)  # 'nccl' mode: the collective's stream
         self._ev_step = [torch.cuda.Event() for _ in range(2)]
-        self._ev_done = [torch.cuda.Event() for _ in range(2)]
-        self._pending = [False, False]
+        self._ev_gath = [torch.cuda.Event() for _ in range(2)]
+        self._ev_rel = [torch.cuda.Event() for _ in range(2)]
+        self._rel_pending = [False, False]
         if mode == 'nccl':
             self.local = [torch.zeros(self.N, self.D, device=self.dev) for _ in range(2)]
             self.gathered = [torch.zeros(self.world * self.N, self.D, device=self.dev) for _ in range(2)]
@@ -68,8 +76,8 @@ class ObsGather:
     # ------------------------------------------------------------------ p2p plumbing (CUDA IPC handles exchanged through the process group)
     def _open_p2p(self):
         L, sim = self.sim.L, self.sim
-        if not hasattr(L, 'qs_gather_create'):
-            raise RuntimeError('libqstep was built without the peer-to-peer gather')
+        if self.world > 8:
+            raise RuntimeError('the peer-to-peer gather spans the GPUs of one node (at most 8)')
         L.qs_gather_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.qs_gather_connect.argtypes = [C.c_void_p, C.c_void_p]
         L.qs_gather_buffer.argtypes = [C.c_void_p, C.c_int]
@@ -92,43 +100,45 @@ class ObsGather:
     def describe(self) -> str:
         if self.mode == 'p2p':
             return ('fused: each warp of the step kernel stores its observation row into the gathered tensor of every rank through '
-                    'peer-mapped memory (CUDA IPC over NVLink), per-rank completion flags raised by the last warp; wait() is a flag-poll kernel on a side stream')
-        return 'NCCL all_gather_into_tensor on a side stream, double-buffered observation rows (overlaps the next step)'
+                    'peer-mapped memory (CUDA IPC over NVLink), per-rank completion flags raised by the last warp of the launch; '
+                    'wait() is a flag-poll kernel on the consumer stream')
+        return 'NCCL all_gather_into_tensor on its own stream, double-buffered observation rows (overlaps the next step)'
 
     # ------------------------------------------------------------------ stepping
     def step_autoreset(self, ctrl, opt):
         k = self.t & 1
         main = torch.cuda.current_stream(self.dev)
-        if self._pending[k]:
-            main.wait_event(self._ev_done[k])  # the consumer / collective of step t - 2 has released this buffer
-            self._pending[k] = False
+        if self._rel_pending[k]:
+            main.wait_event(self._ev_rel[k])  # the consumer of step t - 2 has released this buffer
+            self._rel_pending[k] = False
         if self.mode == 'nccl':
             self.sim.step_autoreset(ctrl, opt, obs_out=self.local[k])
             self._ev_step[k].record(main)
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(self._ev_step[k])
+            with torch.cuda.stream(self._coll):
+                self._coll.wait_event(self._ev_step[k])
                 dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
-                self._ev_done[k].record(self.side)
-            self._pending[k] = True
+                self._ev_gath[k].record(self._coll)
         else:
             self.sim.step_autoreset(ctrl, opt)  # rows go to every rank's gathered[k] from inside the kernel
             self._ev_step[k].record(main)
         self.t += 1
 
     def wait(self) -> torch.Tensor:
-        """Make the current stream wait until the gathered tensor of the last step is complete on this rank; returns it."""
+        """Make the CURRENT stream wait until the gathered tensor of the last step is complete on this rank; returns it."""
         k = (self.t - 1) & 1
-        main = torch.cuda.current_stream(self.dev)
+        cur = torch.cuda.current_stream(self.dev)
         if self.mode == 'nccl':
-            main.wait_event(self._ev_done[k])
+            cur.wait_event(self._ev_gath[k])
         else:
-            with torch.cuda.stream(self.side):
-                self.side.wait_event(self._ev_step[k])
-                self.sim._check(self.sim.L.qs_gather_wait(self.sim.h, C.c_uint64(self.sim.L.qs_gather_steps(self.sim.h)),
-                                                          C.c_void_p(self.side.cuda_stream)))
-                self._ev_done[k].record(self.side)
-            main.wait_event(self._ev_done[k])
+            cur.wait_event(self._ev_step[k])  # own launch enqueued ...
+            self.sim._check(self.sim.L.qs_gather_wait(self.sim.h, C.c_uint64(self.t), C.c_void_p(cur.cuda_stream)))  # ... and every peer's done
         return self.gathered[k]
+
+    def release(self):
+        """The consumer on the current stream is done with the tensor returned by the last `wait()`."""
+        k = (self.t - 1) & 1
+        self._ev_rel[k].record(torch.cuda.current_stream(self.dev))
+        self._rel_pending[k] = True
 
     def close(self):
         torch.cuda.synchronize(self.dev)

@@ -310,6 +310,20 @@ int qs_max_contacts(QsHandle* h);
 int qs_raycast_heightmap(QsHandle* h, int rows, int cols, double dx, double dy, float* dev_out,
                          void* cuda_stream);
 
+/* ---- peer-to-peer gather of the observation rows, fused into the step kernel (the one collective of the
+ * path; one process per GPU, up to 8 GPUs of one node).  Every rank allocates its [2][world * N, D] gathered tensors with
+ * qs_gather_create and publishes the returned 64-byte CUDA IPC handle; after qs_gather_connect (all handles, rank-major) every
+ * qs_step / qs_step_autoreset also stores each finished observation row into the gathered tensor of EVERY rank through
+ * peer-mapped memory (the `dev_obs` argument is then ignored: the own rows live in the gathered tensor) and raises a per-rank
+ * flag; qs_gather_wait enqueues a kernel that returns once all ranks have completed gather step `step_index` (1-based,
+ * qs_gather_steps() = steps issued so far).  Tensor of step t: qs_gather_buffer(h, (t - 1) & 1); it stays valid until step t + 2. */
+int qs_gather_create(QsHandle* h, int world_size, int rank, void* ipc_handle_out_64_bytes);
+int qs_gather_connect(QsHandle* h, const void* ipc_handles_world_x_64_bytes);
+void* qs_gather_buffer(QsHandle* h, int parity);
+uint64_t qs_gather_steps(QsHandle* h);
+int qs_gather_wait(QsHandle* h, uint64_t step_index, void* cuda_stream);
+int qs_gather_close(QsHandle* h);
+
 /* number of kernels this library has launched since create (bench.py "gpu_launches") */
 int64_t qs_launch_count(QsHandle* h);
 

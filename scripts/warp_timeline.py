@@ -29,6 +29,7 @@ sim.L.qs_debug_set_prof(sim.h, C.c_void_p(prof.data_ptr()))
 names = ['load', 'position', 'vel+M+constraints', 'solve', 'integrate', 'pack_obs', 'writeback', 'reset pass']
 agg = []
 for t in range(20):
+    prof.zero_()
     sim.step_autoreset(torch.randn(n, 12, device='cuda', generator=g) * 50, opt)
     torch.cuda.synchronize()
     P = prof.cpu().numpy().astype(np.int64) & 0xffffffff
@@ -48,6 +49,10 @@ for t in range(20):
             print(f'   reset pass (early-out envs)  mean {(tend - t5)[early].mean():9.0f}  max {(tend - t5)[early].max():9.0f}')
         for i in np.argsort(-tend)[:6]:
             print(f'   slow env {i}: end {tend[i]} solve {t4[i]-t3[i]} iters {it[i]} ls {ls[i]} ncon {nc[i]} sm {sm[i]} early-out {int(early[i])}')
+        lifts = P[:, 29]
+        if (lifts > 0).any():
+            sel = lifts > 0
+            print(f'   lift loops: {int(sel.sum())} envs, iterations mean {lifts[sel].mean():.1f} max {lifts.max()}, cycles per lift iteration ~ {((tend - t5)[sel & early] / np.maximum(1, lifts[sel & early])).mean() if (sel & early).any() else 0:.0f}')
         smax = np.array([tend[sm == s].max() for s in np.unique(sm)])
         print(f'   per-SM end: mean {smax.mean():.0f} min {smax.min()} max {smax.max()}')
 P = np.concatenate(agg)
