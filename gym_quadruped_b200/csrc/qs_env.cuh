@@ -780,8 +780,11 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
             mask &= mask - 1;
             const DBox<real>& bx = near_box(bit);
             const real rel[3] = {gx[0] - bx.pos[0], gx[1] - bx.pos[1], gx[2] - bx.pos[2]};
-            const real reach = bx.rad + rb;
-            if (dot3(rel, rel) <= reach * reach) keep |= 1u << bit;
+            // geom's bounding sphere against the box grown by its radius, in the box frame: the terrain boxes are flat slabs, for
+            // which the sphere-sphere test above the robot level lets through several times more candidates
+            real q[3];
+            mul_mtv(q, bx.mat, rel);
+            if (N::abs(q[0]) <= bx.half[0] + rb && N::abs(q[1]) <= bx.half[1] + rb && N::abs(q[2]) <= bx.half[2] + rb) keep |= 1u << bit;
           }
           boxmask = keep;
         }
@@ -923,8 +926,9 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
             const int bx = w.near_id[kb];
             const DBox<real>& B = near_box(kb);
             const real rel[3] = {c[0] - B.pos[0], c[1] - B.pos[1], c[2] - B.pos[2]};
-            const real reach = B.rad + rb;
-            if (dot3(rel, rel) > reach * reach) continue;
+            real qc[3];
+            mul_mtv(qc, B.mat, rel);
+            if (N::abs(qc[0]) > B.half[0] + rb || N::abs(qc[1]) > B.half[1] + rb || N::abs(qc[2]) > B.half[2] + rb) continue;
             real best = N::big;
             int bi = 0x7fffffff;
             for (int i = lane; i < nv; i += 32) {
