@@ -119,9 +119,9 @@ extern "C" int emu_step(const QsModel* model, int precision, double* qpos, doubl
   const int md = model_max_dim(*model);
 #define QS_EMU_RUN(real, MD, F) run_step<real, MD, F>(model, qpos, qvel, warm, ctrl, envp, obs, misc, max_iter, tol, mode)
   if (feat_sel == 1) {
-    // IMU columns / height-map columns are not part of the emulated observation row: the sensor stage runs whenever the model has
-    // an IMU (FEAT_NO_IMU is never asserted here) and mode 2 asks for the height map
-    const int have = model_features(*model, model->has_imu != 0, mode == 2 ? 25 : 0);
+    // as the library with use_imu = 0: IMU columns are not part of the emulated observation row, so a variant that drops the sensor
+    // stage is admissible (the `imu` entries of misc are then not filled); mode 2 asks for the height map
+    const int have = model_features(*model, false, mode == 2 ? 25 : 0);
     auto ok = [&](int feat) { return (feat & ~have) == 0; };
     if (precision == 0) {
       if (md <= 3 && ok(FEAT_CFG2)) return QS_EMU_RUN(float, 3, FEAT_CFG2);

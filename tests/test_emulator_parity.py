@@ -217,3 +217,43 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
         if steps >= 45:
             break
     assert mesh_terrain_contacts >= 5 and worst < 1e-8, (mesh_terrain_contacts, worst)
+
+
+@pytest.mark.parametrize('robot,scene,feat_bits', [('mini_cheetah', 'flat', 8101), ('aliengo', 'perlin', 1641), ('go2', 'random_boxes', 5746), ('hyqreal1', 'flat', 6022)])
+@pytest.mark.parametrize('precision', [0, 1])
+def test_specialised_variants_are_bit_identical_to_generic(robot, scene, feat_bits, precision):
+    """The four specialised step kernels (compile-time feature switches, csrc/qs_env.cuh FEAT_CFG2..5) against the generic
+    variant on the host emulator: every number of a contact-rich rollout must be identical, in fp32 and fp64."""
+    m = Model(robot, scene)
+    rng = np.random.RandomState(5)
+    key = np.array(m.c.key_qpos)
+    q = key.copy()
+    if scene != 'flat':
+        q[0:2] = (3.0, 2.0) if scene == 'perlin' else (2.0, -1.0)
+        q[2] = 0.95 if scene == 'perlin' else 0.45
+    q[7:] += rng.uniform(-0.2, 0.2, 12)
+    o = Oracle(m)
+    o.set_state(q, np.zeros(18), np.zeros(18)); assert o.lift() >= 0
+    q = o.get_state()[0]
+    for _ in range(400):  # lower the robot until its feet press into the surface: contacts from the first step on
+        o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+        if o.flags()['contact_state'].sum() >= 2:
+            break
+        q[2] -= 0.003
+    q[2] -= 0.006
+    q = q.astype(np.float32).astype(np.float64)
+    qa, va, wa = q.copy(), np.zeros(18), np.zeros(18)
+    qb, vb, wb = q.copy(), np.zeros(18), np.zeros(18)
+    saw_contact = False
+    for k in range(40):
+        ctrl = (rng.randn(12) * 6).astype(np.float32).astype(np.float64)
+        a = emu_step(m, qa, va, wa, ctrl, 0.8, 0.8, [0.5, 0, 0, 0.1], precision=precision, tol=1e-8 if precision else 1e-6, mode=1, specialised=True)
+        b = emu_step(m, qb, vb, wb, ctrl, 0.8, 0.8, [0.5, 0, 0, 0.1], precision=precision, tol=1e-8 if precision else 1e-6, mode=1, specialised=False)
+        assert a['feat'] == feat_bits and b['feat'] == 0
+        for name in ('qpos', 'qvel', 'qacc', 'obs', 'fcon', 'M'):
+            assert np.array_equal(a[name], b[name]), f'{name} differs at step {k}'
+        assert a['iters'] == b['iters'] and a['ncon'] == b['ncon'] and a['contact_mask'] == b['contact_mask'] and a['invalid_mask'] == b['invalid_mask']
+        saw_contact |= a['ncon'] > 0
+        qa, va, wa = a['qpos'], a['qvel'], a['qacc']
+        qb, vb, wb = b['qpos'], b['qvel'], b['qacc']
+    assert saw_contact
