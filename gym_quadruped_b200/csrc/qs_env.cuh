@@ -1332,7 +1332,8 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       return;
     }
     const real Dm = N::div(D0, N::max(N::minval, mu * mu * (1 + mu * mu))), NmT = Nn - mu * T;
-    const real T1 = N::div(UV, T), T2d = N::div(VV, T) - N::div(UV * UV, T * T * T), e1 = N1 - mu * T1;
+    const real invT = N::rcp(T);  // one reciprocal instead of three divisions (innermost loop of the line search)
+    const real T1 = UV * invT, T2d = VV * invT - UV * UV * (invT * invT * invT), e1 = N1 - mu * T1;
     cost += real(0.5) * Dm * NmT * NmT;
     d1 += Dm * NmT * e1;
     d2 += Dm * (e1 * e1 - NmT * mu * T2d);
@@ -1385,12 +1386,13 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
     F[0] = -Dm * NmT * mu;
     real de[MAXDIM];
     de[0] = mu;
-    for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? N::div(-mu * fk[k] * U[k], T) : real(0); if (k < dim) F[k] = N::div(-F[0], T) * U[k] * fk[k]; }
+    const real invT = N::rcp(T), invT3 = invT * invT * invT, c1 = Dm * NmT * (-mu);  // reciprocals once, not per Hessian entry
+    for (int k = 1; k < MAXDIM; k++) { de[k] = (k < dim) ? -mu * fk[k] * U[k] * invT : real(0); if (k < dim) F[k] = -F[0] * invT * U[k] * fk[k]; }
     for (int a = 0; a < MAXDIM; a++)
       for (int b = a; b < MAXDIM; b++) {
         if (a >= dim || b >= dim) continue;
         real h = Dm * de[a] * de[b];
-        if (a > 0) h += Dm * NmT * (-mu) * fk[a] * fk[b] * ((a == b ? N::div(real(1), T) : real(0)) - N::div(U[a] * U[b], T * T * T));
+        if (a > 0) h += c1 * fk[a] * fk[b] * ((a == b ? invT : real(0)) - U[a] * U[b] * invT3);
         Wt[widx(a, b)] = h;
       }
     return cost;
@@ -1500,12 +1502,25 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
           const real p0 = w.Jc[c][0][i1], p1 = w.Jc[c][1][i1], p2 = w.Jc[c][2][i1], q0 = w.Jc[c][0][j1], q1 = w.Jc[c][1][j1], q2 = w.Jc[c][2][j1];
           h1 = w00 * p0 * q0 + w01 * (p0 * q1 + p1 * q0) + w02 * (p0 * q2 + p2 * q0) + w11 * p1 * q1 + w22 * p2 * q2;
         }
+      } else if (dim == 3) {
+        // elliptic cone, three rows: the full symmetric 3x3 weight written out (same summation order as the loop below)
+        const real w00 = Wt[widx(0, 0)], w01 = Wt[widx(0, 1)], w02 = Wt[widx(0, 2)], w11 = Wt[widx(1, 1)], w12 = Wt[widx(1, 2)], w22 = Wt[widx(2, 2)];
+        if (on0) {
+          const real p0 = w.Jc[c][0][i0], p1 = w.Jc[c][1][i0], p2 = w.Jc[c][2][i0], q0 = w.Jc[c][0][j0], q1 = w.Jc[c][1][j0], q2 = w.Jc[c][2][j0];
+          h0 = p0 * (w00 * q0 + w01 * q1 + w02 * q2) + p1 * (w01 * q0 + w11 * q1 + w12 * q2) + p2 * (w02 * q0 + w12 * q1 + w22 * q2);
+        }
+        if (on1) {
+          const real p0 = w.Jc[c][0][i1], p1 = w.Jc[c][1][i1], p2 = w.Jc[c][2][i1], q0 = w.Jc[c][0][j1], q1 = w.Jc[c][1][j1], q2 = w.Jc[c][2][j1];
+          h1 = p0 * (w00 * q0 + w01 * q1 + w02 * q2) + p1 * (w01 * q0 + w11 * q1 + w12 * q2) + p2 * (w02 * q0 + w12 * q1 + w22 * q2);
+        }
       } else {
-        for (int a = 0; a < MAXDIM; a++) {
-          if (a >= dim) break;
+        // condim 1 / 6: a real loop (not unrolled): this body runs once per contact per Newton iteration in every lane, and the
+        // elliptic kernels are instruction-fetch bound (no_instruction 4.6 cycles per issue, profiles/r02_cfg4_*)
+#pragma unroll 1
+        for (int a = 0; a < dim; a++) {
           real t0 = 0, t1 = 0;
-          for (int b = 0; b < MAXDIM; b++) {
-            if (b >= dim) break;
+#pragma unroll 1
+          for (int b = 0; b < dim; b++) {
             const real wab = Wt[widx(a, b)];
             if (on0) t0 += wab * w.Jc[c][b][j0];
             if (on1) t1 += wab * w.Jc[c][b][j1];

@@ -19,6 +19,10 @@
 #include "../../include/qstep.h"
 #include "qs_env.cuh"
 
+// branch-layout hints: the reset pass, the lift loop, the schedules' resampling and the peer gather are cold in the step kernel
+#define QS_LIKELY(x) __builtin_expect(!!(x), 1)
+#define QS_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 namespace qs {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
@@ -288,9 +292,9 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   //   command and a new limit = randint(1000, 3000) (:1046-1072).  External disturbances of type 'reset': same cadence for the
   //   wrench (:1074-1139); the current wrench is then written to qfrc_applied and acts from the next step on (:305).
   auto schedule_update = [&]() {
-    if ((p.sch_command_mode & 8) && lane == 0) {
+    if (QS_UNLIKELY((p.sch_command_mode & 8) && lane == 0)) {
       int cnt = B.cmd_count[env] + 1;
-      if (cnt >= B.cmd_limit[env]) {
+      if (QS_UNLIKELY(cnt >= B.cmd_limit[env])) {
         uint32_t r[4];
         const unsigned ce = p.cmd_epoch[env];
         philox4x32(env_g, ce, 0u, 0xC3D0u, p.seed_lo ^ 0x51ED270Bu, p.seed_hi, r);
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       }
       B.cmd_count[env] = cnt;
     }
-    if (p.sch_ext_enabled) {
+    if (QS_UNLIKELY(p.sch_ext_enabled)) {
       int due = 0;
       if (lane == 0) {
         const int cnt = B.ext_count[env] + 1;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         B.ext_count[env] = due ? 0 : cnt;
       }
       due = __shfl_sync(0xffffffffu, due, 0);
-      if (due) {
+      if (QS_UNLIKELY(due)) {
         const unsigned ee = p.ext_epoch[env];
         if (lane < 7) {
           uint32_t r[4];
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     unsigned status = 0;
     int lift_phase = 2;
     real u_late[5] = {0, 0, 0, 0, 0};
-    if (MODE != MODE_FORWARD && resetting) {
+    if (MODE != MODE_FORWARD && (MODE == MODE_RESET ? resetting : QS_UNLIKELY(resetting))) {
       const QsResetOptions& ro = p.ro;
       const unsigned ep = p.episode[env];
       real* u = w.obs;  // scratch for the uniforms (this storage is recycled by the solver later on)
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         e.kinematics();
         if (lift_phase == 2) { e.com_inertia(); e.cdof(); }
         e.collide_floor();
-        if (lift_phase == 2) break;
+        if (QS_LIKELY(lift_phase == 2)) break;
         if (lift_phase == 0) {
           real d = Num<real>::big, mg = 0;
           bool calf = false, boxy = false;
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       // Same-step auto-reset returns the post-reset state / observation of an env that terminates, so once the collision stage has
       // found a contact that terminates the episode (quadruped_env.py:1228-1248) the rest of this step cannot reach any output:
       // raise the flags, keep the IMU bias walk in step, and go straight to the reset pass.
-      if (fl.invalid_mask != 0) {
+      if (QS_UNLIKELY(fl.invalid_mask != 0)) {
         if (lane == 0) {
           if (p.reward) p.reward[env] = 0.f;
           if (p.terminated) p.terminated[env] = 1;
@@ -637,7 +641,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
                   obs + NOBS_BASE + (p.use_imu ? QS_NOBS_IMU : 0));
     }
     if (!(FEAT & FEAT_NO_IMU) && p.use_imu) imu_step(obs, !resetting);
-    if (MODE == MODE_STEP && p.gather_world > 1 && obs && !(p.auto_reset && !resetting && terminated)) {
+    if (MODE == MODE_STEP && QS_UNLIKELY(p.gather_world > 1) && obs && !(p.auto_reset && !resetting && terminated)) {
       // final observation row of this env (a terminated env under auto-reset sends its post-reset row from the second pass):
       // straight to the gathered tensor of every peer, 16-B stores where the destination allows
       syncwarp();
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     }
     QS_MARK(5);
     // in-kernel auto-reset: the warp of an env that just terminated goes round once more as a reset pass
-    if (MODE != MODE_STEP || !p.auto_reset || resetting || !terminated) break;
+    if (QS_LIKELY(MODE != MODE_STEP || !p.auto_reset || resetting || !terminated)) break;
     resetting = true;
     given_state = false;
     e.ls_evals = 0;

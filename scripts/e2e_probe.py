@@ -13,6 +13,8 @@ opt = sim.make_reset_options(**bench.RESET_KW)
 sim.reset(options=opt)
 dev = torch.device('cuda:0')
 act = torch.randn(64, n, 12, device=dev) * 50
+for i in range(300):
+    sim.step_autoreset(act[i % 64], opt)  # steady-state rollout
 def timeit(fn, k=300):
     for i in range(20): fn(i)
     torch.cuda.synchronize(); t0 = time.perf_counter()
