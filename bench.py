@@ -247,6 +247,10 @@ def run_gpu(args):
         raise RuntimeError('bench.py needs a CUDA device; the CPU arm is `--impl reference`')
     torch.cuda.set_device(local_rank)
     dev = torch.device(f'cuda:{local_rank}')
+    numa = ''
+    if world > 1 and not os.environ.get('QS_BENCH_NO_NUMA'):
+        from gym_quadruped_b200.distributed import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)  # pinned host buffers of the e2e path become local to this GPU's socket
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -330,6 +334,18 @@ def run_gpu(args):
         b.record()
     torch.cuda.synchronize(dev)
     launch_ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+    # qs_step_k: the same K launches issued by ONE library call on the non-pipelined handle (overlap without any caller contract)
+    kreg = []
+    ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for r in range(7):
+        base = (r * K) % max(1, ring - K)
+        barrier()
+        ek0.record()
+        ser.step_k(actions[base:base + K], ser_opt)
+        ek1.record()
+        barrier()
+        kreg.append(ek0.elapsed_time(ek1))
+    kstep_ms = statistics.median(kreg[2:])
     # L2 flushed between iterations (256 MB write), each step timed on its own
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     cold = []
@@ -431,10 +447,10 @@ def run_gpu(args):
             gather['p2p_equals_nccl_bitwise'] = bool(same.item() == 1.0)
 
     # ---- reduce over ranks (max time)
-    t = torch.tensor([ser_ms, launch_ms, cold_ms, e2e_s, f64_ms or 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ser_ms, launch_ms, cold_ms, e2e_s, f64_ms or 0.0, kstep_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ser_ms, launch_ms, cold_ms, e2e_s, f64_ms_r = [float(x) for x in t.tolist()]
+    ser_ms, launch_ms, cold_ms, e2e_s, f64_ms_r, kstep_ms = [float(x) for x in t.tolist()]
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
@@ -468,6 +484,9 @@ def run_gpu(args):
             'serialized': {'value': n_gpus * envs * K / (ser_ms * 1e-3), 'ms_per_step': ser_ms / K, 'ms_per_launch_events': launch_ms,
                            'note': 'same launches without overlap (QsConfig.pipeline=0): what a caller gets whose next action depends on '
                                    'the previous observation'},
+            'k_step_call': {'value': n_gpus * envs * K / (kstep_ms * 1e-3), 'ms_per_step': kstep_ms / K,
+                            'note': 'qs_step_k: K steps from one C-ABI call on the pipeline=0 handle, one launch per step, overlapped by the library; '
+                                    'per-step outputs bit-identical to K single calls (tests/test_gpu_round2.py::test_step_k_equals_k_single_steps)'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': peak_src, 'kernel': f'env_kernel<float,16,{6 if ROBOT == "go2" else 3},MODE_STEP,{variant}>',
                          'kernel_ms_per_launch': ms / K, 'kernel_ms_per_launch_serialized': launch_ms,
@@ -477,7 +496,7 @@ def run_gpu(args):
             'e2e': {'value': n_gpus * envs * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': K,
                     'regions': len(e2e_regions), 'ms_per_step': e2e_ms,
                     'api': 'qs_step_host (C-ABI, pinned host buffers, in-kernel auto-reset), synchronous: returns when the results are in host memory',
-                    'exposed_transfer_ms_per_step': e2e_ms - ser_ms / K,
+                    'exposed_transfer_ms_per_step': e2e_ms - ser_ms / K, 'numa_binding_rank0': numa,
                     'note': 'zero-copy: the kernel reads ctrl and writes obs rows through the mapped host buffers; exposed_transfer = e2e - '
                             'serialized device time per step is what PCIe adds on top of the kernel'},
             'gpu_launches': int(lt.item()), 'clocks': clocks,

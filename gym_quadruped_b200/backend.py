@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
     L.qs_step_variant.restype = C.c_char_p
     L.qs_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.qs_step_host.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
+    L.qs_step_k.argtypes = [vp, C.c_int, fp, C.POINTER(QsResetOptions), fp, C.c_size_t, fp, u8p, u8p, vp]
     L.qs_step_autoreset.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
     L.qs_reset.argtypes = [vp, u8p, fp, fp, C.POINTER(QsResetOptions), fp, vp]
     L.qs_reset_done.argtypes = [vp, u8p, C.POINTER(QsResetOptions), fp, vp]
@@ -255,6 +256,26 @@ class BatchSim:
         self._check(self.L.qs_step_autoreset(self.h, ctrl.data_ptr(), C.byref(o), obs.data_ptr(), self.reward.data_ptr(),
                                              self.terminated.data_ptr(), self.truncated.data_ptr(), self._stream()))
         return obs, self.reward, self.terminated, self.truncated
+
+    def step_k(self, ctrl_seq: torch.Tensor, options: QsResetOptions | None = None, auto_reset: bool = True,
+               obs_ring: torch.Tensor | None = None, terminated_ring: torch.Tensor | None = None):
+        """K consecutive steps from one call (`qs_step_k`): ctrl_seq [K, N, 12]; bit-identical to K calls of `step_autoreset` /
+        `step`, one launch per step, launches overlapped on the device.  `obs_ring` [K, N, D] keeps every step's observation rows
+        (default: only the last step's rows, in `self.obs`); `terminated_ring` [K, N] uint8 keeps every step's flags."""
+        K = int(ctrl_seq.shape[0])
+        if ctrl_seq.device != self.device or ctrl_seq.dtype != torch.float32 or not ctrl_seq.is_contiguous() or ctrl_seq.shape[1:] != (self.N, 12):
+            ctrl_seq = torch.as_tensor(ctrl_seq, dtype=torch.float32, device=self.device).reshape(K, self.N, 12).contiguous()
+        o = (options or self.reset_options) if auto_reset else None
+        obs, stride = (self.obs, 0) if obs_ring is None else (obs_ring, self.N * self.obs_dim)
+        if obs_ring is not None:
+            assert obs_ring.shape == (K, self.N, self.obs_dim) and obs_ring.is_contiguous() and obs_ring.dtype == torch.float32
+        if terminated_ring is None:
+            terminated_ring = torch.empty(K, self.N, dtype=torch.uint8, device=self.device)
+        assert terminated_ring.shape == (K, self.N) and terminated_ring.dtype == torch.uint8 and terminated_ring.is_contiguous()
+        self._check(self.L.qs_step_k(self.h, K, ctrl_seq.data_ptr(), C.byref(o) if o is not None else None, obs.data_ptr(), stride,
+                                     None, terminated_ring.data_ptr(), None, self._stream()))
+        self.terminated.copy_(terminated_ring[-1])
+        return obs, terminated_ring
 
     def step_host(self, ctrl_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
                   terminated_host: torch.Tensor, truncated_host: torch.Tensor, auto_reset: QsResetOptions | None = None):

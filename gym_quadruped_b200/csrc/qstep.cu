@@ -381,8 +381,10 @@ static int launch(QsHandle* h, KernelFn fn, const KParams& p, cudaStream_t s, bo
   return 0;
 }
 
+// kmode 0: plain call (overlap with the previous launch only if QsConfig.pipeline allows it); 1 / 2: first / later launch of a
+// qs_step_k sequence -- the library itself issues these launches back to back, so the later ones may always overlap their predecessor
 static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
-                     const QsResetOptions* auto_reset, void* stream) {
+                     const QsResetOptions* auto_reset, void* stream, int kmode = 0) {
   if (!h || !h->bound) return fail(h, 1, "qs_step: handle not bound");
   if (!ctrl) return fail(h, 1, "qs_step: ctrl is null");
   KParams p = base_params(h);
@@ -398,8 +400,8 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
     p.q_in = h->d_queue + size_t(in) * n; p.q_out = h->d_queue + size_t(out) * n;
     p.q_tail = h->d_queue_tail + out;
     p.q_tail_base = unsigned((s / QS_QUEUE_DEPTH) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
-    p.q_contiguous = h->cfg.pipeline ? 1 : 0;
-    p.q_sync = h->cfg.pipeline ? 1 : 0;
+    p.q_contiguous = (h->cfg.pipeline || kmode) ? 1 : 0;
+    p.q_sync = (h->cfg.pipeline || kmode) ? 1 : 0;
   }
   if (h->gather.connected) {
     auto& g = h->gather;
@@ -413,10 +415,25 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
     }
     p.obs = p.gather_peers[g.rank] + size_t(g.rank) * h->cfg.num_envs * h->obs_dim;  // own rows live in the gathered tensor itself
   }
-  const bool chained = h->cfg.pipeline && h->last_was_step && h->last_stream == stream;
+  const bool chained = kmode == 2 || (kmode == 0 && h->cfg.pipeline && h->last_was_step && h->last_stream == stream);
   const int rc = launch(h, h->k_step, p, static_cast<cudaStream_t>(stream), chained);
   h->last_was_step = rc == 0; h->last_stream = stream;
   return rc;
+}
+
+int qs_step_k(QsHandle* h, int k, const float* ctrl, const QsResetOptions* auto_reset, float* obs, size_t obs_step_stride, float* reward,
+              uint8_t* terminated, uint8_t* truncated, void* stream) {
+  if (k <= 0) return fail(h, 1, "qs_step_k: k must be positive");
+  if (!h) return fail(h, 1, "null handle");
+  const size_t n = size_t(h->cfg.num_envs);
+  for (int i = 0; i < k; i++) {
+    const int rc = step_impl(h, ctrl + size_t(i) * n * NU, obs ? obs + size_t(i) * obs_step_stride : nullptr, reward ? reward + size_t(i) * n : nullptr,
+                             terminated ? terminated + size_t(i) * n : nullptr, truncated ? truncated + size_t(i) * n : nullptr, auto_reset,
+                             stream, i == 0 ? 1 : 2);
+    if (rc) return rc;
+  }
+  if (!h->cfg.pipeline) h->last_was_step = false;  // a later plain qs_step of a non-pipelined handle keeps full stream order
+  return 0;
 }
 
 int qs_step(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated, void* stream) {

@@ -145,3 +145,40 @@ class ObsGather:
         if self.mode == 'p2p':
             dist.barrier(group=self.group)
             self.sim.L.qs_gather_close(self.sim.h)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers allocated afterwards
+    are first-touched in memory local to that GPU's PCIe root: with one process per GPU on a multi-socket host the zero-copy
+    observation rows of `qs_step_host` otherwise cross the inter-socket link for half of the ranks.  Returns a description of what
+    was done ('' if the topology could not be read; never raises)."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), 'pci_bus_id') else None
+        if bus is None:
+            import subprocess
+            out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(device_index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bus = out.splitlines()[0].strip() if out else None
+        if not bus:
+            return ''
+        bus = bus.lower()
+        if len(bus.split(':')[0]) == 8:  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        node_path = f'/sys/bus/pci/devices/{bus}/numa_node'
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return ''
+        cpus = open(f'/sys/devices/system/node/node{node}/cpulist').read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            lo, _, hi = part.partition('-')
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if not allowed:
+            return ''
+        os.sched_setaffinity(0, allowed)
+        return f'gpu {device_index} ({bus}) -> NUMA node {node}, {len(allowed)} cpus'
+    except Exception:  # noqa: BLE001
+        return ''

@@ -268,6 +268,16 @@ int qs_step(QsHandle* h, const float* dev_ctrl, float* dev_obs, float* dev_rewar
 int qs_step_autoreset(QsHandle* h, const float* dev_ctrl, const QsResetOptions* opt, float* dev_obs, float* dev_reward,
                       uint8_t* dev_terminated, uint8_t* dev_truncated, void* cuda_stream);
 
+/* K consecutive steps in one call: step i uses dev_ctrl[i] ([K,N,12]) and writes its observation rows to
+ * dev_obs + i * obs_step_stride floats (stride 0: every step overwrites the same [N,D] tensor; stride N*D: an observation ring),
+ * its reward / flags to row i of [K,N] arrays (NULL allowed).  Bit-identical to K calls of qs_step / qs_step_autoreset
+ * (auto_reset NULL / non-NULL).  It is still one kernel launch per step, but because the library issues the launches back to
+ * back it lets each overlap its predecessor on the device (see QsConfig.pipeline) without any contract on the caller: the first
+ * launch of the sequence is ordered after everything enqueued before the call.  For open-loop action segments (replay, MPC
+ * roll-outs, the benchmark). */
+int qs_step_k(QsHandle* h, int k, const float* dev_ctrl, const QsResetOptions* auto_reset, float* dev_obs, size_t obs_step_stride,
+              float* dev_reward, uint8_t* dev_terminated, uint8_t* dev_truncated, void* cuda_stream);
+
 /* same call with HOST buffers: H2D(ctrl) -> step -> D2H(obs, reward, flags), stream-synchronised.
  * auto_reset: NULL = plain qs_step, else qs_step_autoreset with these options. */
 int qs_step_host(QsHandle* h, const float* host_ctrl, const QsResetOptions* auto_reset, float* host_obs, float* host_reward,

@@ -549,3 +549,34 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy, cuda_device):
                 worst = max(worst, np.abs(q1[i] - qo).max(), 0.1 * np.abs(v1[i] - vo).max())
     # single-step bound: several contacts on one lying link are a redundant, stiff problem (cf. test_terrain_scenes_match_oracle)
     assert mesh_contacts >= 50 and ties <= 6 and worst < 3e-4, (mesh_contacts, ties, worst)
+
+
+@pytest.mark.parametrize('robot,scene,n', [('mini_cheetah', 'flat', 4096), ('aliengo', 'perlin', 700)])
+def test_step_k_equals_k_single_steps(robot, scene, n, cuda_device):
+    """qs_step_k: K steps from one call, one launch per step, launches overlapped on the device by the library
+    itself (no contract on the caller, works on a handle with pipeline = 0) -- every per-step output (observation ring, terminated
+    ring) and the final state bit-identical to K calls of qs_step_autoreset."""
+    m = Model(robot, scene)
+    hm = (5, 5, 0.1, 0.1) if scene == 'perlin' else None
+    a = BatchSim(m, n, device=cuda_device, seed=4, heightmap=hm)
+    b = BatchSim(m, n, device=cuda_device, seed=4, heightmap=hm)
+    opt = a.make_reset_options(lin_vel_range=(0.5, 1.0), friction_range=(0.2, 1.5))
+    for s in (a, b):
+        s.reset(options=opt)
+    K = 48
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    ctrl = torch.randn(3 * K, n, 12, device=cuda_device, generator=g) * 50
+    for seg in range(3):
+        ring = torch.zeros(K, n, a.obs_dim, device=cuda_device)
+        tring = torch.zeros(K, n, dtype=torch.uint8, device=cuda_device)
+        a.step_k(ctrl[seg * K:(seg + 1) * K], opt, obs_ring=ring, terminated_ring=tring)
+        a.friction.mul_(1.0)  # a foreign kernel between two K-step calls: ordered after the whole sequence
+        for k in range(K):
+            obs, _, term, _ = b.step_autoreset(ctrl[seg * K + k], opt)
+            assert torch.equal(ring[k], obs), f'observation of step {seg * K + k} differs'
+            assert torch.equal(tring[k], term)
+    for name in ('qpos', 'qvel', 'qacc_warmstart', 'base_pos64', 'command', 'friction', 'step_count', 'sim_time', 'terminated'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    # without a ring only the last step's rows remain
+    a.step_k(ctrl[:5], opt); [b.step_autoreset(ctrl[k], opt) for k in range(5)]
+    assert torch.equal(a.obs, b.obs) and torch.equal(a.terminated, b.terminated)
