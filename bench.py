@@ -363,7 +363,9 @@ def run_gpu(args):
     # ---- end to end through the C-ABI with HOST buffers (pinned): H2D ctrl + kernel + D2H obs/reward/flags every step, synchronous
     host_ring = 8
     ctrl_h = [(torch.randn(envs, 12) * TORQUE_SCALE).pin_memory() for _ in range(host_ring)]
-    obs_h = torch.empty(envs, sim.obs_dim).pin_memory(); rew_h = torch.empty(envs).pin_memory()
+    # rows padded to a multiple of 32 floats (128 B): every zero-copy row write crosses PCIe as whole lines (qs_step_host_strided)
+    row = (sim.obs_dim + 31) // 32 * 32
+    obs_h = torch.empty(envs, row).pin_memory()[:, :sim.obs_dim]; rew_h = torch.empty(envs).pin_memory()
     term_h = torch.empty(envs, dtype=torch.uint8).pin_memory(); trunc_h = torch.empty(envs, dtype=torch.uint8).pin_memory()
     for i in range(5):
         ser.step_host(ctrl_h[i % host_ring], obs_h, rew_h, term_h, trunc_h, auto_reset=ser_opt)
@@ -495,7 +497,8 @@ def run_gpu(args):
             'cpu_baseline': cpu,
             'e2e': {'value': n_gpus * envs * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': K,
                     'regions': len(e2e_regions), 'ms_per_step': e2e_ms,
-                    'api': 'qs_step_host (C-ABI, pinned host buffers, in-kernel auto-reset), synchronous: returns when the results are in host memory',
+                    'api': 'qs_step_host_strided (C-ABI, pinned host buffers, observation rows on 128-byte boundaries, in-kernel auto-reset), '
+                           'synchronous: returns when the results are in host memory',
                     'exposed_transfer_ms_per_step': e2e_ms - ser_ms / K, 'numa_binding_rank0': numa,
                     'note': 'zero-copy: the kernel reads ctrl and writes obs rows through the mapped host buffers; exposed_transfer = e2e - '
                             'serialized device time per step is what PCIe adds on top of the kernel'},

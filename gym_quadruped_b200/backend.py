@@ -59,6 +59,7 @@ def load_library() -> C.CDLL:
     L.qs_step_variant.restype = C.c_char_p
     L.qs_step.argtypes = [vp, fp, fp, fp, u8p, u8p, vp]
     L.qs_step_host.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
+    L.qs_step_host_strided.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, C.c_size_t, fp, u8p, u8p, vp]
     L.qs_step_k.argtypes = [vp, C.c_int, fp, C.POINTER(QsResetOptions), fp, C.c_size_t, fp, u8p, u8p, vp]
     L.qs_step_autoreset.argtypes = [vp, fp, C.POINTER(QsResetOptions), fp, fp, u8p, u8p, vp]
     L.qs_reset.argtypes = [vp, u8p, fp, fp, C.POINTER(QsResetOptions), fp, vp]
@@ -279,10 +280,13 @@ class BatchSim:
 
     def step_host(self, ctrl_host: torch.Tensor, obs_host: torch.Tensor, reward_host: torch.Tensor,
                   terminated_host: torch.Tensor, truncated_host: torch.Tensor, auto_reset: QsResetOptions | None = None):
-        """Same step through HOST buffers (pinned CPU tensors): H2D ctrl, kernel, D2H results, stream-synchronised."""
-        self._check(self.L.qs_step_host(self.h, ctrl_host.data_ptr(), C.byref(auto_reset) if auto_reset is not None else None,
-                                        obs_host.data_ptr(), reward_host.data_ptr(),
-                                        terminated_host.data_ptr(), truncated_host.data_ptr(), self._stream()))
+        """Same step through HOST buffers (pinned CPU tensors): H2D ctrl, kernel, D2H results, stream-synchronised.
+        `obs_host` may be a [N, D] view of a wider pinned tensor (padded rows, e.g. `torch.empty(N, 256).pin_memory()[:, :D]`)."""
+        stride = int(obs_host.stride(0)) if obs_host.dim() == 2 else self.obs_dim
+        assert obs_host.dim() != 2 or obs_host.stride(1) == 1
+        self._check(self.L.qs_step_host_strided(self.h, ctrl_host.data_ptr(), C.byref(auto_reset) if auto_reset is not None else None,
+                                                obs_host.data_ptr(), stride, reward_host.data_ptr(),
+                                                terminated_host.data_ptr(), truncated_host.data_ptr(), self._stream()))
 
     def reset(self, mask: torch.Tensor | None = None, qpos: torch.Tensor | None = None, qvel: torch.Tensor | None = None,
               options: QsResetOptions | None = None):

@@ -43,6 +43,7 @@ struct KParams {
   float hm_dx, hm_dy;
   float* hm_out;       // stand-alone ray cast destination [N, rows, cols, 3]
   int num_envs, obs_dim, use_imu, max_iter, env_id_offset, auto_reset;
+  int obs_stride;      // floats between consecutive observation rows (obs_dim unless the caller pads its rows, qs_step_host_strided)
   float tol;
   unsigned seed_lo, seed_hi;
   float imu_an, imu_gn, imu_abr, imu_gbr;
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       B.qacc[size_t(env) * NV + lane] = float(w.qacc[lane]);
       B.qacc_warmstart[size_t(env) * NV + lane] = float(w.qacc[lane]);
     }
-    float* obs = p.obs ? p.obs + size_t(env) * p.obs_dim : nullptr;
+    float* obs = p.obs ? p.obs + size_t(env) * p.obs_stride : nullptr;
     if (obs) {
       // The staged row leaves as a scalar head up to 16-B alignment, a float4 body and a scalar tail: rows bound for mapped host
       // memory cross PCIe in 16-B stores (measured 45 GB/s against 38 GB/s for 4-B stores, scripts/micro/zc_write.cu).

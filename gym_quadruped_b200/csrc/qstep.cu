@@ -345,7 +345,7 @@ static KParams base_params(QsHandle* h) {
   KParams p{};
   p.dm = h->d_dm; p.vert = h->d_vert; p.hf = h->d_hf; p.boxes = h->d_boxes;
   p.hm_rows = h->cfg.hm_rows; p.hm_cols = h->cfg.hm_cols; p.hm_dx = float(h->cfg.hm_dx); p.hm_dy = float(h->cfg.hm_dy);
-  p.num_envs = h->cfg.num_envs; p.obs_dim = h->obs_dim; p.use_imu = h->cfg.use_imu;
+  p.num_envs = h->cfg.num_envs; p.obs_dim = h->obs_dim; p.obs_stride = h->obs_dim; p.use_imu = h->cfg.use_imu;
   p.max_iter = h->cfg.solver_max_iter > 0 ? h->cfg.solver_max_iter : (h->cfg.precision == 0 ? 50 : 100);
   p.tol = h->cfg.precision == 0 ? 1e-6f : 1e-8f;
   p.env_id_offset = h->cfg.env_id_offset;
@@ -384,11 +384,12 @@ static int launch(QsHandle* h, KernelFn fn, const KParams& p, cudaStream_t s, bo
 // kmode 0: plain call (overlap with the previous launch only if QsConfig.pipeline allows it); 1 / 2: first / later launch of a
 // qs_step_k sequence -- the library itself issues these launches back to back, so the later ones may always overlap their predecessor
 static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
-                     const QsResetOptions* auto_reset, void* stream, int kmode = 0) {
+                     const QsResetOptions* auto_reset, void* stream, int kmode = 0, size_t obs_row_stride = 0) {
   if (!h || !h->bound) return fail(h, 1, "qs_step: handle not bound");
   if (!ctrl) return fail(h, 1, "qs_step: ctrl is null");
   KParams p = base_params(h);
   p.ctrl = ctrl; p.obs = obs; p.reward = reward; p.terminated = terminated; p.truncated = truncated;
+  if (obs_row_stride) p.obs_stride = int(obs_row_stride);
   if (auto_reset) { p.auto_reset = 1; p.ro = *auto_reset; }
 #ifdef QS_PROF
   p.prof = h->prof;
@@ -448,7 +449,13 @@ int qs_step_autoreset(QsHandle* h, const float* ctrl, const QsResetOptions* opt,
 
 int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_reset, float* obs, float* reward, uint8_t* terminated,
                  uint8_t* truncated, void* stream) {
+  return qs_step_host_strided(h, ctrl, auto_reset, obs, 0, reward, terminated, truncated, stream);
+}
+
+int qs_step_host_strided(QsHandle* h, const float* ctrl, const QsResetOptions* auto_reset, float* obs, size_t obs_row_stride, float* reward,
+                         uint8_t* terminated, uint8_t* truncated, void* stream) {
   if (!h || !h->bound) return fail(h, 1, "qs_step_host: handle not bound");
+  if (obs_row_stride && obs_row_stride < size_t(h->obs_dim)) return fail(h, 1, "qs_step_host_strided: row stride smaller than the observation width");
   if (!ctrl) return fail(h, 1, "qs_step_host: ctrl is null");
   const size_t n = size_t(h->cfg.num_envs);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -468,9 +475,10 @@ int qs_step_host(QsHandle* h, const float* ctrl, const QsResetOptions* auto_rese
   // of following the kernel.  Pageable buffers fall back to staging + cudaMemcpyAsync.
   float* k_obs = mapped_alias(obs); float* k_rew = mapped_alias(reward);
   uint8_t* k_term = mapped_alias(terminated); uint8_t* k_trunc = mapped_alias(truncated);
+  if (obs && !k_obs && obs_row_stride && obs_row_stride != size_t(h->obs_dim)) return fail(h, 1, "qs_step_host_strided: padded rows need a pinned (mapped) observation buffer");
   int rc = step_impl(h, k_ctrl ? k_ctrl : h->d_ctrl, obs ? (k_obs ? k_obs : h->d_obs) : nullptr, reward ? (k_rew ? k_rew : h->d_reward) : nullptr,
                      terminated ? (k_term ? k_term : h->d_term) : h->d_term, truncated ? (k_trunc ? k_trunc : h->d_trunc) : nullptr,
-                     auto_reset, stream);
+                     auto_reset, stream, 0, k_obs ? obs_row_stride : 0);
   if (rc) return rc;
   if (obs && !k_obs) QS_CUDA(h, cudaMemcpyAsync(obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (reward && !k_rew) QS_CUDA(h, cudaMemcpyAsync(reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));

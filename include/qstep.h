@@ -283,6 +283,12 @@ int qs_step_k(QsHandle* h, int k, const float* dev_ctrl, const QsResetOptions* a
 int qs_step_host(QsHandle* h, const float* host_ctrl, const QsResetOptions* auto_reset, float* host_obs, float* host_reward,
                  uint8_t* host_terminated, uint8_t* host_truncated, void* cuda_stream);
 
+/* qs_step_host with padded observation rows: row i starts at host_obs + i * obs_row_stride floats (>= D; 0 = D).  With a pinned
+ * buffer whose rows start on 128-byte boundaries (e.g. stride 256 floats for D = 227) the zero-copy row writes cross PCIe as
+ * whole lines instead of two partial lines per row. */
+int qs_step_host_strided(QsHandle* h, const float* host_ctrl, const QsResetOptions* auto_reset, float* host_obs, size_t obs_row_stride,
+                         float* host_reward, uint8_t* host_terminated, uint8_t* host_truncated, void* cuda_stream);
+
 /* reset, quadruped_env.py:309-406. env_mask [N] (NULL = all). If dev_qpos/dev_qvel are non-NULL
  * ([N,19]/[N,18]) they are taken verbatim (the `else` branch, :389-391), otherwise keyframe + noise +
  * lift-until-no-foot-contact. Always followed by one full step with zero ctrl (:397) and an obs pack. */

@@ -28,6 +28,12 @@ for pinned in (True, False):
     obs_h, rew_h = mk(torch.empty(n, sim.obs_dim)), mk(torch.empty(n))
     term_h, trunc_h = mk(torch.empty(n, dtype=torch.uint8)), mk(torch.empty(n, dtype=torch.uint8))
     print('step_host pinned=%s           us' % pinned, timeit(lambda i: sim.step_host(ctrl_h[i % 8], obs_h, rew_h, term_h, trunc_h, auto_reset=opt)))
+ctrl_h = [(torch.randn(n, 12) * 50).pin_memory() for _ in range(8)]
+rew_h = torch.empty(n).pin_memory(); term_h = torch.empty(n, dtype=torch.uint8).pin_memory(); trunc_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+for width in (sim.obs_dim, 228, 256):
+    wide = torch.empty(n, width).pin_memory()
+    view = wide[:, :sim.obs_dim]
+    print('step_host pinned, row stride %d floats us' % width, timeit(lambda i: sim.step_host(ctrl_h[i % 8], view, rew_h, term_h, trunc_h, auto_reset=opt)))
 # kernel duration when the obs rows are written straight into pinned host memory (zero-copy) vs device memory
 import ctypes as C
 obs_h = torch.empty(n, sim.obs_dim).pin_memory()

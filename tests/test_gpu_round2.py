@@ -580,3 +580,24 @@ def test_step_k_equals_k_single_steps(robot, scene, n, cuda_device):
     # without a ring only the last step's rows remain
     a.step_k(ctrl[:5], opt); [b.step_autoreset(ctrl[k], opt) for k in range(5)]
     assert torch.equal(a.obs, b.obs) and torch.equal(a.terminated, b.terminated)
+
+
+def test_host_entry_point_with_padded_rows(cuda_device):
+    """qs_step_host_strided: observation rows of a pinned host buffer on 128-byte boundaries ([N, 256] storage, [N, 227] view)
+    receive exactly what the contiguous host buffer and the device path receive."""
+    m = Model('mini_cheetah', 'flat')
+    n = 64
+    qpos, qvel = seeded_states(m, n, seed=6)
+    sims = [BatchSim(m, n, device=cuda_device) for _ in range(3)]
+    for s in sims:
+        s.set_state(torch.tensor(qpos), torch.tensor(qvel))
+    ctrl = torch.randn(n, 12) * 10
+    ctrl_h = ctrl.clone().pin_memory()
+    rew_h = torch.empty(n).pin_memory(); term_h = torch.empty(n, dtype=torch.uint8).pin_memory(); trunc_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    wide = torch.full((n, 256), -7.0).pin_memory()
+    sims[0].step_host(ctrl_h, wide[:, :227], rew_h, term_h, trunc_h)
+    flat = torch.empty(n, 227).pin_memory()
+    sims[1].step_host(ctrl_h, flat, rew_h, term_h, trunc_h)
+    obs, _, _, _ = sims[2].step(ctrl.to(cuda_device))
+    assert torch.equal(wide[:, :227], flat) and torch.equal(flat, obs.cpu())
+    assert (wide[:, 227:] == -7.0).all()  # the padding is never written
