@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       // final observation row of this env (a terminated env under auto-reset sends its post-reset row from the second pass):
       // straight to the gathered tensor of every peer, 16-B stores where the destination allows
       syncwarp();
-      const size_t row = (size_t(p.gather_rank) * p.num_envs + env) * p.obs_dim;
+      const size_t row = (size_t(p.gather_rank) * p.num_envs + env) * p.obs_stride;
       auto val = [&](int i) { return i < NOBS_BASE ? float(w.obs[i]) : __ldcg(obs + i); };
       for (int q = 0; q < p.gather_world; q++) {
         if (q == p.gather_rank) continue;

@@ -100,6 +100,7 @@ struct QsHandle_ {
     unsigned char* block = nullptr;     // this rank's allocation: 2 gathered tensors + 2 x 8 flags
     unsigned char* peer[8] = {};        // the same block on every rank (peer[rank] == block)
     size_t tensor_bytes = 0;
+    int row_stride = 0;                 // floats per row of the gathered tensors: D rounded up to 32 (rows start on 128-byte boundaries)
     uint64_t steps = 0;                 // gather steps launched so far
     bool connected = false;
   } gather;
@@ -285,7 +286,8 @@ int qs_gather_create(QsHandle* h, int world, int rank, void* ipc_handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   auto& g = h->gather;
   g.world = world; g.rank = rank;
-  g.tensor_bytes = (size_t(world) * h->cfg.num_envs * h->obs_dim * sizeof(float) + 255) & ~size_t(255);
+  g.row_stride = (h->obs_dim + 31) / 32 * 32;
+  g.tensor_bytes = (size_t(world) * h->cfg.num_envs * g.row_stride * sizeof(float) + 255) & ~size_t(255);
   const size_t total = 2 * g.tensor_bytes + 256;
   QS_CUDA(h, cudaMalloc(&g.block, total));
   QS_CUDA(h, cudaMemset(g.block, 0, total));
@@ -316,6 +318,7 @@ void* qs_gather_buffer(QsHandle* h, int parity) {
 }
 
 uint64_t qs_gather_steps(QsHandle* h) { return h ? h->gather.steps : 0; }
+int qs_gather_row_stride(QsHandle* h) { return h ? h->gather.row_stride : 0; }
 
 int qs_gather_wait(QsHandle* h, uint64_t step_index, void* stream) {
   if (!h || !h->gather.connected) return fail(h, 1, "qs_gather_wait: gather not connected");
@@ -414,7 +417,8 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
       p.gather_peers[q] = reinterpret_cast<float*>(g.peer[q] + size_t(k) * g.tensor_bytes);
       p.gather_flags[q] = reinterpret_cast<unsigned*>(g.peer[q] + 2 * g.tensor_bytes) + 8 * k;
     }
-    p.obs = p.gather_peers[g.rank] + size_t(g.rank) * h->cfg.num_envs * h->obs_dim;  // own rows live in the gathered tensor itself
+    p.obs = p.gather_peers[g.rank] + size_t(g.rank) * h->cfg.num_envs * g.row_stride;  // own rows live in the gathered tensor itself
+    p.obs_stride = g.row_stride;
   }
   const bool chained = kmode == 2 || (kmode == 0 && h->cfg.pipeline && h->last_was_step && h->last_stream == stream);
   const int rc = launch(h, h->k_step, p, static_cast<cudaStream_t>(stream), chained);

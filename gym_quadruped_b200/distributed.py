@@ -94,7 +94,9 @@ class ObsGather:
         buf = (C.c_ubyte * (64 * self.world))(*allh.cpu().tolist())
         sim._check(L.qs_gather_connect(sim.h, buf))
         dist.barrier(group=self.group)
-        self.gathered = [torch.as_tensor(_DevArray(L.qs_gather_buffer(sim.h, k), (self.world * self.N, self.D)), device=self.dev)
+        L.qs_gather_row_stride.argtypes = [C.c_void_p]
+        stride = int(L.qs_gather_row_stride(sim.h))  # rows padded to 128 bytes: whole-line stores over NVLink
+        self.gathered = [torch.as_tensor(_DevArray(L.qs_gather_buffer(sim.h, k), (self.world * self.N, stride)), device=self.dev)[:, :self.D]
                          for k in range(2)]
 
     def describe(self) -> str:
@@ -155,7 +157,10 @@ def bind_to_gpu_numa_node(device_index: int) -> str:
     import os
     try:
         import torch
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), 'pci_bus_id') else None
+        prop = torch.cuda.get_device_properties(device_index)
+        bus = None
+        if all(hasattr(prop, k) for k in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bus = f'{int(prop.pci_domain_id):04x}:{int(prop.pci_bus_id):02x}:{int(prop.pci_device_id):02x}.0'
         if bus is None:
             import subprocess
             out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(device_index)],

@@ -327,7 +327,7 @@ int qs_raycast_heightmap(QsHandle* h, int rows, int cols, double dx, double dy, 
                          void* cuda_stream);
 
 /* ---- peer-to-peer gather of the observation rows, fused into the step kernel (the one collective of the
- * path; one process per GPU, up to 8 GPUs of one node).  Every rank allocates its [2][world * N, D] gathered tensors with
+ * path; one process per GPU, up to 8 GPUs of one node).  Every rank allocates its [2][world * N, D (row stride qs_gather_row_stride)] gathered tensors with
  * qs_gather_create and publishes the returned 64-byte CUDA IPC handle; after qs_gather_connect (all handles, rank-major) every
  * qs_step / qs_step_autoreset also stores each finished observation row into the gathered tensor of EVERY rank through
  * peer-mapped memory (the `dev_obs` argument is then ignored: the own rows live in the gathered tensor) and raises a per-rank
@@ -337,6 +337,7 @@ int qs_gather_create(QsHandle* h, int world_size, int rank, void* ipc_handle_out
 int qs_gather_connect(QsHandle* h, const void* ipc_handles_world_x_64_bytes);
 void* qs_gather_buffer(QsHandle* h, int parity);
 uint64_t qs_gather_steps(QsHandle* h);
+int qs_gather_row_stride(QsHandle* h); /* floats between rows of the gathered tensors (D rounded up to 32: 128-byte aligned rows) */
 int qs_gather_wait(QsHandle* h, uint64_t step_index, void* cuda_stream);
 int qs_gather_close(QsHandle* h);
 
