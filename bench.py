@@ -338,10 +338,14 @@ def run_gpu(args):
     kreg = []
     ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for r in range(7):
-        base = (r * K) % max(1, ring - K)
         barrier()
         ek0.record()
-        ser.step_k(actions[base:base + K], ser_opt)
+        done = 0
+        while done < K:  # exactly K steps; the action ring may be shorter than K
+            base = (r * K + done) % ring
+            cnt = min(K - done, ring - base)
+            ser.step_k(actions[base:base + cnt], ser_opt)
+            done += cnt
         ek1.record()
         barrier()
         kreg.append(ek0.elapsed_time(ek1))
@@ -518,8 +522,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=1000)   # >= 200 warm-up, >= 1000 timed steps, median of 5
+    ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs', type=int, default=None, help='envs per GPU (default: the workload\'s)')
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS), help='cfg2 = BASELINE configs[1] (the bench line)')
