@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from gym_quadruped_b200.backend import CMD_FORWARD, CMD_RANDOM, CMD_RESET, CMD_ROTATE, FIELD_CONTACTS, BatchSim
+from gym_quadruped_b200.backend import CMD_FORWARD, CMD_RANDOM, CMD_RESET, CMD_ROTATE, BatchSim
 from gym_quadruped_b200.model import Model
 from oracle.oracle import F_CONTACTS, Oracle
 from tests.helpers import oracle_rollout, seeded_states

@@ -18,7 +18,7 @@ import scipy.linalg
 import scipy.optimize
 
 from gym_quadruped_b200.model import Model
-from oracle.oracle import F_EFC_FULL, F_M, F_QACC_SMOOTH, F_SMOOTH, Oracle
+from oracle.oracle import F_EFC_FULL, F_M, F_QACC_SMOOTH, Oracle
 
 T_FRICTION, T_LIMIT, T_FRICTIONLESS, T_PYRAMIDAL, T_ELLIPTIC = range(5)
 
@@ -127,21 +127,6 @@ def _dual_bvls(P):
     rhs = -scipy.linalg.solve_triangular(C.T, b, lower=True)
     res = scipy.optimize.lsq_linear(C, rhs, bounds=(lo, hi), method='bvls', tol=1e-15, max_iter=2000)
     return P['a0'] + Minv @ P['J'].T @ res.x, res.x
-
-
-def _project_cone(f, efc):
-    """Euclidean projection onto the product of: boxes (friction loss), half lines, and elliptic cones
-    K = {f0 >= 0, sum_k (f_k / mu_k)^2 <= f0^2} handled in the scaled variables g_k = f_k / mu_k (second-order cone)."""
-    out = f.copy()
-    for r, n in _units(efc):
-        t = int(efc[r, 0])
-        if t == T_FRICTION:
-            out[r] = np.clip(f[r], -efc[r, 7], efc[r, 7])
-        elif t != T_ELLIPTIC:
-            out[r] = max(f[r], 0.0)
-        else:
-            raise AssertionError('projection in the scaled variables is done by the caller')
-    return out
 
 
 def _dual_apg_elliptic(P, iters=400000):
