@@ -421,9 +421,7 @@ def run_gpu(args):
             def gstep(i):
                 g.step_autoreset(actions[i % ring], gopt)
                 with torch.cuda.stream(g.side):  # the consumer of the gathered rows lives on its own stream
-                    rows = g.wait()
-                    if not os.environ.get('QS_BENCH_NO_RELEASE'):
-                        g.release()
+                    rows = g.wait()  # (an empty consumer: the double buffer is free again long before step t + 2)
                 return rows
             for i in range(10):
                 rows = gstep(i)

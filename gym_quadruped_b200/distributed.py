@@ -49,8 +49,11 @@ class ObsGather:
         with torch.cuda.stream(g.side):          # the consumer lives on its own stream, so the next step is not held back
             rows = g.wait()                      # stream-ordered: work enqueued after it sees the complete tensor of the last step
             ... consume rows ...
-            g.release()                          # step t + 2 may overwrite this buffer
-    """
+
+    Double-buffer contract: the tensor of step t is overwritten by step t + 2, on every rank.  A closed-loop caller (the actions of
+    step t + 1 are computed from `rows`) satisfies it by construction.  A consumer that may lag more than one step behind calls
+    `g.release()` after consuming: step t + 2 then waits for it -- at the price of an event wait between two step launches,
+    which ends their overlap on the device (QsConfig.pipeline)."""
 
     def __init__(self, sim, mode: str = 'p2p', group=None):
         if not dist.is_initialized():
@@ -111,7 +114,7 @@ class ObsGather:
         k = self.t & 1
         main = torch.cuda.current_stream(self.dev)
         if self._rel_pending[k]:
-            main.wait_event(self._ev_rel[k])  # the consumer of step t - 2 has released this buffer
+            main.wait_event(self._ev_rel[k])  # explicit back-pressure: the consumer of step t - 2 has released this buffer
             self._rel_pending[k] = False
         if self.mode == 'nccl':
             self.sim.step_autoreset(ctrl, opt, obs_out=self.local[k])
