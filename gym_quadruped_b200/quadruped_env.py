@@ -314,7 +314,9 @@ class QuadrupedEnv(Env):
         return self.sim.qvel
 
     def set_state(self, qpos, qvel, env_ids=None):
-        """`env.mjData.qpos[...] = ...` equivalent (examples/aliengo_with_heightmap.py:32-34)."""
+        """`env.mjData.qpos[...] = ...` equivalent (examples/aliengo_with_heightmap.py:32-34).  The packed observation row (and the
+        accessors that slice it: base velocities, feet positions, `frame='base'` conversions) still describes the state before the
+        write until the next `step`; the `qs_forward`-based accessors (Jacobians, mass matrix, com, hip positions) see it at once."""
         self.sim.set_state(torch.as_tensor(qpos), torch.as_tensor(qvel), env_ids)
 
     # ------------------------------------------------------------------ accessors (quadruped_env.py:488-1044)
