@@ -680,16 +680,24 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       for (int i = 0; i < 3; i++) { c.nrm[i] = nn[i]; c.pos[i] = p[i] - nn[i] * (r + real(0.5) * dist); }
       cand_insert(list, n, c);
     } else if (ttype() == 2) {
+      unsigned mask = boxmask;
+      while (mask) {
+        const int k = ctz(mask);
+        mask &= mask - 1;
+        point_vs_box(p, r, margin, robot_first, k, list, n);
+      }
+    }
+  }
+  // point feature (centre p, radius r) against the k-th near box
+  QS_DEV void point_vs_box(const real* p, real r, real margin, bool robot_first, int k, Cand* list, int& n) const {
+    {
       {
-        unsigned mask = boxmask;
-        while (mask) {
-          const int k = ctz(mask);
-          mask &= mask - 1;
+        {
           const DBox<real>& bx = near_box(k);
           const int b = w.near_id[k];
           const real rel[3] = {p[0] - bx.pos[0], p[1] - bx.pos[1], p[2] - bx.pos[2]};
           const real reach = bx.rad + r + real(0.01);
-          if (dot3(rel, rel) > reach * reach) continue;
+          if (dot3(rel, rel) > reach * reach) return;
           real q[3], cl, dl[3], nl[3] = {0, 0, 0}, dist;
           mul_mtv(q, bx.mat, rel);
           bool inside = true;
@@ -705,7 +713,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
             dist = -depth - r;
             nl[best] = q[best] >= 0 ? real(1) : real(-1);
           }
-          if (dist > margin) continue;
+          if (dist > margin) return;
           real nw[3];
           mul_mv(nw, bx.mat, nl);
           Cand c;
@@ -714,6 +722,46 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
           cand_insert(list, n, c);
         }
       }
+    }
+  }
+
+  // Capsule against static boxes beyond its two end spheres: where an interior point of the axis is strictly nearer to a box than
+  // both ends (a leg lying across a stair edge) that point is a third sphere feature; not generated when the ends are as near
+  // (capsule flat on a face: the two end contacts carry it).  The nearest point is the root of the monotone derivative of the
+  // squared segment-box distance, found by bisection.  [MJ-approx of mjc_CapsuleBox]
+  QS_DEV void capsule_mid_vs_boxes(const real* c, const real* a, real L, real r, real margin, unsigned boxmask, Cand* list, int& n) const {
+    unsigned mask = boxmask;
+    while (mask) {
+      const int k = ctz(mask);
+      mask &= mask - 1;
+      const DBox<real>& bx = near_box(k);
+      const real rel[3] = {c[0] - bx.pos[0], c[1] - bx.pos[1], c[2] - bx.pos[2]};
+      real q0[3], dv[3];
+      mul_mtv(q0, bx.mat, rel);
+      mul_mtv(dv, bx.mat, a);
+      auto g = [&](real t) {
+        real s = 0;
+        for (int i = 0; i < 3; i++) {
+          const real q = q0[i] + t * dv[i];
+          s += q > bx.half[i] ? dv[i] * (q - bx.half[i]) : (q < -bx.half[i] ? dv[i] * (q + bx.half[i]) : real(0));
+        }
+        return s;
+      };
+      real lo = -L, hi = L;
+      if (g(lo) >= 0 || g(hi) <= 0) continue;  // the nearest point is an end: the end spheres cover it
+#pragma unroll 1
+      for (int it = 0; it < (sizeof(real) == 4 ? 30 : 60); it++) {
+        const real mid = real(0.5) * (lo + hi);
+        if (g(mid) < 0) lo = mid; else hi = mid;
+      }
+      const real t = real(0.5) * (lo + hi);
+      if (!(t > -L * (1 - real(1e-6)) && t < L * (1 - real(1e-6)))) continue;
+      const real pm[3] = {c[0] + t * a[0], c[1] + t * a[1], c[2] + t * a[2]};
+      const real p1[3] = {c[0] + L * a[0], c[1] + L * a[1], c[2] + L * a[2]}, p2[3] = {c[0] - L * a[0], c[1] - L * a[1], c[2] - L * a[2]};
+      real nw[3];
+      const real dm = point_box_distance(bx, pm, nw), d1 = point_box_distance(bx, p1, nw), d2 = point_box_distance(bx, p2, nw);
+      if (!(dm < N::min(d1, d2) - real(1e-6))) continue;
+      point_vs_box(pm, r, margin, true, k, list, n);
     }
   }
 
@@ -800,6 +848,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
           const real p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
           point_vs_terrain(p, sz[0], margin, true, boxmask, list, n);
         }
+        if (ttype() == 2) capsule_mid_vs_boxes(gx, axis, sz[1], sz[0], margin, boxmask, list, n);
       } else if ((type_on(GEOM_BOX) && type == GEOM_BOX) || (type_on(GEOM_CYLINDER) && type == GEOM_CYLINDER)) {
         // box corners / eight cylinder rim points (four per cap) as point features
         real gm[9];

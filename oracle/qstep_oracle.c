@@ -525,6 +525,9 @@ static int hfieldHeight(const OData* d, double x, double y, double* z, double* n
   return 1;
 }
 
+static void pointBoxContact(OData* d, int g, int b, const double* p, double r, int geom_type, const double* yaxis);
+static double pointBoxDistance(const QsModel* m, int b, const double* p, double* nw);
+
 /* point feature (centre p, radius r) of robot geom g against every terrain surface except the floor plane */
 static void collidePointTerrain(OData* d, int g, const double* p, double r, int geom_type, const double* yaxis) {
   const QsModel* m = &d->m;
@@ -538,10 +541,19 @@ static void collidePointTerrain(OData* d, int g, const double* p, double r, int 
     double pos[3] = {p[0] - n[0] * (r + 0.5 * dist), p[1] - n[1] * (r + 0.5 * dist), p[2] - n[2] * (r + 0.5 * dist)};
     addContact(d, g, 1, 1, dist, pos, n, yaxis, &m->hf_par, m->hf_par.friction);
   } else if (m->terrain_type == QS_TERRAIN_BOXES) {
-    for (int b = 0; b < m->nbox; b++) {
+    for (int b = 0; b < m->nbox; b++) pointBoxContact(d, g, b, p, r, geom_type, yaxis);
+  }
+}
+
+/* point feature (centre p, radius r) of robot geom g against static box b */
+static void pointBoxContact(OData* d, int g, int b, const double* p, double r, int geom_type, const double* yaxis) {
+  const QsModel* m = &d->m;
+  const QsGeomParams* gp = &m->geom_par[g];
+  {
+    {
       double R[9], q[3], rel[3] = {p[0] - m->box_pos[b][0], p[1] - m->box_pos[b][1], p[2] - m->box_pos[b][2]};
       const double* h = m->box_half[b];
-      if (dot3(rel, rel) > (norm3(h) + r + 0.01) * (norm3(h) + r + 0.01)) continue;
+      if (dot3(rel, rel) > (norm3(h) + r + 0.01) * (norm3(h) + r + 0.01)) return;
       quat2Mat(R, m->box_quat[b]);
       mulMatTVec3(q, R, rel);
       double margin = gp->margin > m->box_par.margin ? gp->margin : m->box_par.margin;
@@ -558,7 +570,7 @@ static void collidePointTerrain(OData* d, int g, const double* p, double r, int 
         dist = -depth - r;
         nl[0] = nl[1] = nl[2] = 0; nl[best] = q[best] >= 0 ? 1 : -1;
       }
-      if (dist > margin) continue;
+      if (dist > margin) return;
       double nw[3];
       mulMatVec3(nw, R, nl); /* box -> point */
       double pos[3] = {p[0] - nw[0] * (r + 0.5 * dist), p[1] - nw[1] * (r + 0.5 * dist), p[2] - nw[2] * (r + 0.5 * dist)};
@@ -591,6 +603,49 @@ static double pointBoxDistance(const QsModel* m, int b, const double* p, double*
   }
   mulMatVec3(nw, R, nl);
   return dist;
+}
+
+/* Parameter t in [-L, L] of the point of the segment c + t*a (|a| = 1) nearest to static box b.  In the box frame the squared
+ * distance f(t) = sum_i excess_i(t)^2 (excess = how far coordinate i lies outside its slab) is convex and C1, so its derivative
+ * g(t) = sum_i dv_i * excess_i(t) is monotone: bisect for its root. */
+static double segmentBoxClosest(const QsModel* m, int b, const double* c, const double* a, double L) {
+  double R[9], q0[3], dv[3], rel[3] = {c[0] - m->box_pos[b][0], c[1] - m->box_pos[b][1], c[2] - m->box_pos[b][2]};
+  const double* h = m->box_half[b];
+  quat2Mat(R, m->box_quat[b]);
+  mulMatTVec3(q0, R, rel);
+  mulMatTVec3(dv, R, a);
+#define SEG_G(t, out) do { double g_ = 0; for (int i_ = 0; i_ < 3; i_++) { double q_ = q0[i_] + (t) * dv[i_]; \
+    if (q_ > h[i_]) g_ += dv[i_] * (q_ - h[i_]); else if (q_ < -h[i_]) g_ += dv[i_] * (q_ + h[i_]); } out = g_; } while (0)
+  double lo = -L, hi = L, glo, ghi;
+  SEG_G(lo, glo); SEG_G(hi, ghi);
+  if (glo >= 0) return -L;
+  if (ghi <= 0) return L;
+  for (int it = 0; it < 60; it++) {
+    double mid = 0.5 * (lo + hi), gm;
+    SEG_G(mid, gm);
+    if (gm < 0) lo = mid; else hi = mid;
+  }
+#undef SEG_G
+  return 0.5 * (lo + hi);
+}
+
+/* Capsule against static boxes beyond its two end spheres: where an interior point of the axis is strictly nearer to a box than
+ * both ends (a leg lying across a stair edge), that point is a third sphere feature.  Not generated when the ends are as near
+ * (capsule flat on a face: the two end contacts carry it). [MJ-approx of mjc_CapsuleBox] */
+static void collideCapsuleMidBoxes(OData* d, int g, const double* c, const double* a, double L, double r) {
+  const QsModel* m = &d->m;
+  for (int b = 0; b < m->nbox; b++) {
+    double rel[3] = {c[0] - m->box_pos[b][0], c[1] - m->box_pos[b][1], c[2] - m->box_pos[b][2]};
+    double reach = norm3(m->box_half[b]) + L + r + 0.01;
+    if (dot3(rel, rel) > reach * reach) continue;
+    double t = segmentBoxClosest(m, b, c, a, L);
+    if (!(t > -L * (1 - 1e-6) && t < L * (1 - 1e-6))) continue;
+    double pm[3] = {c[0] + t * a[0], c[1] + t * a[1], c[2] + t * a[2]}, p1[3], p2[3], nw[3];
+    for (int i = 0; i < 3; i++) { p1[i] = c[i] + L * a[i]; p2[i] = c[i] - L * a[i]; }
+    double dm = pointBoxDistance(m, b, pm, nw), d1 = pointBoxDistance(m, b, p1, nw), d2 = pointBoxDistance(m, b, p2, nw);
+    if (!(dm < fmin(d1, d2) - 1e-6)) continue;
+    pointBoxContact(d, g, b, pm, r, QS_GEOM_CAPSULE, a);
+  }
 }
 
 /* convex mesh g (hull vertices in the body frame) against the height field / the static boxes */
@@ -651,6 +706,7 @@ static void collideTerrain(OData* d) {
           double p[3] = {gx[0] + s * axis[0] * sz[1], gx[1] + s * axis[1] * sz[1], gx[2] + s * axis[2] * sz[1]};
           collidePointTerrain(d, g, p, sz[0], QS_GEOM_CAPSULE, axis);
         }
+        if (m->terrain_type == QS_TERRAIN_BOXES) collideCapsuleMidBoxes(d, g, gx, axis, sz[1], sz[0]);
       } break;
       case QS_GEOM_BOX:
         for (int i = 0; i < 8; i++) {

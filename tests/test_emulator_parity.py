@@ -257,3 +257,86 @@ def test_specialised_variants_are_bit_identical_to_generic(robot, scene, feat_bi
         qa, va, wa = a['qpos'], a['qvel'], a['qacc']
         qb, vb, wb = b['qpos'], b['qvel'], b['qacc']
     assert saw_contact
+
+
+def _capsule_segments(m, q):
+    """World end points of every capsule geom from an independent numpy FK over the compiled tree (hinge angle = qpos - qpos0)."""
+    c = m.c
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+    def rot(qt, v):
+        w, x, y, z = qt
+        R = np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+        return R @ np.asarray(v)
+
+    pos = {1: q[:3]}; quat = {1: q[3:7] / np.linalg.norm(q[3:7])}
+    for b in range(2, 14):
+        pa = c.body_parent[b]
+        pos[b] = pos[pa] + rot(quat[pa], c.body_pos[b])
+        qb = qmul(quat[pa], np.array(c.body_quat[b]))
+        ang = q[7 + b - 2] - c.qpos0[7 + b - 2]
+        ax = np.array(c.jnt_axis[b - 2])
+        quat[b] = qmul(qb, np.r_[np.cos(ang / 2), np.sin(ang / 2) * ax])
+    out = {}
+    for g in range(c.ngeom):
+        if c.geom_type[g] != 3:
+            continue
+        b = c.geom_body[g]
+        ctr = pos[b] + rot(quat[b], c.geom_pos[g])
+        axis = rot(qmul(quat[b], np.array(c.geom_quat[g])), [0, 0, 1])
+        out[g] = (ctr, axis, c.geom_size[g][1], c.geom_size[g][0])
+    return out
+
+
+def test_capsule_lying_across_a_box_edge_gets_a_mid_segment_contact():
+    """A capsule link draped over a stair edge touches it between its two end spheres: the nearest point of the capsule axis to the
+    box (bisection on the derivative of the squared segment-box distance) becomes a third sphere feature when it is strictly nearer
+    than both ends.  Random poses of go1 on the stairs; the kernel source (fp64, emulated warp) must reproduce the oracle's
+    contacts, and contacts whose foot point on the capsule axis lies well inside the segment must occur (checked with an independent
+    numpy FK of the capsule end points)."""
+    m = Model('go1', 'stairs')  # thin, long `fromto` capsules on thighs and calves (go1.xml:47-59)
+    rng = np.random.RandomState(3)
+    key = np.array(m.c.key_qpos)
+    mids, checked = 0, 0
+    for trial in range(600):
+        q = key.copy()
+        q[0] = rng.uniform(0.8, 3.0); q[1] = rng.uniform(-0.5, 0.5); q[2] = rng.uniform(0.25, 0.75)
+        ang = rng.uniform(-0.6, 0.6, 3)
+        cr, sr, cp, sp, cy, sy = np.cos(ang[0] / 2), np.sin(ang[0] / 2), np.cos(ang[1] / 2), np.sin(ang[1] / 2), np.cos(ang[2] / 2), np.sin(ang[2] / 2)
+        q[3:7] = [cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy]
+        q[7:] += rng.uniform(-0.6, 0.6, 12)
+        q = q.astype(np.float32).astype(np.float64)
+        o = Oracle(m)
+        o.set_state(q, np.zeros(18), np.zeros(18)); o.forward(np.zeros(12))
+        oc = o.get(F_CONTACTS)
+        if len(oc) == 0 or len(oc) > 16:
+            continue
+        segs = _capsule_segments(m, q)
+        n_mid = 0
+        for row in oc:
+            g = int(row[16])
+            if g not in segs:
+                continue
+            ctr, axis, L, r = segs[g]
+            t = float(np.dot(row[1:4] - ctr, axis))  # foot of the contact point on the capsule axis
+            # an end-sphere contact projects to |t| >= L - r; anything well inside that can only be the mid-segment feature
+            if abs(t) < L - r - 0.002 and row[3] > 0.02:
+                n_mid += 1
+        if n_mid == 0 and checked >= 12:
+            continue  # enough poses without a mid contact have been compared already
+        e = emu_step(m, q, np.zeros(18), np.zeros(18), np.zeros(12), -1.0, -1.0, [0, 0, 0, 0], precision=1, mode=0)
+        assert e['ncon'] == len(oc), f'trial {trial}'
+        ec = e['contacts']
+        key_ = lambda cc: np.lexsort((np.round(cc[:, 2], 7), np.round(cc[:, 1], 7), np.round(cc[:, 0], 9), cc[:, 16]))
+        oc2, ec2 = oc[key_(oc)], ec[key_(ec)]
+        assert (oc2[:, 16:18] == ec2[:, 16:18]).all()
+        np.testing.assert_allclose(ec2[:, 0:13], oc2[:, 0:13], atol=1e-7)
+        checked += 1
+        mids += n_mid
+        if mids >= 6 and checked >= 20:
+            break
+    assert checked >= 12 and mids >= 3, (checked, mids)
