@@ -161,3 +161,20 @@ def test_lane_role_table_of_the_kernel_source():
                               for e in (lane, lane + 32)]
         dl, dk = ((lane - 6) // 3, (lane - 6) % 3) if 6 <= lane < 18 else (0, 0)
         assert v == i0 | (j0 << 4) | (i1 << 8) | (j1 << 12) | (dl << 16) | (dk << 18) | ((lane // 6) << 20) | ((lane % 6) << 23)
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) must work on a CPU-only host and print one
+    JSON line whose `config` has the keys of the GPU arm's (the driver compares the two objects)."""
+    import json
+    out = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1', '--envs', '32'],
+                         capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['unit'] == 'env-steps/s' and line['higher_is_better'] is True
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    sys.path.insert(0, str(ROOT))
+    import bench
+    bench.select_workload('cfg2')
+    assert set(line['config']) == set(bench.workload_config(1, 32))
