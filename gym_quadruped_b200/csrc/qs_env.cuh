@@ -119,6 +119,10 @@ constexpr int FEAT_CFG2 = FEAT_PYR | FEAT_FLAT | FEAT_NO_IMU | FEAT_NO_HM | FEAT
 constexpr int FEAT_CFG3 = FEAT_PYR | FEAT_HFIELD | FEAT_NO_IMU | FEAT_NO_MESH | FEAT_NO_CYL | FEAT_NGEOM32;                                              // aliengo / perlin (+ height map)
 constexpr int FEAT_CFG4 = FEAT_ELL | FEAT_BOXES | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_MESH | FEAT_NO_CYL | FEAT_NGEOM32;                                 // go2 / random_boxes
 constexpr int FEAT_CFG5 = FEAT_ELL | FEAT_FLAT | FEAT_NO_HM | FEAT_NO_CAPSULE | FEAT_NO_BOX | FEAT_NO_CYL | FEAT_NGEOM32;                               // hyqreal1 / flat (+ IMU)
+// further flat-floor variants for the robots outside the BASELINE configurations
+constexpr int FEAT_PYR_FLAT_PRIM = FEAT_PYR | FEAT_FLAT | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_MESH | FEAT_NGEOM32;                                       // aliengo, hyqreal2, b2 / flat
+constexpr int FEAT_ELL_FLAT_PRIM = FEAT_ELL | FEAT_FLAT | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_MESH;                                                      // go2, go1 / flat (condim 6)
+constexpr int FEAT_ELL_FLAT_MESH6 = FEAT_ELL | FEAT_FLAT | FEAT_NO_IMU | FEAT_NO_HM | FEAT_NO_CAPSULE | FEAT_NO_BOX | FEAT_NO_CYL | FEAT_NGEOM32;      // spot / flat (condim 6)
 
 template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   using N = Num<real>;

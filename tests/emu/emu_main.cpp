@@ -128,11 +128,17 @@ extern "C" int emu_step(const QsModel* model, int precision, double* qpos, doubl
       if (md <= 3 && ok(FEAT_CFG3)) return QS_EMU_RUN(float, 3, FEAT_CFG3);
       if (md <= 3 && ok(FEAT_CFG5)) return QS_EMU_RUN(float, 3, FEAT_CFG5);
       if (md > 3 && ok(FEAT_CFG4)) return QS_EMU_RUN(float, 6, FEAT_CFG4);
+      if (md <= 3 && ok(FEAT_PYR_FLAT_PRIM)) return QS_EMU_RUN(float, 3, FEAT_PYR_FLAT_PRIM);
+      if (md > 3 && ok(FEAT_ELL_FLAT_MESH6)) return QS_EMU_RUN(float, 6, FEAT_ELL_FLAT_MESH6);
+      if (md > 3 && ok(FEAT_ELL_FLAT_PRIM)) return QS_EMU_RUN(float, 6, FEAT_ELL_FLAT_PRIM);
     } else {
       if (md <= 3 && ok(FEAT_CFG2)) return QS_EMU_RUN(double, 3, FEAT_CFG2);
       if (md <= 3 && ok(FEAT_CFG3)) return QS_EMU_RUN(double, 3, FEAT_CFG3);
       if (md <= 3 && ok(FEAT_CFG5)) return QS_EMU_RUN(double, 3, FEAT_CFG5);
       if (md > 3 && ok(FEAT_CFG4)) return QS_EMU_RUN(double, 6, FEAT_CFG4);
+      if (md <= 3 && ok(FEAT_PYR_FLAT_PRIM)) return QS_EMU_RUN(double, 3, FEAT_PYR_FLAT_PRIM);
+      if (md > 3 && ok(FEAT_ELL_FLAT_MESH6)) return QS_EMU_RUN(double, 6, FEAT_ELL_FLAT_MESH6);
+      if (md > 3 && ok(FEAT_ELL_FLAT_PRIM)) return QS_EMU_RUN(double, 6, FEAT_ELL_FLAT_PRIM);
     }
   }
   if (precision == 0) return md > 3 ? QS_EMU_RUN(float, 6, 0) : QS_EMU_RUN(float, 3, 0);

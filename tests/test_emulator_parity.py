@@ -219,7 +219,8 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
     assert mesh_terrain_contacts >= 5 and worst < 1e-8, (mesh_terrain_contacts, worst)
 
 
-@pytest.mark.parametrize('robot,scene,feat_bits', [('mini_cheetah', 'flat', 8101), ('aliengo', 'perlin', 1641), ('go2', 'random_boxes', 5746), ('hyqreal1', 'flat', 6022)])
+@pytest.mark.parametrize('robot,scene,feat_bits', [('mini_cheetah', 'flat', 8101), ('aliengo', 'perlin', 1641), ('go2', 'random_boxes', 5746), ('hyqreal1', 'flat', 6022),
+                                                   ('b2', 'flat', 5221), ('go1', 'flat', 4198), ('spot', 'flat', 6054)])
 @pytest.mark.parametrize('precision', [0, 1])
 def test_specialised_variants_are_bit_identical_to_generic(robot, scene, feat_bits, precision):
     """The four specialised step kernels (compile-time feature switches, csrc/qs_env.cuh FEAT_CFG2..5) against the generic

@@ -21,7 +21,8 @@ from tests.helpers import oracle_rollout, seeded_states
 pytestmark = pytest.mark.gpu
 
 CONFIGS = [('mini_cheetah', 'flat', False, None, 'f3_pyr_flat_mesh'), ('aliengo', 'perlin', False, (5, 5, 0.1, 0.1), 'f3_pyr_hfield_prim'),
-           ('go2', 'random_boxes', False, None, 'f6_ell_boxes_prim'), ('hyqreal1', 'flat', True, None, 'f3_ell_flat_mesh')]
+           ('go2', 'random_boxes', False, None, 'f6_ell_boxes_prim'), ('hyqreal1', 'flat', True, None, 'f3_ell_flat_mesh'),
+           ('aliengo', 'flat', False, None, 'f3_pyr_flat_prim'), ('go1', 'flat', False, None, 'f6_ell_flat_prim'), ('spot', 'flat', False, None, 'f6_ell_flat_mesh')]
 
 
 def _state(sim):
