@@ -405,6 +405,7 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
     p.q_tail = h->d_queue_tail + out;
     p.q_tail_base = unsigned((s / QS_QUEUE_DEPTH) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
     p.q_contiguous = (h->cfg.pipeline || kmode) ? 1 : 0;
+    if (const char* ev = getenv("QSTEP_QMAP")) p.q_contiguous = atoi(ev);  // placement experiments: 0 balanced, 1 finish-order groups
     p.q_sync = (h->cfg.pipeline || kmode) ? 1 : 0;
   }
   if (h->gather.connected) {
