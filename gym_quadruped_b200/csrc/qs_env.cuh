@@ -452,10 +452,10 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
 
   // ------------------------------------------------------------------ structured linear algebra
   // y = A x for a block matrix (bb, lb, ll); valid on dof lanes (< NV), x read from shared memory
-  QS_DEV real block_matvec(const real (*Abb)[6], const real (*Alb)[3][6], const real (*All)[3][3], const real* x) const {
+  QS_DEV static real block_matvec(const real (*Abb)[6], const real (*Alb)[3][6], const real (*All)[3][3], const real* x, const int lane, const int tri) {
     // both row shapes are evaluated on clamped indices and the lane keeps its own: a divergent warp would run both anyway
     const bool isbase = lane < 6;
-    const int l = dof_leg(), k = dof_k(), bl = isbase ? lane : 0;
+    const int l = tri_dof_leg(tri), k = tri_dof_k(tri), bl = isbase ? lane : 0;
     const real* row = isbase ? Abb[bl] : Alb[l][k];
     real s = 0, sb = 0, sl = 0;
 #pragma unroll
@@ -465,6 +465,10 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
 #pragma unroll
     for (int k2 = 0; k2 < 3; k2++) sl += All[l][k][k2] * x[6 + 3 * l + k2];
     return s + (isbase ? sb : sl);
+  }
+  // (M x)[lane] with the mass blocks of the workspace: one out-of-line copy for the five call sites of a step
+  QS_NOINLINE static real mass_matvec(const W& w, const real* x, const int lane, const int tri) {
+    return block_matvec(w.Mbb, w.Mlb, w.Mll, x, lane, tri);
   }
 
   // Factor the block matrix in w.hes (Hbb, Hlb, Hll): leg blocks C_l -> explicit inverses Ci, Y_l = C_l^-1 B_l,
@@ -1704,7 +1708,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
     units_Jx(w.warm, w.u_r, w.c_r, true);
     real cost_w = units_cost();
     {
-      const real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.warm);
+      const real ma = mass_matvec(w, w.warm, lane, tri);
       cost_w += warp_sum((lane < NV) ? real(0.5) * (ma - w.fsm[lane]) * (w.warm[lane] - w.asmooth[lane]) : real(0));
     }
     units_Jx(w.asmooth, w.u_r, w.c_r, true);
@@ -1714,7 +1718,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
     syncwarp();
     if (use_warm) units_Jx(w.qacc, w.u_r, w.c_r, true);
     {
-      const real ma = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+      const real ma = mass_matvec(w, w.qacc, lane, tri);
       if (lane < NV) w.Ma[lane] = ma;
     }
     syncwarp();
@@ -1774,7 +1778,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       QS_TACC(4);
 #endif
       // exact line search
-      const real mv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.search);
+      const real mv = mass_matvec(w, w.search, lane, tri);
       if (lane < NV) w.Mv[lane] = mv;
       units_Jx(w.search, w.u_v, w.c_v, false);
       const real sd = (lane < NV) ? w.search[dl_] : real(0);
@@ -1911,7 +1915,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
     real* o = w.obs;
     const real ox = real(w.org[0]), oy = real(w.org[1]);
     // kinetic energy / work first: they need nothing from the recycled region
-    const real mvv = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qvel), maa = block_matvec(w.Mbb, w.Mlb, w.Mll, w.qacc);
+    const real mvv = mass_matvec(w, w.qvel, lane, tri), maa = mass_matvec(w, w.qacc, lane, tri);
     const int dl_ = lane < NV ? lane : 0;
     real ke = (lane < NV) ? real(0.5) * w.qvel[dl_] * mvv : real(0), wk = (lane < NV) ? maa * w.qvel[dl_] : real(0);
     warp_sum2(ke, wk);
