@@ -26,7 +26,7 @@
 namespace qs {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
-constexpr int QS_QUEUE_DEPTH = 8;
+constexpr int QS_QUEUE_DEPTH = 8;  // allocated ring entries; QSTEP_RING_DEPTH (2..8, read by qs_create) uses fewer (tests)
 constexpr int NCON_MAX = 16;
 constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6 + 3 * 216;  // 1640
 constexpr int AUX_OFF_M = 0, AUX_OFF_BIAS = 324, AUX_OFF_PASSIVE = 342, AUX_OFF_JACP = 360, AUX_OFF_FEETPOS = 576, AUX_OFF_COM = 588,
@@ -690,6 +690,16 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     __syncwarp();
     if (lane == 0) {
       if (p.gather_world > 1) __threadfence_system();  // this warp's peer stores are performed before it counts as finished
+      if (p.q_sync) {
+        // The publish counter of a ring entry is shared by every launch that fills it (s, s + depth, ...): wait until the previous
+        // one has published all of its envs, i.e. until the counter has reached this launch's base.  Only an env that lags `depth`
+        // launches behind (a reset that lifts the robot 100 times) ever makes a fast env wait here.
+        unsigned t_;
+        do {
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(t_) : "l"(p.q_tail) : "memory");
+          if (int(t_ - p.q_tail_base) < 0) __nanosleep(200);
+        } while (int(t_ - p.q_tail_base) < 0);
+      }
       const unsigned pos = atomicAdd(p.q_tail, 1u) - p.q_tail_base;
       if (p.q_sync) {
         while (ld_acquire(p.q_out + pos) >= 0) __nanosleep(200);  // the consumer of this ring entry's previous use is far behind: wait

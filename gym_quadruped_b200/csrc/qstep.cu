@@ -90,6 +90,7 @@ struct QsHandle_ {
   KernelFn k_raycast = nullptr;
   int* d_queue = nullptr;          // QS_QUEUE_DEPTH x [N] finish-order queues (see KParams)
   unsigned* d_queue_tail = nullptr; // one monotonic publish counter per ring entry
+  int ring_depth = QS_QUEUE_DEPTH;  // ring entries in use (QSTEP_RING_DEPTH lowers it: tests of the depth-limited case)
   uint64_t step_seq = 0;           // number of step launches so far: launch s reads ring entry s % DEPTH and fills (s + 1) % DEPTH
   bool last_was_step = false;      // the previous launch of this handle was a step kernel (nothing of ours in between)
   void* last_stream = nullptr;
@@ -215,6 +216,7 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
   h->maxdim = model_max_dim(*model) > 3 ? 6 : 3;
   int rc;
   h->seed = cfg->seed;
+  if (const char* ev = getenv("QSTEP_RING_DEPTH")) { const int v = atoi(ev); if (v >= 2 && v <= QS_QUEUE_DEPTH) h->ring_depth = v; }
   rc = cfg->precision == 0 ? setup_variant<float>(h, model) : setup_variant<double>(h, model);
   if (rc == 0) {
     const size_t n = size_t(cfg->num_envs);
@@ -400,10 +402,11 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
   {
     const size_t n = size_t(h->cfg.num_envs);
     const uint64_t s = h->step_seq++;
-    const int in = int(s % QS_QUEUE_DEPTH), out = int((s + 1) % QS_QUEUE_DEPTH);
+    const uint64_t D = uint64_t(h->ring_depth);
+    const int in = int(s % D), out = int((s + 1) % D);
     p.q_in = h->d_queue + size_t(in) * n; p.q_out = h->d_queue + size_t(out) * n;
     p.q_tail = h->d_queue_tail + out;
-    p.q_tail_base = unsigned((s / QS_QUEUE_DEPTH) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
+    p.q_tail_base = unsigned((s / D) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
     p.q_contiguous = (h->cfg.pipeline || kmode) ? 1 : 0;
     if (const char* ev = getenv("QSTEP_QMAP")) p.q_contiguous = atoi(ev);  // placement experiments: 0 balanced, 1 finish-order groups
     p.q_sync = (h->cfg.pipeline || kmode) ? 1 : 0;

@@ -60,12 +60,19 @@ def test_specialised_variant_equals_generic(robot, scene, imu, hm, variant, cuda
     assert n_term > 0
 
 
-@pytest.mark.parametrize('robot,scene,n', [('mini_cheetah', 'flat', 4096), ('mini_cheetah', 'flat', 100), ('go2', 'random_boxes', 1500)])
-def test_pipelined_launches_equal_serialized(robot, scene, n, cuda_device):
+@pytest.mark.parametrize('robot,scene,n,ring', [('mini_cheetah', 'flat', 4096, 0), ('mini_cheetah', 'flat', 100, 0), ('go2', 'random_boxes', 1500, 0),
+                                                ('mini_cheetah', 'flat', 4096, 2), ('go2', 'random_boxes', 4096, 2), ('go2', 'random_boxes', 4096, 3)])
+def test_pipelined_launches_equal_serialized(robot, scene, n, ring, cuda_device, monkeypatch):
     """QsConfig.pipeline: consecutive step launches overlap on the device (programmatic dependent launch; every env waits only for
     its own previous step through the finish-order queues).  Results must not depend on it: K back-to-back launches with overlap
     == the same K launches in plain stream order, for the state, the per-step flags and the observation of the last step; also
-    across launch-chain breaks (a reset or a host read between steps)."""
+    across launch-chain breaks (a reset or a host read between steps).
+
+    `ring` > 0 shortens the queue ring (QSTEP_RING_DEPTH, read by qs_create): fast envs then catch up with the ring entry a
+    straggler (an env whose reset lifts the robot out of a box, up to 100 times) has not published to yet -- they have to wait for
+    the entry's publish counter to reach their launch's base instead of taking a position relative to the older launch."""
+    if ring:
+        monkeypatch.setenv('QSTEP_RING_DEPTH', str(ring))
     m = Model(robot, scene)
     a = BatchSim(m, n, device=cuda_device, seed=7, pipeline=True)
     b = BatchSim(m, n, device=cuda_device, seed=7, pipeline=False)
