@@ -22,9 +22,10 @@ for robot, scene, pipeline in cases:
         q = sim.qpos.clone(); q[:, 0] = 2.0; q[:, 1] = -1.0 if scene == 'random_boxes' else 2.0; q[:, 2] = 0.5 if scene == 'random_boxes' else 0.9
         sim.set_state(q, sim.qvel)
     g = torch.Generator(device='cuda').manual_seed(0)
-    ctrl = torch.randn(16, 96, 12, device='cuda', generator=g) * 30
+    T = int(os.environ.get('SAN_STEPS', '16'))
+    ctrl = torch.randn(T, 96, 12, device='cuda', generator=g) * 30
     torch.cuda.synchronize()
-    for t in range(16):
+    for t in range(T):
         sim.step_autoreset(ctrl[t], opt)  # back-to-back launches: chained when pipeline=True
     sim.forward(); sim.get(FIELD_CONTACTS)
     torch.cuda.synchronize()
