@@ -9,6 +9,10 @@
 // The tree sparsity (6-dof base + four independent 3-dof legs) is exploited throughout: M and the Newton Hessian are
 // stored as {base 6x6, four 3x6 couplings, four 3x3 leg blocks} and factored by a Schur complement on the leg blocks.
 //
+// Third-party attribution: comments marked [MJ] name the routine of the MuJoCo physics engine (Google DeepMind, Apache License 2.0;
+// the engine behind the reference's `mujoco` dependency, not part of the reference checkout) whose published algorithm a phase
+// restates.  No MuJoCo source was copied.
+//
 // This header is compiled by nvcc for sm_100a (qstep.cu) and, unchanged, by g++ against a 32-thread warp emulator
 // (tests/emu) so the exact kernel source can be checked against the fp64 oracle on a CPU-only host.
 #pragma once
@@ -1118,32 +1122,32 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       } else if (type_on(GEOM_CYLINDER) && type == GEOM_CYLINDER) {
         // [MJ] mjc_PlaneCylinder: nearest rim point of the lower cap, its twin on the other cap, two more lower-rim points at +-120 deg
         real gxa[3] = {m.geom_mat[g][0], m.geom_mat[g][3], m.geom_mat[g][6]}, gza[3] = {m.geom_mat[g][2], m.geom_mat[g][5], m.geom_mat[g][8]};
-        real xax[3], axis[3], vec[3];
+        real xax[3], axis[3], rim[3];
         mul_mv(xax, w.kin.xmat[b], gxa);
         mul_mv(axis, w.kin.xmat[b], gza);
-        real prjaxis = axis[2];
-        if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
-        const real dist0 = gx[2];
-        vec[0] = axis[0] * prjaxis; vec[1] = axis[1] * prjaxis; vec[2] = axis[2] * prjaxis - 1;
-        const real len_sqr = dot3(vec, vec);
-        if (len_sqr >= real(1e-30)) { const real scl = sz[0] * N::rsqrt(len_sqr); for (int i = 0; i < 3; i++) vec[i] *= scl; }
-        else for (int i = 0; i < 3; i++) vec[i] = xax[i] * sz[0];
-        const real prjvec = vec[2];
-        const real ax[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
-        prjaxis *= sz[1];
-        real dist = dist0 + prjaxis + prjvec;
+        real axis_z = axis[2];
+        if (axis_z > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; axis_z = -axis_z; }
+        const real height = gx[2];
+        rim[0] = axis[0] * axis_z; rim[1] = axis[1] * axis_z; rim[2] = axis[2] * axis_z - 1;
+        const real rim_n2 = dot3(rim, rim);
+        if (rim_n2 >= real(1e-30)) { const real scl = sz[0] * N::rsqrt(rim_n2); for (int i = 0; i < 3; i++) rim[i] *= scl; }
+        else for (int i = 0; i < 3; i++) rim[i] = xax[i] * sz[0];
+        const real rim_z = rim[2];
+        const real half[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
+        axis_z *= sz[1];
+        real dist = height + axis_z + rim_z;
         if (!(dist > margin)) {
-          cd[0] = dist; for (int i = 0; i < 3; i++) cp[0][i] = gx[i] + vec[i] + ax[i]; cp[0][2] -= real(0.5) * dist; nc = 1;
-          dist = dist0 - prjaxis + prjvec;
-          if (!(dist > margin)) { cd[nc] = dist; for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + vec[i] - ax[i]; cp[nc][2] -= real(0.5) * dist; nc++; }
-          dist = dist0 + prjaxis - real(0.5) * prjvec;
+          cd[0] = dist; for (int i = 0; i < 3; i++) cp[0][i] = gx[i] + rim[i] + half[i]; cp[0][2] -= real(0.5) * dist; nc = 1;
+          dist = height - axis_z + rim_z;
+          if (!(dist > margin)) { cd[nc] = dist; for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + rim[i] - half[i]; cp[nc][2] -= real(0.5) * dist; nc++; }
+          dist = height + axis_z - real(0.5) * rim_z;
           if (!(dist > margin)) {
-            real vec1[3];
-            cross3(vec1, vec, ax);
-            const real n2 = dot3(vec1, vec1), scl = n2 > 0 ? sz[0] * real(0.86602540378443864676) * N::rsqrt(n2) : real(0);
+            real side[3];
+            cross3(side, rim, half);
+            const real n2 = dot3(side, side), scl = n2 > 0 ? sz[0] * real(0.86602540378443864676) * N::rsqrt(n2) : real(0);
             for (int sgn = 1; sgn >= -1; sgn -= 2) {
               cd[nc] = dist;
-              for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + sgn * scl * vec1[i] + ax[i] - real(0.5) * vec[i];
+              for (int i = 0; i < 3; i++) cp[nc][i] = gx[i] + sgn * scl * side[i] + half[i] - real(0.5) * rim[i];
               cp[nc][2] -= real(0.5) * dist;
               nc++;
             }

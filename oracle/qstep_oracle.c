@@ -4,6 +4,10 @@
  * env-side observation pack (`_get_obs`, quadruped_env.py:1146-1226), termination checks (:1228-1257), the reset lift
  * loop (:376-388), IMU truth signals (sensors/imu.py:110-139) and the height-map ray cast (sensors/heightmap.py:66-104).
  *
+ * Third-party attribution: the formulas marked [MJ] restate published algorithms of the MuJoCo physics engine (Google DeepMind,
+ * Apache License 2.0), the engine the reference calls through its `mujoco` dependency.  MuJoCo's sources are not part of
+ * /root/reference and nothing was copied from them; the restatements follow the engine's documentation and SURVEY.md App. A.
+ *
  * PARITY UNPINNED: the arithmetic of this path lives in the third-party engine MuJoCo (pyproject.toml:30,
  * `mujoco>=3.10.0`, no lock file), which is neither vendored under /root/reference nor installable in this image, and
  * the reference's only test (tests/env_test.py:14-53) holds no golden numbers.  This file restates the engine's
@@ -442,31 +446,31 @@ static void collideFloor(OData* d) {
       case QS_GEOM_CYLINDER: {
         /* [MJ] mjc_PlaneCylinder (b2.xml:96, go1.xml:27-44): the rim point nearest to the plane on the lower cap, the matching
          * point of the other cap, and two more points of the lower rim at +-120 degrees */
-        double axis[3] = {gm[2], gm[5], gm[8]}, prjaxis = axis[2], vec[3];
-        if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
-        const double dist0 = gx[2];
-        for (int i = 0; i < 3; i++) vec[i] = axis[i] * prjaxis - n[i];
-        const double len_sqr = dot3(vec, vec);
-        if (len_sqr >= 1e-30) { const double scl = sz[0] / sqrt(len_sqr); for (int i = 0; i < 3; i++) vec[i] *= scl; }
-        else { vec[0] = gm[0] * sz[0]; vec[1] = gm[3] * sz[0]; vec[2] = gm[6] * sz[0]; }
-        const double prjvec = vec[2];
-        double ax[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
-        prjaxis *= sz[1];
-        double dist = dist0 + prjaxis + prjvec;
+        double axis[3] = {gm[2], gm[5], gm[8]}, axis_z = axis[2], rim[3];
+        if (axis_z > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; axis_z = -axis_z; }
+        const double height = gx[2];
+        for (int i = 0; i < 3; i++) rim[i] = axis[i] * axis_z - n[i];
+        const double rim_n2 = dot3(rim, rim);
+        if (rim_n2 >= 1e-30) { const double scl = sz[0] / sqrt(rim_n2); for (int i = 0; i < 3; i++) rim[i] *= scl; }
+        else { rim[0] = gm[0] * sz[0]; rim[1] = gm[3] * sz[0]; rim[2] = gm[6] * sz[0]; }
+        const double rim_z = rim[2];
+        double half[3] = {axis[0] * sz[1], axis[1] * sz[1], axis[2] * sz[1]};
+        axis_z *= sz[1];
+        double dist = height + axis_z + rim_z;
         if (dist > margin) break;
-        { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + vec[i] + ax[i] - n[i] * dist * 0.5;
+        { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + rim[i] + half[i] - n[i] * dist * 0.5;
           addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri); }
-        dist = dist0 - prjaxis + prjvec;
-        if (!(dist > margin)) { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + vec[i] - ax[i] - n[i] * dist * 0.5;
+        dist = height - axis_z + rim_z;
+        if (!(dist > margin)) { double pos[3]; for (int i = 0; i < 3; i++) pos[i] = gx[i] + rim[i] - half[i] - n[i] * dist * 0.5;
           addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri); }
-        dist = dist0 + prjaxis - 0.5 * prjvec;
+        dist = height + axis_z - 0.5 * rim_z;
         if (!(dist > margin)) {
-          double vec1[3];
-          cross3(vec1, vec, ax);
-          const double nv = norm3(vec1), scl = nv > 0 ? sz[0] * sqrt(3.0) * 0.5 / nv : 0.0;
+          double side[3];
+          cross3(side, rim, half);
+          const double nv = norm3(side), scl = nv > 0 ? sz[0] * sqrt(3.0) * 0.5 / nv : 0.0;
           for (int sgn = 1; sgn >= -1; sgn -= 2) {
             double pos[3];
-            for (int i = 0; i < 3; i++) pos[i] = gx[i] + sgn * scl * vec1[i] + ax[i] - 0.5 * vec[i] - n[i] * dist * 0.5;
+            for (int i = 0; i < 3; i++) pos[i] = gx[i] + sgn * scl * side[i] + half[i] - 0.5 * rim[i] - n[i] * dist * 0.5;
             addContact(d, g, 0, 1, dist, pos, n, NULL, &m->floor_par, wfri);
           }
         }
