@@ -1215,6 +1215,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
         const int oi = shfl_xor(bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
+      if (bi == 0x7fffffff) continue;  // non-finite pose: no vertex compares greater (the step then ends the episode, status bit0)
       const Vert4<real> p = v[bi];
       const real pw[3] = {w.kin.xpos[b][0] + R[0] * p.x + R[1] * p.y + R[2] * p.z, w.kin.xpos[b][1] + R[3] * p.x + R[4] * p.y + R[5] * p.z,
                           w.kin.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};

@@ -578,7 +578,13 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     e.integrate(base64);
     QS_MARK(6);
     fl.out_of_bounds = e.out_of_bounds();  // bounds are tested on the post-step base position (:1252-1256)
-    const bool terminated = fl.invalid_mask != 0 || fl.out_of_bounds;
+    // A non-finite state also ends the episode (status bit0): the engine warns and resets its data in that case; here the reset
+    // is the caller's (or the auto-reset pass's), so that one bad env cannot stay bad for the rest of a rollout.
+    bool finite_state = true;
+    if (lane < NQ) finite_state = isfinite(w.qpos[lane]);
+    if (lane < NV) finite_state = finite_state && isfinite(w.qvel[lane]);
+    if (QS_UNLIKELY(qs::ballot(!finite_state) != 0)) status |= 1u;
+    const bool terminated = fl.invalid_mask != 0 || fl.out_of_bounds || (status & 1u);
     sim_time += float(m.timestep);
     step_count = resetting ? 0 : step_count + 1;
     if (resetting) {
@@ -604,12 +610,6 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     QS_MARK(7);
 
     // ---- write back
-    {
-      bool ok = true;
-      if (lane < NQ) ok = ok && isfinite(w.qpos[lane]);
-      if (lane < NV) ok = ok && isfinite(w.qvel[lane]);
-      if (qs::ballot(!ok) != 0) status |= 1u;
-    }
     if (w.overflow) status |= 2u;
     if (e.solver_maxed) status |= 4u;
     if (lane < NQ) B.qpos[size_t(env) * NQ + lane] = (lane < 3) ? float(base64[lane]) : float(w.qpos[lane]);

@@ -1440,7 +1440,11 @@ int orc_step(void* h, const double* ctrl, double* obs) {
     packObs(d, obs);
     if (d->m.has_imu) { memcpy(obs + QS_NOBS_BASE, d->sensor_acc, sizeof(d->sensor_acc)); memcpy(obs + QS_NOBS_BASE + 3, d->sensor_gyro, sizeof(d->sensor_gyro)); }
   }
-  return d->invalid_contact || d->out_of_bounds;
+  /* libqstep rule (no counterpart in the env; the engine itself warns and resets its data on a bad state): a non-finite state ends the episode */
+  int bad = 0;
+  for (int i = 0; i < QS_NQ; i++) bad |= !isfinite(d->qpos[i]);
+  for (int i = 0; i < QS_NV; i++) bad |= !isfinite(d->qvel[i]);
+  return d->invalid_contact || d->out_of_bounds || bad;
 }
 
 /* reset lift loop, quadruped_env.py:376-388: returns number of lifts, -1 if contact could not be cleared */

@@ -609,3 +609,48 @@ def test_host_entry_point_with_padded_rows(cuda_device):
     obs, _, _, _ = sims[2].step(ctrl.to(cuda_device))
     assert torch.equal(wide[:, :227], flat) and torch.equal(flat, obs.cpu())
     assert (wide[:, 227:] == -7.0).all()  # the padding is never written
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('robot,scene', [('mini_cheetah', 'flat'), ('go2', 'random_boxes'), ('aliengo', 'perlin'), ('hyqreal1', 'flat'),
+                                         ('mini_cheetah', 'random_boxes'), ('go1', 'stairs')])
+def test_non_finite_state_ends_the_episode(robot, scene, cuda_device):
+    """Safety net of the batch path (no counterpart in the env; the engine itself warns and resets its data on a bad state): an env
+    whose state became non-finite reports terminated = 1 with status bit0, the auto-reset pass brings it back to a finite state in
+    the same launch, and no other env of the batch is affected (compared bit for bit with an untouched twin)."""
+    n = 256
+    m = Model(robot, scene)
+    kw = dict(device=cuda_device, seed=11, use_imu=bool(m.c.has_imu), heightmap=(3, 3, 0.1, 0.1) if scene == 'perlin' else None)
+    a = BatchSim(m, n, **kw)
+    b = BatchSim(m, n, **kw)
+    opt = a.make_reset_options(lin_vel_range=(0.5, 1.0), friction_range=(0.2, 1.5))
+    for s in (a, b):
+        s.reset(options=opt)
+        if scene != 'flat':  # bring the robots onto the terrain patch
+            q = s.qpos.clone(); q[:, 0] = 2.0; q[:, 1] = -1.0 if scene == 'random_boxes' else 2.0; q[:, 2] = 0.9
+            s.set_state(q, s.qvel)
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    ctrl = torch.randn(40, n, 12, device=cuda_device, generator=g) * 20
+    for t in range(20):
+        a.step_autoreset(ctrl[t], opt); b.step_autoreset(ctrl[t], opt)
+    bad = torch.tensor([3, 77, 200], device=cuda_device)
+    a.qvel[bad[0], 7] = float('nan'); a.qvel[bad[1], 2] = float('inf'); a.qpos[bad[2], 9] = float('nan')
+    # plain step: flags only, the state stays what the dynamics made of it
+    c = BatchSim(m, n, **kw)
+    c.reset(options=opt)
+    c.set_state(a.qpos.clone(), a.qvel.clone())
+    c.step(ctrl[20])
+    torch.cuda.synchronize()
+    assert c.terminated[bad].all() and (c.status[bad] & 1).all()
+    # auto-reset: same flags, finite state afterwards, every other env identical to the twin
+    a.step_autoreset(ctrl[20], opt); b.step_autoreset(ctrl[20], opt)
+    torch.cuda.synchronize()
+    assert a.terminated[bad].all()
+    assert torch.isfinite(a.qpos).all() and torch.isfinite(a.qvel).all() and torch.isfinite(a.obs).all()
+    others = torch.ones(n, dtype=torch.bool, device=cuda_device); others[bad] = False
+    for name in ('qpos', 'qvel', 'qacc', 'obs', 'terminated'):
+        assert torch.equal(getattr(a, name)[others], getattr(b, name)[others]), name
+    for t in range(21, 40):
+        a.step_autoreset(ctrl[t], opt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a.qpos).all() and torch.isfinite(a.qvel).all() and (a.status & 1).sum() == 0
