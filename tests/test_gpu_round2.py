@@ -61,7 +61,8 @@ def test_specialised_variant_equals_generic(robot, scene, imu, hm, variant, cuda
 
 
 @pytest.mark.parametrize('robot,scene,n,ring', [('mini_cheetah', 'flat', 4096, 0), ('mini_cheetah', 'flat', 100, 0), ('go2', 'random_boxes', 1500, 0),
-                                                ('mini_cheetah', 'flat', 4096, 2), ('go2', 'random_boxes', 4096, 2), ('go2', 'random_boxes', 4096, 3)])
+                                                ('mini_cheetah', 'flat', 4096, 2), ('go2', 'random_boxes', 4096, 2), ('go2', 'random_boxes', 4096, 3),
+                                                ('mini_cheetah', 'flat', 40000, 0), ('hyqreal1', 'flat', 20000, 2)])  # ten waves of CTAs per launch
 def test_pipelined_launches_equal_serialized(robot, scene, n, ring, cuda_device, monkeypatch):
     """QsConfig.pipeline: consecutive step launches overlap on the device (programmatic dependent launch; every env waits only for
     its own previous step through the finish-order queues).  Results must not depend on it: K back-to-back launches with overlap
