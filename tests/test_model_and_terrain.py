@@ -116,3 +116,44 @@ def test_fromto_capsules_of_go1_reproduce_their_end_points():
             if np.allclose(np.r_[p1, p2], seg, atol=1e-12) and abs(g['size'][0] - rad) < 1e-15:
                 found += 1
     assert found == 20  # five segments on each of the four legs
+
+
+def test_self_contact_census_distance_routine():
+    """scripts/self_contact_census.py quantifies the robot-robot contacts the engine would generate (deviations): its
+    convex-distance routine (Gilbert's iteration on support functions) against closed forms, on geoms of a compiled robot."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location('census', Path(__file__).resolve().parents[1] / 'scripts' / 'self_contact_census.py')
+    census = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ['census']
+    try:
+        spec.loader.exec_module(census)
+    finally:
+        sys.argv = argv
+    from gym_quadruped_b200.model import Model
+
+    m = Model('go2', 'flat')
+    G = census.Geoms(m)
+    q = np.array(m.c.key_qpos, dtype=float)
+    G.place(q)
+    c = m.c
+    spheres = [g for g in range(c.ngeom) if c.geom_type[g] == 2]
+    boxes = [g for g in range(c.ngeom) if c.geom_type[g] == 6]
+    assert len(spheres) >= 4 and boxes
+    # sphere - sphere: |c1 - c2| - r1 - r2
+    a, b = spheres[1], spheres[2]
+    want = np.linalg.norm(G.p[a] - G.p[b]) - c.geom_size[a][0] - c.geom_size[b][0]
+    assert abs(G.distance(a, b, iters=200, tol=1e-9) - want) < 1e-4
+    # sphere - box: closed form in the box frame
+    a, b = spheres[1], boxes[0]
+    loc = G.R[b].T @ (G.p[a] - G.p[b])
+    half = np.array(c.geom_size[b][:3])
+    want = np.linalg.norm(np.maximum(np.abs(loc) - half, 0.0)) - c.geom_size[a][0]
+    assert want > 0 and abs(G.distance(a, b, iters=400, tol=1e-10) - want) < 1e-4
+    # overlapping geoms report (almost) zero; the same geom pair list as the engine's filter: no parent-child, no same-body pairs
+    assert G.distance(boxes[0], boxes[0]) == 0.0
+    for a, b in G.pairs:
+        ba, bb = c.geom_body[a], c.geom_body[b]
+        assert ba != bb and c.body_parent[ba] != bb and c.body_parent[bb] != ba
