@@ -26,6 +26,7 @@
 namespace qs {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
+constexpr int QS_SLOT_ENV_BITS = 20, QS_SLOT_GEN_MASK = 0x7ff;  // queue slot = (generation << 20) | env id; see KParams
 constexpr int QS_QUEUE_DEPTH = 8;  // allocated ring entries; QSTEP_RING_DEPTH (2..8, read by qs_create) uses fewer (tests)
 constexpr int NCON_MAX = 16;
 constexpr int AUX_STRIDE = 324 + 18 + 18 + 216 + 12 + 3 + QS_CONTACT_STRIDE * NCON_MAX + 18 + 18 + 39 + 6 + 3 * 216;  // 1640
@@ -63,6 +64,12 @@ struct KParams {
   unsigned q_tail_base;    // its value before this launch's first publish
   int q_contiguous;        // 1: CTA c takes slots [c*W, c*W + W); 0: slot = warp * gridDim + c
   int q_sync;              // 1: launches of this handle may overlap -> acquire / release on the queue slots; 0: the grid boundary orders everything
+  // Slot encoding.  A ring entry is read by the launches s, s + depth, s + 2 depth, ... and several of them can be resident at once
+  // (all but the oldest spinning on their slots), so a slot value carries the GENERATION of the read it is meant for:
+  //   filled:  (gen << 20) | env  (>= 0)          empty: -1 - gen of the read that consumed it  (< 0)
+  // gen = (number of earlier reads of this entry) mod 2048.  A consumer only takes a value of its own generation, a producer only
+  // overwrites the empty marker of the generation before its own.
+  int q_gen_in, q_gen_out;
   // Peer-to-peer observation gather fused into the step (north_star's one collective): with gather_world > 1
   // every warp also stores its finished observation row into the [world * N, D] tensor of EVERY rank (peer-mapped memory, NVLink),
   // and the warp that completes the launch raises this rank's flag on every peer.  `obs` then points into this rank's own tensor.
@@ -180,12 +187,14 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
       int e_ = 0;
       if (lane == 0) {
         if (p.q_sync) {
-          while ((e_ = ld_acquire(p.q_in + slot)) < 0) __nanosleep(200);
-          st_release(p.q_in + slot, -1);  // consumed: free for the launch that reuses this ring entry (QS_QUEUE_DEPTH launches later)
+          // only a value of this launch's generation: a later launch that reads the same ring entry may already be spinning here too
+          while ((e_ = ld_acquire(p.q_in + slot)) < 0 || (e_ >> QS_SLOT_ENV_BITS) != p.q_gen_in) __nanosleep(200);
+          st_release(p.q_in + slot, -1 - p.q_gen_in);  // consumed: free for the producer of the next generation
         } else {
           e_ = p.q_in[slot];  // plain stream order: the previous launch has completed, every slot is filled
-          p.q_in[slot] = -1;
+          p.q_in[slot] = -1 - p.q_gen_in;
         }
+        e_ &= (1 << QS_SLOT_ENV_BITS) - 1;
       }
       env = __shfl_sync(0xffffffffu, e_, 0);
     }
@@ -701,11 +710,14 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         } while (int(t_ - p.q_tail_base) < 0);
       }
       const unsigned pos = atomicAdd(p.q_tail, 1u) - p.q_tail_base;
+      const int filled = (p.q_gen_out << QS_SLOT_ENV_BITS) | env;
       if (p.q_sync) {
-        while (ld_acquire(p.q_out + pos) >= 0) __nanosleep(200);  // the consumer of this ring entry's previous use is far behind: wait
-        st_release(p.q_out + pos, env);
+        // wait for the consumer of this slot's previous generation (far behind, or not even served yet by its own producer)
+        const int want = -1 - ((p.q_gen_out - 1) & QS_SLOT_GEN_MASK);
+        while (ld_acquire(p.q_out + pos) != want) __nanosleep(200);
+        st_release(p.q_out + pos, filled);
       } else {
-        p.q_out[pos] = env;
+        p.q_out[pos] = filled;
       }
       if (p.gather_world > 1 && pos == unsigned(p.num_envs) - 1u) {
         // last env of the launch: every other warp fenced before its increment, so all rows of this rank are on their way before

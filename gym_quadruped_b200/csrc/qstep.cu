@@ -68,13 +68,13 @@ __global__ void gather_wait_kernel(const unsigned* flags, int world, unsigned se
   }
 }
 
-__global__ void queue_init_kernel(int* q, unsigned* tails, int n) {
+__global__ void queue_init_kernel(int* q, unsigned* tails, int n, unsigned tail0, int gen0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    q[i] = i;  // ring entry 0: identity placement for the first launch
-    for (int r = 1; r < QS_QUEUE_DEPTH; r++) q[size_t(r) * n + i] = -1;
+    q[i] = (gen0 << QS_SLOT_ENV_BITS) | i;  // ring entry 0: identity placement for the first launch (generation gen0)
+    for (int r = 1; r < QS_QUEUE_DEPTH; r++) q[size_t(r) * n + i] = -1 - ((gen0 - 1) & QS_SLOT_GEN_MASK);  // empty, first read is generation gen0
   }
-  if (i < QS_QUEUE_DEPTH) tails[i] = 0;
+  if (i < QS_QUEUE_DEPTH) tails[i] = tail0;
 }
 
 }  // namespace
@@ -201,10 +201,17 @@ int qs_max_contacts(QsHandle*) { return NCON_MAX; }
 int qs_debug_set_prof(QsHandle* h, unsigned* prof) { h->prof = prof; return 0; }  // diagnostic builds only (scripts/warp_timeline.py)
 #endif
 int64_t qs_launch_count(QsHandle* h) { return h ? h->launches : 0; }
+// diagnostics (scripts/ring_probe.py): device addresses of the finish-order queue ring and its publish counters, ring depth, launch count
+int qs_debug_queue(QsHandle* h, void** queue, void** tails, int* depth, uint64_t* step_seq) {
+  if (!h) return 1;
+  *queue = h->d_queue; *tails = h->d_queue_tail; *depth = h->ring_depth; *step_seq = h->step_seq;
+  return 0;
+}
 
 int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
   if (!model || !cfg || !out) return fail(nullptr, 1, "null argument");
   if (cfg->num_envs <= 0) return fail(nullptr, 1, "num_envs must be positive");
+  if (cfg->num_envs >= (1 << QS_SLOT_ENV_BITS)) return fail(nullptr, 1, "num_envs must be below 1048576 per handle");
   if (cfg->hm_rows < 0 || cfg->hm_cols < 0 || cfg->hm_rows * cfg->hm_cols > 1024) return fail(nullptr, 1, "height-map grid out of range");
   QsHandle* h = new (std::nothrow) QsHandle_();
   if (!h) return fail(nullptr, 1, "out of host memory");
@@ -227,7 +234,11 @@ int qs_create(const QsModel* model, const QsConfig* cfg, QsHandle** out) {
     else {
       h->d_episode = ctr; h->d_tick = ctr + n; h->d_cmd_epoch = ctr + 2 * n; h->d_ext_epoch = ctr + 3 * n;
       cudaMemset(ctr, 0, 4 * n * sizeof(unsigned));
-      queue_init_kernel<<<unsigned((n + 255) / 256), 256>>>(h->d_queue, h->d_queue_tail, int(n));
+      // QSTEP_SEQ_START: pretend that many step launches have already happened (rounded down to a multiple of the ring depth), so
+      // that tests reach the 32-bit wrap of the publish counters (4096 envs: every 8.4 M launches) within a few steps
+      if (const char* ev = getenv("QSTEP_SEQ_START")) h->step_seq = strtoull(ev, nullptr, 10) / uint64_t(h->ring_depth) * uint64_t(h->ring_depth);
+      const uint64_t g0 = h->step_seq / uint64_t(h->ring_depth);
+      queue_init_kernel<<<unsigned((n + 255) / 256), 256>>>(h->d_queue, h->d_queue_tail, int(n), unsigned(g0 * n), int(g0 & QS_SLOT_GEN_MASK));
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(h, 5, "queue initialisation failed");
     }
   }
@@ -406,6 +417,7 @@ static int step_impl(QsHandle* h, const float* ctrl, float* obs, float* reward, 
     const int in = int(s % D), out = int((s + 1) % D);
     p.q_in = h->d_queue + size_t(in) * n; p.q_out = h->d_queue + size_t(out) * n;
     p.q_tail = h->d_queue_tail + out;
+    p.q_gen_in = int((s / D) & QS_SLOT_GEN_MASK); p.q_gen_out = int(((s + 1) / D) & QS_SLOT_GEN_MASK);
     p.q_tail_base = unsigned((s / D) * n);  // launches s - DEPTH, s - 2 DEPTH, ... filled this ring entry before: n envs each
     p.q_contiguous = (h->cfg.pipeline || kmode) ? 1 : 0;
     if (const char* ev = getenv("QSTEP_QMAP")) p.q_contiguous = atoi(ev);  // placement experiments: 0 balanced, 1 finish-order groups

@@ -60,10 +60,14 @@ def test_specialised_variant_equals_generic(robot, scene, imu, hm, variant, cuda
     assert n_term > 0
 
 
-@pytest.mark.parametrize('robot,scene,n,ring', [('mini_cheetah', 'flat', 4096, 0), ('mini_cheetah', 'flat', 100, 0), ('go2', 'random_boxes', 1500, 0),
-                                                ('mini_cheetah', 'flat', 4096, 2), ('go2', 'random_boxes', 4096, 2), ('go2', 'random_boxes', 4096, 3),
-                                                ('mini_cheetah', 'flat', 40000, 0), ('hyqreal1', 'flat', 20000, 2)])  # ten waves of CTAs per launch
-def test_pipelined_launches_equal_serialized(robot, scene, n, ring, cuda_device, monkeypatch):
+@pytest.mark.parametrize('robot,scene,n,ring,wrap', [
+    ('mini_cheetah', 'flat', 4096, 0, False), ('mini_cheetah', 'flat', 100, 0, False), ('go2', 'random_boxes', 1500, 0, False),
+    ('mini_cheetah', 'flat', 4096, 2, False), ('go2', 'random_boxes', 4096, 2, False), ('go2', 'random_boxes', 4096, 3, False),
+    ('mini_cheetah', 'flat', 40000, 0, False), ('hyqreal1', 'flat', 20000, 2, False),  # ten waves of CTAs per launch
+    ('mini_cheetah', 'flat', 4096, 0, True), ('go2', 'random_boxes', 1500, 3, True),  # publish counters cross 2^32 during the rollout
+    # small batches: many launches are resident at once (a launch is 16 / 6 CTAs), several of them spinning on the same ring entry
+    ('go2', 'random_boxes', 300, 0, False), ('go2', 'random_boxes', 100, 2, False), ('aliengo', 'perlin', 60, 3, True)])
+def test_pipelined_launches_equal_serialized(robot, scene, n, ring, wrap, cuda_device, monkeypatch):
     """QsConfig.pipeline: consecutive step launches overlap on the device (programmatic dependent launch; every env waits only for
     its own previous step through the finish-order queues).  Results must not depend on it: K back-to-back launches with overlap
     == the same K launches in plain stream order, for the state, the per-step flags and the observation of the last step; also
@@ -71,9 +75,16 @@ def test_pipelined_launches_equal_serialized(robot, scene, n, ring, cuda_device,
 
     `ring` > 0 shortens the queue ring (QSTEP_RING_DEPTH, read by qs_create): fast envs then catch up with the ring entry a
     straggler (an env whose reset lifts the robot out of a box, up to 100 times) has not published to yet -- they have to wait for
-    the entry's publish counter to reach their launch's base instead of taking a position relative to the older launch."""
+    the entry's publish counter to reach their launch's base instead of taking a position relative to the older launch; and the
+    launches s, s + ring, ... that read the same ring entry can be resident together, so a queue slot carries the generation of the
+    read it is meant for (without the tag a later launch took an env published for an earlier one: a hang with ring 3 / 1500 envs)."""
     if ring:
         monkeypatch.setenv('QSTEP_RING_DEPTH', str(ring))
+    if wrap:
+        # `wrap`: start the handle's launch sequence just below the point where the 32-bit publish counters (n per use of a ring entry)
+        # wrap -- with 4096 envs that point comes every 8.4 M launches, ten minutes into a pipelined rollout
+        depth = ring or 8
+        monkeypatch.setenv('QSTEP_SEQ_START', str(depth * ((1 << 32) // n - 3)))
     m = Model(robot, scene)
     a = BatchSim(m, n, device=cuda_device, seed=7, pipeline=True)
     b = BatchSim(m, n, device=cuda_device, seed=7, pipeline=False)
