@@ -666,3 +666,87 @@ def test_non_finite_state_ends_the_episode(robot, scene, cuda_device):
         a.step_autoreset(ctrl[t], opt)
     torch.cuda.synchronize()
     assert torch.isfinite(a.qpos).all() and torch.isfinite(a.qvel).all() and (a.status & 1).sum() == 0
+
+
+@pytest.mark.parametrize('robot,scene,n,ring,seed', [('mini_cheetah', 'flat', 333, 0, 0), ('go2', 'random_boxes', 200, 3, 1), ('aliengo', 'perlin', 500, 2, 2),
+                                                     ('hyqreal1', 'flat', 1000, 0, 3)])
+def test_random_api_sequences_pipelined_equals_serialized(robot, scene, n, ring, seed, cuda_device, monkeypatch):
+    """Differential fuzz of the launch-chain logic: a seeded random sequence of C-ABI calls (plain steps, auto-reset steps, K-step
+    calls, host-buffer steps, masked resets, reset_done, state writes, forward / get, schedule and seed changes, host reads) is applied
+    to a pipelined handle and to a serialized twin; every caller-visible buffer must be bit-identical afterwards, and at random
+    check points in between.  Overlapped launches, chain breaks and resumptions must never change a result."""
+    if ring:
+        monkeypatch.setenv('QSTEP_RING_DEPTH', str(ring))
+    from gym_quadruped_b200.backend import FIELD_MASS_MATRIX as FIELD_M
+    m = Model(robot, scene)
+    kw = dict(device=cuda_device, seed=21, use_imu=bool(m.c.has_imu), heightmap=(3, 3, 0.1, 0.1) if scene == 'perlin' else None)
+    sims = [BatchSim(m, n, pipeline=True, **kw), BatchSim(m, n, pipeline=False, **kw)]
+    opt = sims[0].make_reset_options(lin_vel_range=(0.5, 1.0), friction_range=(0.2, 1.5), command_mode=CMD_FORWARD | CMD_ROTATE | CMD_RESET)
+    for s in sims:
+        s.set_schedule(command_mode=CMD_FORWARD | CMD_ROTATE | CMD_RESET, lin_vel_range=(0.3, 0.9), ang_vel_range=(-0.4, 0.4), ext_enabled=True,
+                       ext_ranges={'x': (-20, 20), 'z': (5,)})
+        s.reset(options=opt)
+        s.cmd_limit[:] = 7; s.ext_limit[:] = 5
+    rng = np.random.RandomState(seed)
+    g = torch.Generator(device=cuda_device).manual_seed(seed)
+    D = sims[0].obs_dim
+    pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
+    host = [dict(ctrl=pin(n, 12), obs=pin(n, (D + 31) // 32 * 32)[:, :D], rew=pin(n), term=pin(n, dtype=torch.uint8), trunc=pin(n, dtype=torch.uint8)) for _ in sims]
+    names = ('obs', 'qpos', 'qvel', 'qacc', 'qacc_warmstart', 'terminated', 'base_pos64', 'command', 'friction', 'step_count', 'sim_time', 'status',
+             'cmd_count', 'ext_count', 'ext_wrench', 'qfrc_applied', 'imu_bias', 'ncon', 'solver_iter')
+
+    def same(where):
+        torch.cuda.synchronize()
+        for name in names:
+            assert torch.equal(getattr(sims[0], name), getattr(sims[1], name)), f'{name} differs after {where}'
+
+    ops = ['step'] * 3 + ['auto'] * 12 + ['stepk'] * 2 + ['host', 'reset_mask', 'reset_done', 'set_state', 'forward', 'seed', 'schedule', 'read', 'check']
+    pool = torch.randn(1200, n, 12, device=cuda_device, generator=g) * 40  # actions made up front: no foreign kernel between two step launches
+    cur = 0
+    torch.cuda.synchronize()
+    for it in range(200):
+        op = ops[rng.randint(len(ops))]
+        if op in ('step', 'auto', 'host'):
+            ctrl = pool[cur]; cur += 1
+        if op == 'step':
+            for s in sims: s.step(ctrl)
+        elif op == 'auto':
+            for s in sims: s.step_autoreset(ctrl, opt)
+        elif op == 'stepk':
+            K = int(rng.randint(2, 7))
+            cs = pool[cur:cur + K]; cur += K
+            rings = [torch.empty(K, n, D, device=cuda_device) for _ in sims]
+            auto_k = bool(rng.randint(2))
+            terms = [s.step_k(cs, opt, auto_reset=auto_k, obs_ring=r)[1] for s, r in zip(sims, rings)]
+            torch.cuda.synchronize()
+            assert torch.equal(rings[0], rings[1]) and torch.equal(terms[0], terms[1]), 'step_k rings differ'
+        elif op == 'host':
+            for s, h in zip(sims, host):
+                h['ctrl'].copy_(ctrl)
+                s.step_host(h['ctrl'], h['obs'], h['rew'], h['term'], h['trunc'], auto_reset=opt)
+            assert torch.equal(host[0]['obs'], host[1]['obs']) and torch.equal(host[0]['term'], host[1]['term'])
+        elif op == 'reset_mask':
+            mask = (torch.rand(n, device=cuda_device, generator=g) < 0.1).to(torch.uint8)
+            for s in sims: s.reset(mask=mask, options=opt)
+        elif op == 'reset_done':
+            for s in sims: s.reset_done(opt)
+        elif op == 'set_state':
+            ids = torch.randperm(n, device=cuda_device, generator=g)[:5]
+            src = torch.randperm(n, device=cuda_device, generator=g)[:5]
+            q = sims[1].qpos[src].clone(); q[:, :3] = sims[1].base_pos64[src].float(); v = sims[1].qvel[src].clone() * 0.5
+            for s in sims: s.set_state(q, v, env_ids=ids)
+        elif op == 'forward':
+            for s in sims: s.forward()
+            assert torch.equal(sims[0].get(FIELD_M), sims[1].get(FIELD_M))
+        elif op == 'seed':
+            sd = int(rng.randint(1 << 30))
+            for s in sims: s.set_seed(sd)
+        elif op == 'schedule':
+            lim = int(rng.randint(2, 9))
+            for s in sims: s.cmd_limit[:] = lim
+        elif op == 'read':
+            assert torch.equal(sims[0].terminated.cpu(), sims[1].terminated.cpu())  # a host read between launches
+        else:
+            same(f'op {it}')
+    same('the whole sequence')
+    assert torch.isfinite(sims[0].qpos).all()
