@@ -13,7 +13,7 @@
 // the engine behind the reference's `mujoco` dependency, not part of the reference checkout) whose published algorithm a phase
 // restates.  No MuJoCo source was copied.
 //
-// This header is compiled by nvcc for sm_100a (qstep.cu) and, unchanged, by g++ against a 32-thread warp emulator
+// This header is compiled by nvcc for sm_100a (qstep.cu) and, unchanged, by g++ against a 32-lane warp emulator (lock-step fibers)
 // (tests/emu) so the exact kernel source can be checked against the fp64 oracle on a CPU-only host.
 #pragma once
 #include "qs_math.cuh"

@@ -1,9 +1,8 @@
 // emu_main.cpp -- TEST INFRASTRUCTURE. Host build of the fused-step device code (see warp_emu.h).
-// Exposes one C entry point that advances a single environment by one step with 32 host threads acting as the warp.
+// Exposes one C entry point that advances a single environment by one step with 32 fibers acting as the warp.
 #include "warp_emu.h"
 
 #include <memory>
-#include <thread>
 #include <vector>
 
 #include "../../gym_quadruped_b200/csrc/qs_host_model.h"
@@ -39,11 +38,8 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
   unsigned cmask = 0, imask = 0;
   static float hm_out[75];
   bool oob = false;
-  std::vector<std::thread> th;
-  for (int lane = 0; lane < 32; lane++) {
-    th.emplace_back([&, lane]() {
-      g_ctx = &ctx;
-      g_lane = lane;
+  {
+    ctx.run([&](int lane) {
       Env<real, NCON, MAXDIM, FEAT> e(*dm, *ws, verts.data(), lane);
       e.bias_out = bias_buf.data();
       e.hf = hfv.data(); e.boxes = boxes.data();
@@ -63,7 +59,6 @@ int run_step(const QsModel* model, double* qpos, double* qvel, double* warm, con
       if (lane == 0) { iters = e.solver_iter; maxed = e.solver_maxed; cmask = f.contact_mask; imask = f.invalid_mask; oob = f.out_of_bounds; }
     });
   }
-  for (auto& t : th) t.join();
   // results
   for (int i = 0; i < 19; i++) qpos[i] = double(ws->qpos[i]) + (i < 2 ? ws->org[i] : 0.0);
   if (mode == 1) for (int i = 0; i < 3; i++) qpos[i] = base64[i];

@@ -1,4 +1,4 @@
-"""CPU-only parity of the *kernel source*: gym_quadruped_b200/csrc/qs_env.cuh compiled for the host against a 32-thread warp
+"""CPU-only parity of the *kernel source*: gym_quadruped_b200/csrc/qs_env.cuh compiled for the host against a 32-lane (fiber) warp
 emulator (tests/emu) versus the fp64 oracle.  The same comparison runs on the real GPU in tests/test_gpu_parity.py; this one
 lets `pytest -m "not gpu"` catch algorithmic regressions of the device code without a GPU."""
 import numpy as np
@@ -194,7 +194,7 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
         o.step(ctrl)
         f = o.flags()
         if f['ncon'] == 0 or k % 3:
-            continue  # emulate only every third contact step (32 host threads per emulated step are slow)
+            continue  # emulate only every third contact step (emulated steps are slow)
         e = emu_step(m, q0, v0, w0, ctrl, 0.8, 0.8, [0, 0, 0, 0], precision=1, mode=1)
         steps += 1
         if f['ncon'] > 16:
