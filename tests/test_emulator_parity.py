@@ -193,8 +193,8 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
         ctrl = np.zeros(12)
         o.step(ctrl)
         f = o.flags()
-        if f['ncon'] == 0 or k % 3:
-            continue  # emulate only every third contact step (emulated steps are slow)
+        if f['ncon'] == 0:
+            continue  # free fall: nothing to compare yet
         e = emu_step(m, q0, v0, w0, ctrl, 0.8, 0.8, [0, 0, 0, 0], precision=1, mode=1)
         steps += 1
         if f['ncon'] > 16:
@@ -214,7 +214,7 @@ def test_mesh_links_collide_with_the_terrain(robot, scene, xy):
         np.testing.assert_allclose(ec[:, 0:13], oc[:, 0:13], atol=1e-9)
         on_terrain = np.abs(oc[:, 3]) > 1e-3 if scene == 'random_boxes' else np.ones(len(oc), dtype=bool)  # contact point above the floor plane
         mesh_terrain_contacts += int((mesh[oc[:, 16].astype(int)] & on_terrain & (oc[:, 3] - 0.5 * oc[:, 0] > 0.01)).sum())
-        if steps >= 45:
+        if steps >= 100:
             break
     assert mesh_terrain_contacts >= 5 and worst < 1e-8, (mesh_terrain_contacts, worst)
 
