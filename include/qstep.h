@@ -344,6 +344,16 @@ int qs_gather_close(QsHandle* h);
 /* number of kernels this library has launched since create (bench.py "gpu_launches") */
 int64_t qs_launch_count(QsHandle* h);
 
+/* Diagnostics (scripts/ring_probe.py): device addresses of the finish-order queue ring ([8][num_envs] int32, see QsConfig.pipeline)
+ * and of its publish counters ([8] uint32), the ring depth in use and the number of step launches issued so far.
+ * Environment knobs read by the library, all for tests / experiments, none needed in production:
+ *   QSTEP_GENERIC=1        run the generic (run-time dispatch) step kernel instead of the specialised variant
+ *   QSTEP_RING_DEPTH=2..8  use fewer entries of the queue ring (read by qs_create)
+ *   QSTEP_SEQ_START=<n>    start the launch sequence number at n (read by qs_create; reaches the 32-bit counter wrap quickly)
+ *   QSTEP_QMAP=0|1         slot placement: 0 balanced over the CTAs, 1 finish-order groups
+ *   QS_WARPS_PER_CTA=<n>   cap the warps per CTA (occupancy experiments) */
+int qs_debug_queue(QsHandle* h, void** dev_queue, void** dev_publish_counters, int* ring_depth, uint64_t* step_launches);
+
 #ifdef __cplusplus
 }
 #endif
