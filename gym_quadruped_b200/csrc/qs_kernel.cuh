@@ -11,7 +11,11 @@
 // Kernels are instantiated in the qs_inst_*.cu translation units (compiled in parallel) and reach the host code of qstep.cu
 // through the VariantInfo table declared at the bottom.
 #pragma once
+// QS_HOST_EMU: the same kernel body compiled by g++ for the host warp emulator (tests/emu/kernel_emu.h supplies threadIdx / blockIdx,
+// the warp primitives and plain-memory stand-ins for TMA, mbarrier and the acquire / release accesses) -- test infrastructure only.
+#ifndef QS_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 #include <cstddef>
 #include <cstdint>
@@ -103,6 +107,7 @@ struct KParams {
 #define QS_MARK(k) do { } while (0)
 #endif
 
+#ifndef QS_HOST_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // one TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS)
@@ -128,6 +133,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
         : "memory");
   }
 }
+#else
+inline void tma_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) { std::memcpy(dst_smem, src_gmem, bytes); }
+inline void mbar_init(uint64_t*, uint32_t) {}
+inline void mbar_wait(uint64_t*, uint32_t) {}
+#endif
 
 template <typename real> __device__ __forceinline__ void euler_to_quat(real roll, real pitch, real yaw, real* q) {
   real sr, cr, sp, cp, sy, cy;
@@ -143,15 +153,30 @@ template <typename real> struct LaunchCfg { static constexpr int kMaxWarps = 28;
 template <> struct LaunchCfg<double> { static constexpr int kMaxWarps = 8; };
 
 // acquire / release accesses to the finish-order queues (system scope is not needed: producer and consumer are on one GPU)
+#ifndef QS_HOST_EMU
 __device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int lane_id() { int v; asm volatile("mov.u32 %0, %%laneid;" : "=r"(v)); return v; }
+__device__ __forceinline__ void launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define QS_SMEM_DECL extern __shared__ __align__(128) unsigned char smem[]
+#else
+inline int ld_acquire(const int* p) { return *p; }
+inline void st_release(int* p, int v) { *p = v; }
+inline unsigned ld_relaxed(const unsigned* p) { return *p; }
+inline void st_release_sys(unsigned* p, unsigned v) { *p = v; }
+inline int lane_id() { return g_lane; }
+inline void launch_dependents() {}
+#define QS_SMEM_DECL unsigned char* smem = g_smem
+#endif
 
 template <typename real, int NCON, int MAXDIM, int MODE, int FEAT>
 __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(const KParams p) {
   using W = WS<real, NCON, MAXDIM>;
   using EnvT = Env<real, NCON, MAXDIM, FEAT>;
   using DM = DModel<real>;
-  extern __shared__ __align__(128) unsigned char smem[];
+  QS_SMEM_DECL;
   constexpr size_t DM_BYTES = (sizeof(DM) + 127) & ~size_t(127);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + DM_BYTES);
   W* wsbase = reinterpret_cast<W*>(smem + DM_BYTES + 128);
@@ -160,9 +185,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
   // the lane id is read once through an opaque asm: left to itself the compiler re-materialises `threadIdx.x & 31` with an S2R (a
   // ~25-cycle special-register read) at ~65 places per env-step to save one register
-  int lane_reg;
-  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_reg));
-  const int lane = lane_reg;
+  const int lane = lane_id();
   // The model sits at offset 0 of the dynamic shared memory.  Its base is tied to the (shuffle-produced, hence opaque) warp index so
   // that it lives in a register like the workspace base: otherwise every indexed access to a model table re-derives the shared
   // window base from the CgaCtaId special register (~50 S2R per env-step on address-critical paths).  warp < 32, so the term is 0.
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
     // The next step launch may be scheduled as soon as every CTA of this one is resident (or done): whatever env one of its warps
     // waits for is then held by a running warp, so the waits below always end.  Without the pipeline attribute on the next launch
     // this is a no-op.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    launch_dependents();
     // take this warp's env from the finish-order queue filled by the previous step launch (results do not depend on the
     // placement)
     const int slot = p.q_contiguous ? blockIdx.x * nwarp + warp : warp * int(gridDim.x) + int(blockIdx.x);
@@ -705,7 +728,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         // launches behind (a reset that lifts the robot 100 times) ever makes a fast env wait here.
         unsigned t_;
         do {
-          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(t_) : "l"(p.q_tail) : "memory");
+          t_ = ld_relaxed(p.q_tail);
           if (int(t_ - p.q_tail_base) < 0) __nanosleep(200);
         } while (int(t_ - p.q_tail_base) < 0);
       }
@@ -724,7 +747,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
         // the flag; release at system scope, the peers' wait kernel acquires it
         __threadfence_system();
         for (int q = 0; q < p.gather_world; q++)
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.gather_flags[q] + p.gather_rank), "r"(p.gather_seq) : "memory");
+          st_release_sys(p.gather_flags[q] + p.gather_rank, p.gather_seq);
       }
     }
   }
@@ -733,6 +756,7 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
 #endif
 }
 
+#ifndef QS_HOST_EMU
 // HeightMap.update_height_map for every env (sensors/heightmap.py:106-169): one warp per env, rays spread over the lanes
 template <typename real>
 __global__ void __launch_bounds__(256) raycast_kernel(const KParams p) {
@@ -780,5 +804,7 @@ template <typename real, int MAXDIM, int FEAT, bool ALL_MODES> VariantInfo make_
   v.max_warps = LaunchCfg<real>::kMaxWarps;
   return v;
 }
+
+#endif  // QS_HOST_EMU
 
 }  // namespace qs
