@@ -108,6 +108,7 @@ class EmuSim:
         self.obs = np.zeros((n, self.obs_dim), f32); self.reward = np.zeros(n, f32)
         self.terminated = np.zeros(n, np.uint8); self.truncated = np.zeros(n, np.uint8)
         self.sched = QsSchedule()
+        self.imu_noise = (0.0, 0.0, 0.0, 0.0)  # accel noise, gyro noise, accel bias rate, gyro bias rate (QsConfig.imu_*)
         q = np.array(model.c.qpos0, dtype=np.float64)
         self.qpos[:] = q.astype(f32); self.base_pos64[:] = q[:3]
         self.aux = None
@@ -123,6 +124,7 @@ class EmuSim:
         L.max_iter, L.env_id_offset, L.auto_reset = self.max_iter, self.env_id_offset, int(auto_reset is not None)
         L.tol = 1e-6 if self.precision == 0 else 1e-8
         L.seed = self.seed
+        L.imu_an, L.imu_gn, L.imu_abr, L.imu_gbr = self.imu_noise
         for name, _ in QsBuffers._fields_:
             setattr(L.buf, name, getattr(self, name).ctypes.data)
         for name in ('episode', 'tick', 'cmd_epoch', 'ext_epoch', 'obs', 'reward', 'terminated', 'truncated'):

@@ -244,3 +244,42 @@ def test_kernel_non_finite_state_terminates_and_autoreset_recovers():
     b.step_autoreset(np.zeros((n, 12), F32), ro)
     assert b.terminated.tolist() == [0, 0, 1] and np.isfinite(b.qpos).all() and np.isfinite(b.qvel).all() and np.isfinite(b.obs).all()
     assert b.step_count.tolist() == [1, 1, 0]
+
+
+def test_kernel_imu_columns_reconstructed():
+    """sensors/imu.py:102-139 inside the kernel: reading = truth + bias + N(0, sigma), bias random walk; Box-Muller on Philox draws
+    keyed by (global env id, per-env step counter).  Truth signals against the oracle, noise and bias against the restatement."""
+    m = Model('hyqreal1', 'flat')
+    assert m.c.has_imu
+    n, seed, off = 2, 99, 7
+    s = EmuSim(m, n, precision=1, seed=seed, use_imu=True, env_id_offset=off)
+    s.imu_noise = (0.05, 0.01, 0.002, 0.0005)
+    q, v = standing(m, n, 4)
+    s.set_state(q, v)
+    s.tick[:] = [3, 10]
+    s.imu_bias[:] = 0.01
+    orcs = []
+    for i in range(n):
+        o = Oracle(m); o.set_state(s.qpos[i].astype(float), s.qvel[i].astype(float), np.zeros(18)); o.set_env(-1.0, -1.0, [0, 0, 0, 0]); orcs.append(o)
+    bias = s.imu_bias.copy()
+    for t in range(3):
+        ctrl = np.zeros((n, 12), F32)
+        s.step(ctrl)
+        for i, o in enumerate(orcs):
+            obs, _ = o.step(np.zeros(12))
+            truth = obs[227:233]
+            io = s.obs[i, 227:245]
+            for lane in range(3):
+                r = philox4x32(i + off, int([3, 10][i]) + t, lane, 0x1A2B, (seed & 0xffffffff) ^ 0x9E3779B9, seed >> 32)
+                u1, u2, u3, u4 = (max(float(u32_to_unit(r[0])), 5.9604645e-8), float(u32_to_unit(r[1])), max(float(u32_to_unit(r[2])), 5.9604645e-8), float(u32_to_unit(r[3])))
+                ra, rb = math.sqrt(-2 * math.log(u1)), math.sqrt(-2 * math.log(u3))
+                n_acc, n_ab = ra * math.cos(2 * math.pi * u2) * 0.05, ra * math.sin(2 * math.pi * u2) * 0.002
+                n_gyr, n_gb = rb * math.cos(2 * math.pi * u4) * 0.01, rb * math.sin(2 * math.pi * u4) * 0.0005
+                bias[i, lane] += n_ab; bias[i, 3 + lane] += n_gb
+                np.testing.assert_allclose([io[3 + lane], io[6 + lane], io[12 + lane], io[15 + lane]], [n_acc, bias[i, lane], n_gyr, bias[i, 3 + lane]], atol=2e-6)
+                np.testing.assert_allclose(io[lane], truth[lane] + bias[i, lane] + n_acc, atol=2e-3, rtol=1e-4)
+                np.testing.assert_allclose(io[9 + lane], truth[3 + lane] + bias[i, 3 + lane] + n_gyr, atol=1e-4)
+            qo, vo, _, _ = o.get_state()
+            o.set_state(np.r_[s.base_pos64[i], s.qpos[i, 3:].astype(float)], s.qvel[i].astype(float), s.qacc_warmstart[i].astype(float))
+    np.testing.assert_allclose(s.imu_bias, bias, atol=2e-6)
+    assert s.tick.tolist() == [6, 13]
