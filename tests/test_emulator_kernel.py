@@ -283,3 +283,20 @@ def test_kernel_imu_columns_reconstructed():
             o.set_state(np.r_[s.base_pos64[i], s.qpos[i, 3:].astype(float)], s.qvel[i].astype(float), s.qacc_warmstart[i].astype(float))
     np.testing.assert_allclose(s.imu_bias, bias, atol=2e-6)
     assert s.tick.tolist() == [6, 13]
+
+
+def test_kernel_heightmap_columns():
+    """sensors/heightmap.py:106-169 as extra observation columns: the grid is cast around the post-step base position / heading."""
+    m = Model('aliengo', 'perlin')
+    n = 2
+    s = EmuSim(m, n, precision=1, heightmap=(3, 4, 0.1, 0.15))
+    q, v = standing(m, n, 12)
+    q[:, 0] = [3.0, -2.5]; q[:, 1] = [2.0, 4.0]; q[:, 2] = 1.1
+    s.set_state(q, v)
+    s.step(np.zeros((n, 12), F32))
+    for i in range(n):
+        o = Oracle(m)
+        center = np.r_[s.base_pos64[i, :2], float(s.qpos[i, 2])]
+        hm = o.heightmap(center, float(s.obs[i, 20]), 3, 4, 0.1, 0.15)
+        np.testing.assert_allclose(s.obs[i, 227:].reshape(3, 4, 3), hm, atol=2e-5)
+    assert s.obs.shape[1] == 227 + 36 and np.ptp(s.obs[:, 227:].reshape(n, -1, 3)[:, :, 2]) > 1e-3
