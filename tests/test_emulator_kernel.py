@@ -300,3 +300,28 @@ def test_kernel_heightmap_columns():
         hm = o.heightmap(center, float(s.obs[i, 20]), 3, 4, 0.1, 0.15)
         np.testing.assert_allclose(s.obs[i, 227:].reshape(3, 4, 3), hm, atol=2e-5)
     assert s.obs.shape[1] == 227 + 36 and np.ptp(s.obs[:, 227:].reshape(n, -1, 3)[:, :, 2]) > 1e-3
+
+
+@pytest.mark.parametrize('robot', ['mini_cheetah', 'go2'])
+def test_kernel_forward_tables(robot):
+    """MODE_FORWARD (qs_forward + qs_get: mj_fullM, qfrc_bias, qfrc_passive, mj_jac, subtree_com users, quadruped_env.py:543-929): the
+    accessor tables the kernel dumps, against the oracle's."""
+    from oracle.oracle import F_BIAS, F_COM, F_FEET_JACP, F_FEET_POS, F_M, F_PASSIVE
+    m = Model(robot, 'flat')
+    n = 2
+    q, v = standing(m, n, 21)
+    s = EmuSim(m, n, precision=1)
+    s.set_state(q, v)
+    s.forward()
+    for i in range(n):
+        o = Oracle(m)
+        o.set_state(np.r_[s.base_pos64[i], s.qpos[i, 3:].astype(float)], s.qvel[i].astype(float), np.zeros(18))
+        o.set_env(-1.0, -1.0, [0, 0, 0, 0])
+        o.forward(np.zeros(12))
+        a = s.aux[i]
+        np.testing.assert_allclose(a[0:324].reshape(18, 18), o.get(F_M), atol=2e-5, rtol=1e-5)
+        np.testing.assert_allclose(a[324:342], o.get(F_BIAS)[:18], atol=2e-4, rtol=1e-5)
+        np.testing.assert_allclose(a[342:360], o.get(F_PASSIVE)[:18], atol=1e-5)
+        np.testing.assert_allclose(a[360:576].reshape(4, 3, 18), o.get(F_FEET_JACP), atol=1e-5)
+        np.testing.assert_allclose(a[576:588].reshape(4, 3), o.get(F_FEET_POS), atol=1e-5)
+        np.testing.assert_allclose(a[588:591], o.get(F_COM)[:3], atol=1e-5)
