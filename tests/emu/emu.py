@@ -68,6 +68,8 @@ class EmuLaunch(C.Structure):
         ('mask', C.c_void_p), ('in_qpos', C.c_void_p), ('in_qvel', C.c_void_p),
         ('ro', QsResetOptions),
         ('aux', C.c_void_p),
+        ('gather_world', C.c_int), ('gather_rank', C.c_int), ('gather_row_stride', C.c_int), ('gather_seq', C.c_int),
+        ('gather_peers', C.c_void_p * 8), ('gather_flags', C.c_void_p * 8),
     ]
 
 
@@ -112,6 +114,7 @@ class EmuSim:
         q = np.array(model.c.qpos0, dtype=np.float64)
         self.qpos[:] = q.astype(f32); self.base_pos64[:] = q[:3]
         self.aux = None
+        self.gather = None  # dict(world, rank, stride, seq, peers=[float32 arrays [world*N, stride]], flags=[uint32 arrays [8]])
 
     def set_state(self, qpos, qvel):
         qpos = np.asarray(qpos, dtype=np.float64).reshape(self.N, 19)
@@ -137,6 +140,12 @@ class EmuSim:
                 setattr(L, name, a.ctypes.data)
         if ro is not None or auto_reset is not None:
             L.ro = ro if ro is not None else auto_reset
+        if self.gather is not None and mode == 0:
+            g = self.gather
+            L.gather_world, L.gather_rank, L.gather_row_stride, L.gather_seq = g['world'], g['rank'], g['stride'], g['seq']
+            for k in range(g['world']):
+                L.gather_peers[k] = g['peers'][k].ctypes.data
+                L.gather_flags[k] = g['flags'][k].ctypes.data
         if mode == 2:
             stride = lib().emu_aux_stride()
             self.aux = np.zeros((self.N, stride), np.float32)

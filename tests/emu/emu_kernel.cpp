@@ -34,6 +34,10 @@ struct EmuLaunch {
   const float* in_qvel;
   QsResetOptions ro;
   float* aux;
+  // fused observation gather (qs_gather_*): `gather_world` host tensors stand in for the peer-mapped ones
+  int gather_world, gather_rank, gather_row_stride, gather_seq;
+  float* gather_peers[8];
+  unsigned* gather_flags[8];
 };
 int emu_launch_sizeof(void) { return int(sizeof(EmuLaunch)); }
 int emu_aux_stride(void) { return qs::AUX_STRIDE; }
@@ -66,6 +70,12 @@ int run_kernel(const QsModel* model, const EmuLaunch& L) {
   p.ctrl = L.ctrl; p.obs = L.obs; p.reward = L.reward; p.terminated = L.terminated; p.truncated = L.truncated;
   p.mask = L.mask; p.in_qpos = L.in_qpos; p.in_qvel = L.in_qvel; p.ro = L.ro; p.aux = L.aux;
   p.auto_reset = L.auto_reset;
+  if (L.gather_world > 1) {  // as in step_impl: own rows live in this rank's block of its own gathered tensor
+    p.gather_world = L.gather_world; p.gather_rank = L.gather_rank; p.gather_seq = unsigned(L.gather_seq);
+    for (int q = 0; q < L.gather_world; q++) { p.gather_peers[q] = L.gather_peers[q]; p.gather_flags[q] = L.gather_flags[q]; }
+    p.obs = p.gather_peers[L.gather_rank] + size_t(L.gather_rank) * n * L.gather_row_stride;
+    p.obs_stride = L.gather_row_stride;
+  }
   // finish-order queues in plain stream order: identity placement, generation 0
   std::vector<int> q_in(n), q_out(n, -1 - QS_SLOT_GEN_MASK);
   for (int i = 0; i < n; i++) q_in[i] = i;

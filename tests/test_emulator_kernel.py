@@ -325,3 +325,35 @@ def test_kernel_forward_tables(robot):
         np.testing.assert_allclose(a[360:576].reshape(4, 3, 18), o.get(F_FEET_JACP), atol=1e-5)
         np.testing.assert_allclose(a[576:588].reshape(4, 3), o.get(F_FEET_POS), atol=1e-5)
         np.testing.assert_allclose(a[588:591], o.get(F_COM)[:3], atol=1e-5)
+
+
+@pytest.mark.parametrize('stride', [256, 229])
+def test_kernel_gather_rows_and_flags(stride):
+    """The fused observation gather (qs_gather_*) on host stand-ins for the peer-mapped tensors: every env's row lands in
+    this rank's block of EVERY rank's gathered tensor (also for a row stride that leaves the rows off 16-byte boundaries: scalar
+    head / float4 body / scalar tail), an env that auto-resets sends its post-reset row, and the last env raises the flags."""
+    m = Model('mini_cheetah', 'flat')
+    n, world, rank = 4, 3, 1
+    q, v = standing(m, n, 31)
+    qf, vf = _fallen(m, n, 32)
+    q[2], v[2] = qf[2], vf[2]
+    ro = reset_options(m)
+    ref = EmuSim(m, n, precision=1, seed=4)
+    ref.set_state(q, v)
+    ctrl = (np.random.RandomState(1).randn(n, 12) * 5).astype(F32)
+    ref.step_autoreset(ctrl, ro)
+    assert ref.terminated[2] == 1 and (ref.terminated == 0).any()
+    s = EmuSim(m, n, precision=1, seed=4)
+    s.set_state(q, v)
+    peers = [np.full((world * n, stride), -7.0, F32) for _ in range(world)]
+    flags = [np.zeros(8, np.uint32) for _ in range(world)]
+    s.gather = dict(world=world, rank=rank, stride=stride, seq=5, peers=peers, flags=flags)
+    s.step_autoreset(ctrl, ro)
+    for k in range(world):
+        block = peers[k][rank * n:(rank + 1) * n]
+        assert np.array_equal(block[:, :227], ref.obs), f'rank {k}'
+        assert (block[:, 227:] == -7.0).all()                                        # padding untouched
+        others = np.delete(peers[k], np.s_[rank * n:(rank + 1) * n], axis=0)
+        assert (others == -7.0).all()                                                # nobody else's rows touched
+        assert flags[k].tolist() == [0, 5, 0, 0, 0, 0, 0, 0]
+    assert np.array_equal(s.qpos, ref.qpos) and np.array_equal(s.terminated, ref.terminated)
