@@ -56,7 +56,7 @@ struct KParams {
   unsigned* episode;  // per-env reset counter (keys the reset RNG)
   unsigned* tick;     // per-env step counter  (keys the IMU noise RNG)
   // Finish-order queues (MODE_STEP).  A step launch takes its envs from `q_in` (slot -> env id, filled by the previous step launch in
-  // the order in which its envs finished; -1 = not published yet) and publishes every env it completes to `q_out`.  Because a slot is
+  // the order in which its envs finished; negative = not published yet, see the slot encoding below) and publishes every env it completes to `q_out`.  Because a slot is
   // only handed out once the env behind it has finished its previous step, consecutive step launches may overlap on the device
   // (programmatic dependent launch, QsConfig.pipeline) without any grid-wide dependency: the tail of step t, set by its slowest env,
   // runs next to the head of step t+1.  Envs that finish together are also the ones of similar cost, so a CTA that takes 28
