@@ -127,7 +127,7 @@ class Oracle:
         return self.L.orc_lift(self.h)
 
     def get(self, field):
-        buf = np.zeros(65536)
+        buf = np.zeros(131072)
         n = self.L.orc_get(self.h, field, _p(buf))
         if field == F_EFC_FULL:
             return buf[:EFC_FULL_STRIDE * n].reshape(n, EFC_FULL_STRIDE).copy()

@@ -28,7 +28,7 @@
 #define NV QS_NV
 #define NQ QS_NQ
 #define NU QS_NU
-#define MAXCON 96
+#define MAXCON 208 /* more than the collision stage can produce (48 geoms x 4 + slack): the oracle never truncates its contact set */
 #define MAXEFC (NV + 2 * QS_NJNT + MAXCON * 10)
 #define MINVAL 1e-15 /* [MJ] mjMINVAL */
 #define MINMU 1e-5   /* [MJ] mjMINMU  */
