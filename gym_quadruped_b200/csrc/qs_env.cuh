@@ -178,9 +178,12 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   }
   unsigned cm_acc = 0, im_acc = 0;  // per-lane share of the contact / invalid-contact body masks, collected when a contact is DETECTED
                                     // (before the NCON cap), so that termination stays exact even if the contact buffer overflows
-  QS_DEV void note_contact(int g) {
+  real pen_acc = 0;                 // per-lane share of max |dist| over the calf-body contacts, collected the same way: the reset lift
+                                    // loop raises the robot by 1.1 x this (quadruped_env.py:381-383), also when contacts were dropped
+  QS_DEV void note_contact(int g, real dist) {
     const int b = m.geom_body[g];
-    if (b >= 2 && (b - 2) % 3 == 2) cm_acc |= 1u << ((b - 2) / 3); else im_acc |= 1u << b;
+    if (b >= 2 && (b - 2) % 3 == 2) { cm_acc |= 1u << ((b - 2) / 3); pen_acc = N::max(pen_acc, N::abs(dist)); }
+    else im_acc |= 1u << b;
   }
   bool terrain_on = true;  // false: the base is out of reach of everything but the floor plane (internal frame re-centred like 'flat')
   bool calf_only = false;  // collision stage restricted to the calf-body geoms (the reset lift loop looks at nothing else)
@@ -881,7 +884,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       const unsigned mask = ballot(has);
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
-      if (has) note_contact(g);
+      if (has) note_contact(g, list[r].dist);
       if (has && slot < NCON) store_contact(slot, g, list[r].sign, list[r].dist, list[r].pos, list[r].nrm, is_caps ? yh : nullptr, list[r].wg);
       ncon += popc(mask);
     }
@@ -963,7 +966,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
           if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
         if (bi == 0x7fffffff || best > margin) continue;
-        note_contact(gm_);
+        note_contact(gm_, best);
         if (lane == 0 && ncon < NCON) {
           const Vert4<real> q = v[bi];
           const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
@@ -1015,7 +1018,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
           }
         }
         for (int r = 0; r < n; r++) {
-          note_contact(gm_);
+          note_contact(gm_, ld[r]);
           if (lane == 0 && ncon < NCON) {
             const Vert4<real> q = v[lv[r]];
             const real p[3] = {X[0] + R[0] * q.x + R[1] * q.y + R[2] * q.z, X[1] + R[3] * q.x + R[4] * q.y + R[5] * q.z, X[2] + R[6] * q.x + R[7] * q.y + R[8] * q.z};
@@ -1080,7 +1083,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   // floor plane z = 0 (scene_flat.xml:32) against every robot geom. [MJ] mjc_PlaneSphere/Capsule/Box/Convex
   QS_DEV void collide_floor() {
     int ncon = 0;
-    cm_acc = im_acc = 0;
+    cm_acc = im_acc = 0; pen_acc = 0;
     if (ttype() == 2 && terrain_on) find_near_boxes();
     // one lane per geom; robots with more than 32 collision geoms (go1: 42) take a second round
     if (FEAT & FEAT_NGEOM32) collide_round(0, ncon);
@@ -1174,7 +1177,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
       if (mask == 0) break;
       const int slot = ncon + popc(mask & ((1u << lane) - 1u));
       if (has) {
-        note_contact(g);
+        note_contact(g, cd[r]);
         if (slot < NCON) store_contact(slot, g, real(1), cd[r], cp[r], nrm, (m.geom_type[g] == GEOM_CAPSULE) ? yh : nullptr, WG_FLOOR);
       }
       ncon += popc(mask);
@@ -1221,7 +1224,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
                           w.kin.xpos[b][2] + R[6] * p.x + R[7] * p.y + R[8] * p.z};
       const real dist = pw[2];
       if (dist > margin) continue;
-      note_contact(gm_);
+      note_contact(gm_, dist);
       if (lane == 0 && ncon < NCON) {
         const real pos[3] = {pw[0], pw[1], pw[2] - real(0.5) * dist};
         store_contact(ncon, gm_, real(1), dist, pos, nrm, nullptr, WG_FLOOR);

@@ -476,14 +476,9 @@ __global__ void __launch_bounds__(LaunchCfg<real>::kMaxWarps * 32) env_kernel(co
           }
           continue;
         }
-        real pen = 0;
-        bool any = false;
-        for (int k = lane; k < w.ncon; k += 32) {
-          const int bdy = (w.c_info[k] >> 8) & 0xff;
-          if (bdy >= 2 && (bdy - 2) % 3 == 2) { any = true; pen = Num<real>::max(pen, Num<real>::abs(w.c_dist[k])); }
-        }
-        any = qs::ballot(any) != 0;
-        pen = warp_max(pen);
+        // calf-body contacts as DETECTED by the collision pass, not as stored: the 16-slot contact buffer may have dropped the deepest
+        const bool any = qs::ballot(e.cm_acc != 0) != 0;
+        const real pen = warp_max(e.pen_acc);
         if (!any) { cleared = true; lift_phase = 2; continue; }
         if (c == 100) { lift_phase = 2; continue; }
         if (lane == 0) w.qpos[2] += pen * real(1.1);
