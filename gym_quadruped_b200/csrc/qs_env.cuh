@@ -1084,6 +1084,7 @@ template <typename real, int NCON, int MAXDIM, int FEAT = 0> struct Env {
   QS_DEV void collide_floor() {
     int ncon = 0;
     cm_acc = im_acc = 0; pen_acc = 0;
+    near_overflow = false;  // a reset pass may land outside the terrain patch: nothing of the previous pass's box search carries over
     if (ttype() == 2 && terrain_on) find_near_boxes();
     // one lane per geom; robots with more than 32 collision geoms (go1: 42) take a second round
     if (FEAT & FEAT_NGEOM32) collide_round(0, ncon);
