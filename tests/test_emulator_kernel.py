@@ -360,3 +360,83 @@ def test_kernel_gather_rows_and_flags(stride):
         assert (others == -7.0).all()                                                # nobody else's rows touched
         assert flags[k].tolist() == [0, 5, 0, 0, 0, 0, 0, 0]
     assert np.array_equal(s.qpos, ref.qpos) and np.array_equal(s.terminated, ref.terminated)
+
+
+def _random_states(m, scene, n, rng, low=0.05):
+    q = np.tile(np.array(m.c.key_qpos), (n, 1))
+    q[:, 7:] += rng.uniform(-0.6, 0.6, (n, 12))
+    if scene != 'flat':
+        q[:, 0:2] = rng.uniform(-4, 4, (n, 2))
+    for i in range(n):
+        ax = rng.randn(3); ax /= np.linalg.norm(ax)
+        ang = rng.uniform(0, 0.5) if rng.rand() < 0.6 else rng.uniform(0, np.pi)
+        q[i, 3:7] = np.r_[np.cos(ang / 2), np.sin(ang / 2) * ax]
+    q[:, 2] = rng.uniform(low, 1.2 * m.hip_height + (0.7 if scene != 'flat' else 0.0), n)
+    return q, rng.uniform(-2, 2, (n, 18))
+
+
+ROBOTS = ['mini_cheetah', 'aliengo', 'go2', 'hyqreal1', 'hyqreal2', 'go1', 'b2', 'spot']
+
+
+def test_kernel_autoreset_fuzz_all_robots():
+    """Fused auto-reset == step + masked reset, bit for bit on every buffer, for random (often terminating) states of all eight robots
+    on four scenes, IMU noise on where the robot has one.  (720 further cases of the generator were run once: no difference.)"""
+    scenes = ['flat', 'random_boxes', 'perlin', 'stairs']
+    rng = np.random.RandomState(5)
+    nterm = 0
+    for it in range(32):
+        robot, scene = ROBOTS[it % 8], scenes[(it // 8) % 4]
+        m = Model(robot, scene)
+        n = 4
+        q, v = _random_states(m, scene, n, rng)
+        ctrl = (rng.randn(n, 12) * 30).astype(F32)
+        ro = reset_options(m, mode=CMD_FORWARD | CMD_ROTATE | CMD_RESET)
+        a, b = (EmuSim(m, n, precision=1, seed=it, use_imu=bool(m.c.has_imu)) for _ in range(2))
+        for s in (a, b):
+            s.set_state(q, v); s.friction[:] = 0.9; s.imu_noise = (0.05, 0.01, 0.002, 0.0005)
+        a.step_autoreset(ctrl, ro)
+        b.step(ctrl)
+        term = b.terminated.copy()
+        b.reset(ro, mask=term)
+        nterm += int(term.sum())
+        assert np.array_equal(a.terminated, term), (robot, scene)
+        for name in ('qpos', 'qvel', 'qacc', 'qacc_warmstart', 'base_pos64', 'command', 'friction', 'step_count', 'sim_time', 'episode', 'status',
+                     'cmd_count', 'cmd_limit', 'imu_bias', 'tick'):
+            assert np.array_equal(getattr(a, name), getattr(b, name), equal_nan=True), (robot, scene, name)
+        assert np.array_equal(a.obs[:, :227], b.obs[:, :227], equal_nan=True), (robot, scene)
+    assert nterm >= 30
+
+
+def test_kernel_step_fuzz_observation_rows_and_heightmap():
+    """Random states of all robots on all seven scenes, one kernel step each: the packed observation row, the termination flag and the
+    height-map columns against the oracle (fed with the fp32 state the kernel sees)."""
+    scenes = ['flat', 'random_boxes', 'perlin', 'stairs', 'ramp', 'random_pyramids', 'slippery']
+    rng = np.random.RandomState(0)
+    compared = 0
+    for it in range(36):
+        robot, scene = ROBOTS[rng.randint(8)], scenes[rng.randint(7)]
+        m = Model(robot, scene)
+        n = 3
+        q, v = _random_states(m, scene, n, rng, low=0.1)
+        ctrl = (rng.randn(n, 12) * 30).astype(F32)
+        hm = (3, 3, 0.1, 0.1) if scene != 'flat' else None
+        s = EmuSim(m, n, precision=1, heightmap=hm)
+        s.set_state(q, v); s.friction[:] = 0.8; s.command[:] = [0.4, 0.1, 0, 0.2]
+        orcs = []
+        for i in range(n):
+            o = Oracle(m)
+            o.set_state(np.r_[s.base_pos64[i], s.qpos[i, 3:].astype(float)], s.qvel[i].astype(float), np.zeros(18)); o.set_env(0.8, 0.8, [0.4, 0.1, 0, 0.2])
+            orcs.append(o)
+        s.step(ctrl)
+        for i, o in enumerate(orcs):
+            obs, term = o.step(ctrl[i].astype(float))
+            if o.flags()['ncon'] > 16 or not np.isfinite(obs).all():
+                continue
+            assert bool(s.terminated[i]) == term, (robot, scene, it, i)
+            rel = np.abs(s.obs[i, :227] - obs[:227]) / (1 + np.abs(obs[:227]))
+            assert rel.max() < 3e-5, (robot, scene, it, i, int(np.argmax(rel)), float(rel.max()))
+            if hm:
+                want = Oracle(m).heightmap(np.r_[s.base_pos64[i, :2], float(s.qpos[i, 2])], float(s.obs[i, 20]), 3, 3, 0.1, 0.1)
+                assert np.abs(s.obs[i, 227:].reshape(3, 3, 3) - want).max() < 5e-5, (robot, scene, it, i)
+            compared += 1
+    assert compared >= 60
